@@ -1,0 +1,100 @@
+"""Measurement inputs: the reference's test/ fixtures and the 1 GiB synthetic corpus.
+
+The reference's fixtures (/root/reference/test) are
+data, not source; they travel to the GPU box (where /root/reference does not
+exist) as one packed blob, tests/golden/fixtures.tar.xz, written by
+tests/golden/make_golden.py.  The synthetic corpus is SURVEY.md section 8(d)
+config 5: the six fixtures concatenated and repeated to the requested size, each
+repetition r >= 1 carrying len(base)/64 seeded single-byte mutations.
+"""
+from __future__ import annotations
+
+import io
+import os
+import tarfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PACK = os.path.join(ROOT, "tests", "golden", "fixtures.tar.xz")
+ORDER = ["laozi.txt", "confucius.txt", "x64.elf", "arm64.elf", "mandrill.bmp", "mandrill.png"]
+
+_cache: dict[str, np.ndarray] = {}
+
+
+def fixtures() -> dict[str, np.ndarray]:
+    """name -> uint8 array, in the section 8(d) order."""
+    if not _cache:
+        with tarfile.open(PACK, "r:xz") as tf:
+            for name in ORDER:
+                f = tf.extractfile(name)
+                _cache[name] = np.frombuffer(f.read(), dtype=np.uint8)
+    return dict(_cache)
+
+
+def base() -> np.ndarray:
+    fx = fixtures()
+    return np.concatenate([fx[n] for n in ORDER])
+
+
+def _splitmix64(state: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    """One splitmix64 step on a vector of states (uint64, wrapping)."""
+    with np.errstate(over="ignore"):
+        state = state + np.uint64(0x9E3779B97F4A7C15)
+        z = state.copy()
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return state, z
+
+
+def synthetic(nbytes: int, offset: int = 0) -> np.ndarray:
+    """Bytes [offset, offset+nbytes) of the endless synthetic stream.
+
+    Repetition r of the base occupies [r*B, (r+1)*B).  For r >= 1, B//64 draws k
+    come from counter-mode splitmix64 seeded 0x53515A00 + r: draw k uses output
+    z_k of state seed + (k+1)*golden; position = z_k % B, value = (z_k >> 40) & 0xFF.
+    Later draws overwrite earlier ones.  The stream is a pure function of the
+    absolute offset, so every rank can materialise its own shard plus halo.
+    """
+    b = base()
+    B = b.size
+    out = np.empty(nbytes, dtype=np.uint8)
+    r0, r1 = offset // B, (offset + nbytes - 1) // B if nbytes else offset // B
+    at = 0
+    for r in range(r0, r1 + 1):
+        rep = b
+        if r >= 1:
+            rep = b.copy()
+            m = B // 64
+            k = np.arange(1, m + 1, dtype=np.uint64)
+            with np.errstate(over="ignore"):
+                st = np.uint64(0x53515A00 + r) + k * np.uint64(0x9E3779B97F4A7C15)
+                st = st - np.uint64(0x9E3779B97F4A7C15)
+            _, z = _splitmix64(st)
+            pos = (z % np.uint64(B)).astype(np.int64)
+            val = ((z >> np.uint64(40)) & np.uint64(0xFF)).astype(np.uint8)
+            rep[pos] = val  # numpy keeps the last write for duplicate indices
+        lo = max(offset, r * B) - r * B
+        hi = min(offset + nbytes, (r + 1) * B) - r * B
+        out[at : at + hi - lo] = rep[lo:hi]
+        at += hi - lo
+    assert at == nbytes
+    return out
+
+
+def kat_inputs() -> dict[str, bytes]:
+    """The reference tests' own synthetic vectors (attic/map_experiment/test.c:166-173,
+    test.c:547, bst.c:316-339, shl.c:23-27)."""
+    return {
+        "zeros4096": bytes(4096),
+        "pat1234x1024": bytes([1, 2, 3, 4]) * 1024,
+        "hello": b"Hello World Hello.World Hello World",
+        "abc40": b"abcabcdabcdeabcdefabcdefgabcdefabcdeabcd",
+        "lorem3": b"Lorem ipsum dolor sit amet. " * 3,
+        "empty": b"",
+        "one": b"x",
+        "two": b"xy",
+        "aaa": b"aaa",
+        "aaaa": b"aaaa",
+    }
