@@ -1,0 +1,126 @@
+/* include/sqz.h -- host codec API of sqz-b200 (C99, callable from C and C++).
+ *
+ * Drop-in for the reference's Huffman + LZ77 codec
+ * (/root/reference/attic/map_experiment/squeeze.h:109-125,557-565, the
+ * `squeeze_interface squeeze` vtable; names follow the sqz_* spelling of
+ * /root/reference/shl/README.md:31-63).  Same bitstream, same header, same
+ * sticky-errno error model, caller-owned buffers.  The one thing that changed:
+ * sqz_compress() obtains the LZ77 token stream from the GPU
+ * (include/sqz_gpu.h: sqz_gpu_tokens) instead of running the brute-force loop
+ * of squeeze.h:338-358 on the CPU.  There is no CPU fallback for the search:
+ * without a CUDA device sqz_compress() sets s->error = ENODEV.
+ *
+ *   reference                                  this library
+ *   squeeze.write_header(bs, bytes, win_bits)  sqz_write_header   squeeze.h:255-265
+ *   squeeze.alloc(0) / init_with / free        sqz_init (caller-owned struct, no heap)
+ *   squeeze.compress(s, bs, data, bytes, win)  sqz_compress       squeeze.h:319-409
+ *   squeeze.read_header(bs, &bytes, &win_bits) sqz_read_header    squeeze.h:444-456
+ *   squeeze.decompress(s, bs, data, bytes)     sqz_decompress     squeeze.h:502-551
+ *   struct bitstream                           struct sqz_bitstream  bitstream.h:7-18
+ */
+#ifndef SQZ_H_INCLUDED
+#define SQZ_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    sqz_min_win_bits = 10,   /* squeeze.h:19 */
+    sqz_max_win_bits = 15,   /* squeeze.h:20 */
+    sqz_min_len      = 3,    /* squeeze.h:13 */
+    sqz_max_len      = 257,  /* squeeze.h:15 */
+    sqz_lit_symbols  = 512,  /* squeeze.h:204: 0..255 bytes, 257..284 lengths, 285 NYT */
+    sqz_pos_symbols  = 32,   /* squeeze.h:205: 0..29 distance buckets, 30 NYT */
+    sqz_lit_nyt      = 285,  /* squeeze.h:23 */
+    sqz_pos_nyt      = 30    /* squeeze.h:24 */
+};
+
+/* Bit sink / source.  Either memory mode {data, capacity} (words stored
+ * big-endian, bitstream.h:36-42) or callback mode {stream, output/input}: the
+ * callback moves the 8 bytes at &b64 in host byte order (bitstream.h:44-47,
+ * attic/map_experiment/test.c:39-42).  A memory-mode READER must set `bytes`
+ * to the number of valid bytes in `data` (bitstream.h:70-74).                */
+struct sqz_bitstream {
+    void*    stream;
+    uint8_t* data;
+    uint64_t capacity;
+    uint64_t bytes;     /* bytes written */
+    uint64_t read;      /* bytes read */
+    uint64_t b64;       /* shift register */
+    int32_t  bits;      /* bits held in b64 */
+    int32_t  error;     /* sticky errno */
+    int    (*output)(struct sqz_bitstream* bs);
+    int    (*input)(struct sqz_bitstream* bs);
+};
+
+struct sqz_node {       /* one adaptive-Huffman node, huffman.h:13-20 */
+    uint64_t freq;
+    uint64_t path;      /* code, emitted LSB first */
+    int32_t  bits;      /* code length; 0 = root or unseen leaf */
+    int32_t  up;        /* parent, -1 = none */
+    int32_t  lo;        /* left child  (bit 0) */
+    int32_t  hi;        /* right child (bit 1) */
+};
+
+struct sqz_tree {       /* huffman.h:22-34 */
+    struct sqz_node* node;
+    int32_t n;          /* leaves; nodes = 2n-1, root = 2n-2 */
+    int32_t next;       /* internal nodes are handed out downward from here */
+    int32_t depth;      /* high-water mark, reset by a root-level relabel */
+    int32_t complete;   /* frozen: no more frequency updates */
+};
+
+struct sqz {
+    int32_t error;      /* sticky errno: E2BIG, EINVAL, ENODEV, ENOMEM, EIO */
+    int32_t device;     /* CUDA device for the match search, default 0 */
+    struct sqz_bitstream* bs;
+    struct sqz_tree lit;
+    struct sqz_tree pos;
+    struct sqz_node lit_nodes[sqz_lit_symbols * 2 - 1];
+    struct sqz_node pos_nodes[sqz_pos_symbols * 2 - 1];
+    uint8_t len_index[sqz_max_len + 2]; /* len -> length bucket, squeeze.h:151-161 */
+    uint8_t pos_index[1u << 15];        /* dist -> distance bucket, squeeze.h:162-171 */
+    /* statistics of the last sqz_compress (zero until then) */
+    uint64_t tokens;
+    uint64_t matches;
+    double   search_seconds;            /* GPU search + parse + copies */
+    double   entropy_seconds;           /* host adaptive-Huffman stage */
+};
+
+/* 64 raw bits of `bytes` then 8 raw bits of `win_bits`, each LSB first.
+ * win_bits outside [10,15] sets bs->error = EINVAL.                          */
+void sqz_write_header(struct sqz_bitstream* bs, uint64_t bytes, uint8_t win_bits);
+void sqz_read_header(struct sqz_bitstream* bs, uint64_t* bytes, uint8_t* win_bits);
+
+/* Fresh state; must be called before every sqz_compress / sqz_decompress
+ * (a state is single use, like the reference's squeeze_type).               */
+void sqz_init(struct sqz* s);
+
+/* LZ77 (GPU) + adaptive Huffman (host).  window must be a power of two in
+ * [2^10, 2^15].  Errors are reported in s->error.                            */
+void sqz_compress(struct sqz* s, struct sqz_bitstream* bs,
+                  const uint8_t* data, uint64_t bytes, uint32_t window);
+
+/* The host half of sqz_compress alone: entropy-code an LZ77 token stream
+ * (token = literal byte, or (len << 16) | dist) exactly as
+ * squeeze.h:377-396 would.                                                  */
+void sqz_encode_tokens(struct sqz* s, struct sqz_bitstream* bs,
+                       const uint32_t* tokens, uint64_t count);
+
+void sqz_decompress(struct sqz* s, struct sqz_bitstream* bs,
+                    uint8_t* data, uint64_t bytes);
+
+/* Convenience: whole buffers, memory mode, header included.  Return errno. */
+int sqz_compress_buffer(const uint8_t* data, uint64_t bytes, uint8_t win_bits,
+                        uint8_t* out, uint64_t capacity, uint64_t* written);
+int sqz_decompress_buffer(const uint8_t* comp, uint64_t comp_bytes,
+                          uint8_t* out, uint64_t capacity, uint64_t* bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SQZ_H_INCLUDED */

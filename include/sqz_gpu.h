@@ -1,0 +1,128 @@
+/* include/sqz_gpu.h -- C-ABI of the B200 (sm_100a) LZ77 match search of sqz-b200.
+ *
+ * The reference (leok7v/sqz) has no FFI or plugin interface: its longest-match
+ * search is an inline loop inside squeeze_compress
+ * (/root/reference/attic/map_experiment/squeeze.h:338-358) followed by the
+ * greedy token dispatch (squeeze.h:377-394).  These entry points are what a
+ * maintainer would call at exactly that place: plain
+ * pointers and sizes, int errno return values, no global state visible to the
+ * caller, callable from C99.
+ *
+ * Rule parameters:
+ *   window    the LZ window the stream header announces (power of two)
+ *   min_len   shortest match worth a back-reference     (reference G1: 3)
+ *   max_len   longest match                              (reference G1: 257)
+ *   max_dist  farthest candidate                         (reference G1: window-1)
+ * For every position i the result is the candidate with the longest common
+ * prefix (capped by max_len and by bytes-i), the nearest one among equals --
+ * what the reference's "nearest first, strictly longer wins" scan selects.
+ *
+ * Token word (shared with sqz.h): literal = byte value (bits 31..16 zero);
+ * match = (len << 16) | dist.  A match-table word uses the same packing, with
+ * 0 meaning "no match of at least min_len here".
+ *
+ * Errors: 0, EINVAL (bad rule parameters), E2BIG (output capacity), ENOMEM,
+ * ENODEV (no CUDA device / driver: there is NO CPU fallback), EIO (CUDA error;
+ * sqz_gpu_last_error() has the text).
+ */
+#ifndef SQZ_GPU_H_INCLUDED
+#define SQZ_GPU_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SQZ_GPU_ABI_VERSION 1
+
+enum {
+    sqz_gpu_max_len_limit  = 512,     /* parse hand-off tables are sized for this */
+    sqz_gpu_max_dist_limit = 65535    /* distances are reported in 16 bits */
+};
+
+/* ---- host-buffer entry points (replace squeeze.h:338-358 / 377-394) ------ */
+
+/* Full match table: for every i in [0, bytes) len_out[i] in {0} U
+ * [min_len, max_len] and dist_out[i] in [1, max_dist] (0 when len is 0).
+ * Replaces the search loop squeeze.h:340-358 evaluated at every position.   */
+int sqz_gpu_match_table(const uint8_t* data, size_t bytes,
+                        uint32_t window, uint32_t min_len, uint32_t max_len,
+                        uint32_t max_dist,
+                        uint16_t* len_out, uint16_t* dist_out);
+
+/* Greedy token stream in parse order (squeeze.h:337,377-394): search + parse
+ * on the GPU, tokens copied to the caller.  *n_tokens receives the count even
+ * when it exceeds tokens_cap (then E2BIG is returned).                       */
+int sqz_gpu_tokens(const uint8_t* data, size_t bytes,
+                   uint32_t window, uint32_t min_len, uint32_t max_len,
+                   uint32_t max_dist,
+                   uint32_t* tokens_out, size_t tokens_cap, size_t* n_tokens);
+
+/* Streaming form used by sqz_compress(): tokens arrive chunk by chunk, in
+ * parse order, from double-buffered pinned memory while the device already
+ * works on the next chunk.  *tokens stays valid until the next call.        */
+typedef struct sqz_gpu_stream sqz_gpu_stream;
+int  sqz_gpu_stream_open(sqz_gpu_stream** st, int device,
+                         const uint8_t* data, size_t bytes,
+                         uint32_t window, uint32_t min_len, uint32_t max_len,
+                         uint32_t max_dist, size_t chunk_bytes /* 0 = default */);
+int  sqz_gpu_stream_next(sqz_gpu_stream* st, const uint32_t** tokens, size_t* count);
+void sqz_gpu_stream_close(sqz_gpu_stream* st);
+
+/* ---- device-buffer entry points (shards, benchmarks, multi-GPU) ---------- *
+ * A shard is `n` positions starting at d_shard, with `back` valid bytes
+ * before it (look-back halo, min(global offset, max_dist) is enough) and
+ * `ahead` valid bytes after it (look-ahead halo, min(bytes to the global end,
+ * max_len) is enough).  All pointers are device pointers on the current
+ * device; `stream` is a cudaStream_t (NULL = default stream).  Asynchronous. */
+
+/* table[i] for the n positions of the shard, packed (len << 16) | dist.     */
+int sqz_gpu_match_table_device(const uint8_t* d_shard, size_t back, size_t n,
+                               size_t ahead, uint32_t min_len, uint32_t max_len,
+                               uint32_t max_dist, uint32_t* d_table, void* stream);
+
+/* Split a packed table into the two 16-bit arrays of sqz_gpu_match_table.   */
+int sqz_gpu_unpack_table_device(const uint32_t* d_table, size_t n,
+                                uint16_t* d_len, uint16_t* d_dist, void* stream);
+
+/* Greedy parse of one shard.  `entry` is the offset of the first parse
+ * position inside the shard (0 for the first shard; otherwise the overshoot
+ * of the previous shard's last token).  d_work must hold
+ * sqz_gpu_parse_workspace(n) bytes.  After the stream is synchronised,
+ * h_result[0] = token count, h_result[1] = overshoot into the next shard
+ * (h_result: 2 x uint64 in pinned or pageable host memory, or device memory
+ * when result_on_device != 0).  Tokens beyond tokens_cap are not stored.     */
+size_t sqz_gpu_parse_workspace(size_t n);
+int sqz_gpu_parse_device(const uint8_t* d_shard, const uint32_t* d_table, size_t n,
+                         uint32_t entry, uint32_t min_len, uint32_t max_len,
+                         uint32_t* d_tokens, size_t tokens_cap,
+                         void* d_work, uint64_t* d_result /* 2 x u64, device */,
+                         void* stream);
+
+/* Seam hand-off without waiting for the previous shard: exit_map[e] is the
+ * overshoot this shard produces when entered at offset e, for every
+ * e < max_len.  d_exit_map: max_len x uint16 on the device.                  */
+int sqz_gpu_parse_exit_map_device(const uint32_t* d_table, size_t n,
+                                  uint32_t min_len, uint32_t max_len,
+                                  void* d_work, uint16_t* d_exit_map, void* stream);
+
+/* ---- utilities ----------------------------------------------------------- */
+int         sqz_gpu_abi_version(void);
+int         sqz_gpu_device_count(void);          /* 0 when no driver / device */
+const char* sqz_gpu_last_error(void);            /* thread-local text */
+void*       sqz_gpu_host_alloc(size_t bytes);    /* pinned host memory (NULL on failure) */
+void        sqz_gpu_host_free(void* p);
+/* kernels launched by this library in this process so far (for bench.py)    */
+uint64_t    sqz_gpu_launch_count(void);
+/* average device time of the match-table kernel over the launches since the
+ * last call with reset != 0, measured with CUDA events on the launching
+ * stream; enable with sqz_gpu_set_timing(1).  Seconds.                       */
+void        sqz_gpu_set_timing(int on);
+double      sqz_gpu_match_kernel_seconds(int reset, uint64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SQZ_GPU_H_INCLUDED */

@@ -1,0 +1,12 @@
+"""sqz_b200 -- B200-native LZ77 match search for the sqz codec (leok7v/sqz).
+
+Only the hot path of the reference lives here: the longest-match search and the
+greedy parse on the GPU (csrc/sqz_gpu.cu), the host entropy stage that consumes
+the token stream unchanged (csrc/sqz_codec.c), and this thin ctypes mirror of
+the reference's codec interface.  See DESIGN.md.
+"""
+from .api import (SqzError, compress, decompress, device_count, encode_tokens, launch_count,
+                  match_table, read_header, tokens)
+
+__all__ = ["SqzError", "compress", "decompress", "device_count", "encode_tokens", "launch_count",
+           "match_table", "read_header", "tokens"]

@@ -1,0 +1,172 @@
+"""Host-side mirror of the reference codec interface, over the C-ABI.
+
+The reference exposes one vtable, ``squeeze_interface squeeze``
+(/root/reference/attic/map_experiment/squeeze.h:109-125): write_header,
+compress, read_header, decompress.  ``compress`` / ``decompress`` below are the
+same operations on whole buffers (memory-mode bitstream, header included);
+``match_table`` / ``tokens`` expose the GPU half on its own
+(include/sqz_gpu.h).  Everything goes through libsqz_b200.so; nothing here
+computes a match on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import Bitstream, State, u8p, u16p, u32p
+
+G1_MIN_LEN, G1_MAX_LEN = 3, 257      # squeeze.h:13-15
+
+
+class SqzError(OSError):
+    pass
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = _lib.load().sqz_gpu_last_error() or b""
+        raise SqzError(rc, f"{what}: {os.strerror(rc)} ({msg.decode(errors='replace')})")
+
+
+def _u8(a) -> np.ndarray:
+    if isinstance(a, (bytes, bytearray, memoryview)):
+        a = np.frombuffer(a, dtype=np.uint8)
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def _rules(window: int, min_len: int, max_len: int, max_dist):
+    return window, min_len, max_len, (window - 1 if max_dist is None else max_dist)
+
+
+def device_count() -> int:
+    return int(_lib.load().sqz_gpu_device_count())
+
+
+def launch_count() -> int:
+    return int(_lib.load().sqz_gpu_launch_count())
+
+
+# ---- GPU half, host buffers (sqz_gpu_match_table / sqz_gpu_tokens) ----------
+
+def match_table(data, window: int = 1 << 15, min_len: int = G1_MIN_LEN, max_len: int = G1_MAX_LEN,
+                max_dist: int | None = None, out=None):
+    """(len[u16], dist[u16]) for every position: squeeze.h:340-358 at every i."""
+    L = _lib.load()
+    d = _u8(data)
+    w, lo, hi, md = _rules(window, min_len, max_len, max_dist)
+    if out is None:
+        ln = np.empty(d.size, dtype=np.uint16)
+        ds = np.empty(d.size, dtype=np.uint16)
+    else:
+        ln, ds = out
+    rc = L.sqz_gpu_match_table(d.ctypes.data_as(u8p), d.size, w, lo, hi, md,
+                               ln.ctypes.data_as(u16p), ds.ctypes.data_as(u16p))
+    _check(rc, "sqz_gpu_match_table")
+    return ln, ds
+
+
+def tokens(data, window: int = 1 << 15, min_len: int = G1_MIN_LEN, max_len: int = G1_MAX_LEN,
+           max_dist: int | None = None) -> np.ndarray:
+    """Greedy token stream (squeeze.h:337,377-394): literal byte or (len << 16) | dist."""
+    L = _lib.load()
+    d = _u8(data)
+    w, lo, hi, md = _rules(window, min_len, max_len, max_dist)
+    out = np.empty(max(d.size, 1), dtype=np.uint32)
+    n = C.c_size_t()
+    rc = L.sqz_gpu_tokens(d.ctypes.data_as(u8p), d.size, w, lo, hi, md,
+                          out.ctypes.data_as(u32p), out.size, C.byref(n))
+    _check(rc, "sqz_gpu_tokens")
+    return out[: n.value].copy()
+
+
+# ---- codec (sqz.h) ----------------------------------------------------------
+
+def _capacity(nbytes: int) -> int:
+    # worst case: every byte an escaped literal (NYT code + 9 raw bits), header, padding
+    return nbytes * 10 + 4096
+
+
+def compress(data, win_bits: int = 15, file_mode: bool = False, stats: dict | None = None) -> bytes:
+    """squeeze.write_header + squeeze.compress: GPU search, host entropy stage."""
+    L = _lib.load()
+    d = _u8(data)
+    out = np.empty(_capacity(d.size), dtype=np.uint8)
+    bs = Bitstream()
+    sink = {"at": 0}
+    if file_mode:
+        # callback mode: 8 bytes at &b64 in host byte order, like fwrite(&bs->b64, 8, 1, f)
+        def _out(pbs):
+            word = int(pbs.contents.b64)
+            out[sink["at"]: sink["at"] + 8] = np.frombuffer(word.to_bytes(8, "little"), dtype=np.uint8)
+            sink["at"] += 8
+            return 0
+        cb = _lib.OUTPUT_FN(_out)
+        bs.output = cb
+    else:
+        bs.data = out.ctypes.data_as(u8p)
+        bs.capacity = out.size
+    L.sqz_write_header(C.byref(bs), d.size, win_bits)
+    _check(bs.error, "sqz_write_header")
+    s = State()
+    L.sqz_init(C.byref(s))
+    L.sqz_compress(C.byref(s), C.byref(bs), d.ctypes.data_as(u8p), d.size, 1 << win_bits)
+    _check(s.error, "sqz_compress")
+    if stats is not None:
+        stats.update(tokens=int(s.tokens), matches=int(s.matches),
+                     search_seconds=float(s.search_seconds), entropy_seconds=float(s.entropy_seconds))
+    return out[: bs.bytes].tobytes()
+
+
+def encode_tokens(toks, nbytes: int, win_bits: int = 15, file_mode: bool = False) -> bytes:
+    """Host entropy stage alone (squeeze.h:278-315 + huffman.h + bitstream.h) on a token list."""
+    L = _lib.load()
+    t = np.ascontiguousarray(toks, dtype=np.uint32)
+    out = np.empty(_capacity(nbytes) + 64, dtype=np.uint8)
+    bs = Bitstream()
+    sink = {"at": 0}
+    if file_mode:
+        def _out(pbs):
+            word = int(pbs.contents.b64)
+            out[sink["at"]: sink["at"] + 8] = np.frombuffer(word.to_bytes(8, "little"), dtype=np.uint8)
+            sink["at"] += 8
+            return 0
+        cb = _lib.OUTPUT_FN(_out)
+        bs.output = cb
+    else:
+        bs.data = out.ctypes.data_as(u8p)
+        bs.capacity = out.size
+    L.sqz_write_header(C.byref(bs), nbytes, win_bits)
+    _check(bs.error, "sqz_write_header")
+    s = State()
+    L.sqz_init(C.byref(s))
+    L.sqz_encode_tokens(C.byref(s), C.byref(bs), t.ctypes.data_as(u32p), t.size)
+    _check(s.error, "sqz_encode_tokens")
+    return out[: bs.bytes].tobytes()
+
+
+def read_header(comp) -> tuple[int, int]:
+    L = _lib.load()
+    c = _u8(comp)
+    bs = Bitstream()
+    bs.data = c.ctypes.data_as(u8p)
+    bs.capacity = c.size
+    bs.bytes = c.size
+    n, wb = C.c_uint64(), C.c_uint8()
+    L.sqz_read_header(C.byref(bs), C.byref(n), C.byref(wb))
+    _check(bs.error, "sqz_read_header")
+    return int(n.value), int(wb.value)
+
+
+def decompress(comp) -> bytes:
+    """squeeze.read_header + squeeze.decompress (host only, never touches the GPU)."""
+    L = _lib.load()
+    c = _u8(comp)
+    n, _ = read_header(c)
+    out = np.empty(max(n, 1), dtype=np.uint8)
+    got = C.c_uint64()
+    rc = L.sqz_decompress_buffer(c.ctypes.data_as(u8p), c.size, out.ctypes.data_as(u8p), out.size, C.byref(got))
+    _check(rc, "sqz_decompress")
+    return out[: got.value].tobytes()

@@ -1,0 +1,860 @@
+// sqz_gpu.cu -- B200 (sm_100a) LZ77 longest-match search + greedy parse of
+// sqz-b200, and the C-ABI declared in include/sqz_gpu.h.
+//
+// What it replaces in the reference (leok7v/sqz, generation G1):
+//   /root/reference/attic/map_experiment/squeeze.h:338-358  brute-force search
+//   /root/reference/attic/map_experiment/squeeze.h:337,377-394  greedy parse
+// Results are bit-exact: for every position the longest common prefix with a
+// candidate at distance 1..max_dist (capped by max_len and the end of data),
+// the nearest candidate among equals; then the orbit of position 0 under
+// next[i] = i + (len[i] >= min_len ? len[i] : 1) as the token stream.
+//
+// There is no CPU fallback in this file: without a device every entry point
+// returns ENODEV.
+#include "sqz_gpu.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cerrno>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+static thread_local char g_err[256] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const char* what, cudaError_t ce = cudaSuccess) {
+    if (ce != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(ce));
+    } else {
+        snprintf(g_err, sizeof(g_err), "%s", what);
+    }
+    return code;
+}
+
+static int cuda_code(cudaError_t ce) {
+    switch (ce) {
+        case cudaErrorMemoryAllocation: return ENOMEM;
+        case cudaErrorNoDevice:
+        case cudaErrorInsufficientDriver:
+        case cudaErrorInvalidDevice: return ENODEV;
+        default: return EIO;
+    }
+}
+
+#define CU(call)                                                         \
+    do {                                                                 \
+        cudaError_t ce_ = (call);                                        \
+        if (ce_ != cudaSuccess) { return fail(cuda_code(ce_), #call, ce_); } \
+    } while (0)
+
+#define LAUNCHED(name)                                                   \
+    do {                                                                 \
+        g_launches.fetch_add(1, std::memory_order_relaxed);              \
+        cudaError_t ce_ = cudaGetLastError();                            \
+        if (ce_ != cudaSuccess) { return fail(cuda_code(ce_), name, ce_); } \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// kernel 1: match table, one position per thread, window staged in shared
+// memory.  (First correct path; the tuned kernel replaces it behind the same
+// launcher.)
+//
+// Shared-memory image: bytes [lo, hi) of the shard, where lo reaches back
+// max_dist bytes before the tile and hi runs max_len bytes past it, shifted so
+// that 16-byte global chunks land on 16-byte shared chunks.
+//
+// Scan order and acceptance are the reference's: distance 1 first, a candidate
+// replaces the best only when strictly longer.  The filter that keeps the scan
+// cheap is exact: to beat `best` a candidate must agree on the bytes
+// [need-4, need) with need = max(best+1, min_len) (or on the first `need`
+// bytes while need < 4); only candidates that pass are measured in full.
+// ---------------------------------------------------------------------------
+namespace v1 {
+
+constexpr int kThreads = 512;
+
+__device__ __forceinline__ uint32_t load_u32_unaligned(const uint8_t* S, int x) {
+    const uint32_t* W = reinterpret_cast<const uint32_t*>(S);
+    const int w = x >> 2;
+    const uint32_t lo = W[w], hi = W[w + 1];
+    return __funnelshift_r(lo, hi, (x & 3) * 8);
+}
+
+__global__ void __launch_bounds__(kThreads)
+match_table(const uint8_t* __restrict__ shard, long long back, long long n,
+            long long ahead, uint32_t min_len, uint32_t max_len,
+            uint32_t max_dist, uint32_t* __restrict__ table) {
+    extern __shared__ __align__(16) uint8_t S[];
+    const long long tile0 = (long long)blockIdx.x * kThreads;
+    const long long behind = min((long long)max_dist, tile0 + back);
+    const long long lo = tile0 - behind;                        // first byte staged (shard-relative)
+    const long long hi = min(tile0 + kThreads + (long long)max_len, n + ahead);
+    const uint8_t* g = shard + lo;
+    const int a = (int)(reinterpret_cast<uintptr_t>(g) & 15);   // S[a] holds byte `lo`
+    const int span = a + (int)(hi - lo);                        // bytes of S in use
+    const int chunks = (span + 8 + 15) >> 4;                    // + zero padding for word reads
+    for (int c = threadIdx.x; c < chunks; c += kThreads) {
+        const int s0 = c << 4;
+        uint4 v;
+        if (s0 >= a && s0 + 16 <= span) {
+            v = __ldg(reinterpret_cast<const uint4*>(g - a + s0));
+        } else {
+            uint8_t b[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const int s = s0 + k;
+                b[k] = (s >= a && s < span) ? __ldg(g - a + s) : (uint8_t)0;
+            }
+            memcpy(&v, b, 16);
+        }
+        reinterpret_cast<uint4*>(S)[c] = v;
+    }
+    __syncthreads();
+
+    const long long p = tile0 + threadIdx.x;
+    if (p >= n) { return; }
+    const int xi = a + (int)(p - lo);                           // S index of position p
+    const uint32_t room = (uint32_t)min((long long)max_len, n + ahead - p);
+    const uint32_t reach = (uint32_t)min((long long)max_dist, p + back);
+    const uint32_t* W = reinterpret_cast<const uint32_t*>(S);
+
+    uint32_t best = 0, bdist = 0;
+    uint32_t d = 1;
+    while (d <= reach) {
+        const uint32_t need = max(best + 1, min_len);
+        if (need > room) { break; }
+        const uint32_t o = need >= 4 ? need - 4 : 0;
+        const uint32_t mask = need >= 4 ? 0xFFFFFFFFu : (0xFFFFFFFFu >> (8 * (4 - need)));
+        const uint32_t key = load_u32_unaligned(S, xi + (int)o) & mask;
+        int c = xi + (int)o - (int)d;                           // candidate word starts here
+        const int c_end = xi + (int)o - (int)reach;             // farthest candidate
+        int w = c >> 2;
+        uint32_t hiw = W[w + 1], low = W[w];
+        int kmax = c & 3;
+        int found = -1;
+        for (;;) {
+            const uint32_t t3 = (__byte_perm(low, hiw, 0x6543) ^ key) & mask;
+            const uint32_t t2 = (__byte_perm(low, hiw, 0x5432) ^ key) & mask;
+            const uint32_t t1 = (__byte_perm(low, hiw, 0x4321) ^ key) & mask;
+            const uint32_t t0 = (low ^ key) & mask;
+            if (min(min(t0, t1), min(t2, t3)) == 0) {
+                uint32_t hb = (t0 == 0 ? 1u : 0u) | (t1 == 0 ? 2u : 0u) |
+                              (t2 == 0 ? 4u : 0u) | (t3 == 0 ? 8u : 0u);
+                const int kmin = max(0, c_end - (w << 2));
+                hb &= (2u << kmax) - 1u;
+                hb &= ~((1u << kmin) - 1u);
+                if (hb != 0) { found = (w << 2) + (31 - __clz(hb)); break; }
+            }
+            w--;
+            if ((w << 2) + 3 < c_end) { break; }
+            hiw = low;
+            low = W[w];
+            kmax = 3;
+        }
+        if (found < 0) { break; }
+        const uint32_t dh = (uint32_t)(xi + (int)o - found);
+        const uint8_t* A = S + xi;
+        const uint8_t* B = S + xi - (int)dh;
+        uint32_t m = 0;
+        while (m < room && A[m] == B[m]) { m++; }
+        if (m >= need) {
+            best = m;
+            bdist = dh;
+            if (best >= room) { break; }
+        }
+        d = dh + 1;
+    }
+    table[p] = best >= min_len ? ((best << 16) | bdist) : 0u;
+}
+
+static size_t smem_bytes(uint32_t max_len, uint32_t max_dist) {
+    size_t b = 16 + (size_t)max_dist + kThreads + max_len + 16 + 16;
+    return (b + 15) & ~(size_t)15;
+}
+
+}  // namespace v1
+
+// ---------------------------------------------------------------------------
+// kernel 2: split packed table words into the two u16 arrays of the host ABI
+// ---------------------------------------------------------------------------
+__global__ void unpack_table(const uint32_t* __restrict__ table, size_t n,
+                             uint16_t* __restrict__ len, uint16_t* __restrict__ dist) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const uint32_t w = table[i];
+        len[i] = (uint16_t)(w >> 16);
+        dist[i] = (uint16_t)(w & 0xFFFF);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// greedy parse (squeeze.h:337,377-394) as block-wise pointer jumping.
+//
+// The shard is cut into parse blocks of kPB positions.  A token never jumps
+// more than max_len, so a block can only be entered at an offset < max_len
+// ("entry") and leaves with an overshoot < max_len into the next block.
+//   parse_exit_map   per block: overshoot for every possible entry, by pointer
+//                    doubling over next[] in shared memory
+//   chain_groups     compose the maps of kGroup consecutive blocks
+//   chain_top        serial walk over the groups -> entry of every group,
+//                    overshoot of the whole shard
+//   chain_expand     entry of every block
+//   parse_count      per block: number of tokens on the real path
+//   scan_counts      exclusive prefix sum -> output offsets, total
+//   parse_emit       per block: write the tokens
+// ---------------------------------------------------------------------------
+namespace parse {
+
+constexpr int kPB = 4096;        // positions per parse block
+constexpr int kMapStride = 512;  // = sqz_gpu_max_len_limit entries per exit map
+constexpr int kGroup = 128;      // blocks per chain group
+
+struct Work {                    // carved out of the caller's d_work
+    uint16_t* exit_map;          // [blocks][kMapStride]
+    uint16_t* group_map;         // [groups][kMapStride]
+    uint32_t* group_entry;       // [groups + 1]
+    uint32_t* block_entry;       // [blocks]
+    uint32_t* count;             // [blocks]
+    uint64_t* offset;            // [blocks]
+    size_t blocks, groups;
+};
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static size_t workspace(size_t n) {
+    const size_t blocks = (n + kPB - 1) / kPB + 1;
+    const size_t groups = (blocks + kGroup - 1) / kGroup + 1;
+    return align_up(blocks * kMapStride * 2) + align_up(groups * kMapStride * 2) +
+           align_up((groups + 1) * 4) + align_up(blocks * 4) + align_up(blocks * 4) +
+           align_up(blocks * 8) + 256;
+}
+
+static Work carve(void* d_work, size_t n) {
+    Work w;
+    w.blocks = (n + kPB - 1) / kPB;
+    w.groups = (w.blocks + kGroup - 1) / kGroup;
+    const size_t blocks = w.blocks + 1, groups = w.groups + 1;
+    uint8_t* p = (uint8_t*)d_work;
+    p = (uint8_t*)(((uintptr_t)p + 255) & ~(uintptr_t)255);
+    w.exit_map = (uint16_t*)p;    p += align_up(blocks * kMapStride * 2);
+    w.group_map = (uint16_t*)p;   p += align_up(groups * kMapStride * 2);
+    w.group_entry = (uint32_t*)p; p += align_up((groups + 1) * 4);
+    w.block_entry = (uint32_t*)p; p += align_up(blocks * 4);
+    w.count = (uint32_t*)p;       p += align_up(blocks * 4);
+    w.offset = (uint64_t*)p;
+    return w;
+}
+
+__device__ __forceinline__ uint32_t step_of(uint32_t word, uint32_t min_len) {
+    const uint32_t len = word >> 16;
+    return len >= min_len ? len : 1u;
+}
+
+__global__ void __launch_bounds__(256)
+parse_exit_map(const uint32_t* __restrict__ table, size_t n, uint32_t min_len,
+               uint32_t max_len, uint16_t* __restrict__ exit_map) {
+    __shared__ uint16_t jump[kPB];
+    const size_t b0 = (size_t)blockIdx.x * kPB;
+    const int size = (int)min((size_t)kPB, n - b0);            // positions in this block
+    for (int p = threadIdx.x; p < size; p += blockDim.x) {
+        jump[p] = (uint16_t)(p + step_of(table[b0 + p], min_len));
+    }
+    __syncthreads();
+    // asynchronous pointer doubling: every value stored is a point on p's own
+    // path, so reading a neighbour's half-updated entry is still correct
+    for (;;) {
+        int changed = 0;
+        for (int p = threadIdx.x; p < size; p += blockDim.x) {
+            const int j = jump[p];
+            if (j < size) {
+                jump[p] = jump[j];
+                changed = 1;
+            }
+        }
+        if (!__syncthreads_or(changed)) { break; }
+    }
+    uint16_t* out = exit_map + (size_t)blockIdx.x * kMapStride;
+    for (int e = threadIdx.x; e < (int)max_len; e += blockDim.x) {
+        out[e] = (uint16_t)(e < size ? jump[e] - size : e - size);
+    }
+}
+
+__global__ void chain_groups(const uint16_t* __restrict__ exit_map, size_t blocks,
+                             uint32_t max_len, uint16_t* __restrict__ group_map) {
+    const size_t g = blockIdx.x;
+    const size_t first = g * kGroup;
+    const size_t last = min(first + kGroup, blocks);
+    for (uint32_t e = threadIdx.x; e < max_len; e += blockDim.x) {
+        uint32_t x = e;
+        for (size_t b = first; b < last; b++) { x = exit_map[b * kMapStride + x]; }
+        group_map[g * kMapStride + e] = (uint16_t)x;
+    }
+}
+
+// one thread: entries of all groups, then the shard's overshoot and (later,
+// from scan_counts) the token total
+__global__ void chain_top(const uint16_t* __restrict__ group_map, size_t groups,
+                          const uint32_t* __restrict__ entry_in, uint32_t entry_imm,
+                          uint32_t* __restrict__ group_entry, uint64_t* __restrict__ result) {
+    uint32_t x = entry_in != nullptr ? *entry_in : entry_imm;
+    for (size_t g = 0; g < groups; g++) {
+        group_entry[g] = x;
+        x = group_map[g * kMapStride + x];
+    }
+    group_entry[groups] = x;
+    result[1] = x;
+}
+
+// composed map of the whole shard, for seam hand-off between GPUs
+__global__ void chain_total(const uint16_t* __restrict__ group_map, size_t groups,
+                            uint32_t max_len, uint16_t* __restrict__ out) {
+    for (uint32_t e = threadIdx.x; e < max_len; e += blockDim.x) {
+        uint32_t x = e;
+        for (size_t g = 0; g < groups; g++) { x = group_map[g * kMapStride + x]; }
+        out[e] = (uint16_t)x;
+    }
+}
+
+__global__ void chain_expand(const uint16_t* __restrict__ exit_map, size_t blocks,
+                             size_t groups, const uint32_t* __restrict__ group_entry,
+                             uint32_t* __restrict__ block_entry) {
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= groups) { return; }
+    const size_t first = g * kGroup;
+    const size_t last = min(first + kGroup, blocks);
+    uint32_t x = group_entry[g];
+    for (size_t b = first; b < last; b++) {
+        block_entry[b] = x;
+        x = exit_map[b * kMapStride + x];
+    }
+}
+
+__global__ void parse_count(const uint32_t* __restrict__ table, size_t n, size_t blocks,
+                            uint32_t min_len, const uint32_t* __restrict__ block_entry,
+                            uint32_t* __restrict__ count) {
+    const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= blocks) { return; }
+    const size_t b0 = b * kPB;
+    const size_t end = min(b0 + kPB, n);
+    size_t p = b0 + block_entry[b];
+    uint32_t c = 0;
+    while (p < end) {
+        p += step_of(table[p], min_len);
+        c++;
+    }
+    count[b] = c;
+}
+
+__global__ void __launch_bounds__(1024)
+scan_counts(const uint32_t* __restrict__ count, size_t blocks,
+            uint64_t* __restrict__ offset, uint64_t* __restrict__ result) {
+    __shared__ uint64_t warp_sum[32];
+    __shared__ uint64_t carry_s;
+    if (threadIdx.x == 0) { carry_s = 0; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (size_t base = 0; base < blocks; base += 1024) {
+        const size_t i = base + threadIdx.x;
+        const uint64_t v = i < blocks ? count[i] : 0;
+        uint64_t s = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t t = __shfl_up_sync(0xFFFFFFFFu, s, d);
+            if (lane >= d) { s += t; }
+        }
+        if (lane == 31) { warp_sum[wid] = s; }
+        __syncthreads();
+        if (wid == 0) {
+            uint64_t ws = warp_sum[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint64_t t = __shfl_up_sync(0xFFFFFFFFu, ws, d);
+                if (lane >= d) { ws += t; }
+            }
+            warp_sum[lane] = ws;
+        }
+        __syncthreads();
+        const uint64_t carry = carry_s;
+        const uint64_t before = carry + (wid > 0 ? warp_sum[wid - 1] : 0) + s - v;
+        if (i < blocks) { offset[i] = before; }
+        __syncthreads();
+        if (threadIdx.x == 1023) { carry_s = before + v; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { result[0] = carry_s; }
+}
+
+__global__ void parse_emit(const uint8_t* __restrict__ shard,
+                           const uint32_t* __restrict__ table, size_t n, size_t blocks,
+                           uint32_t min_len, const uint32_t* __restrict__ block_entry,
+                           const uint64_t* __restrict__ offset,
+                           uint32_t* __restrict__ tokens, size_t cap) {
+    const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= blocks) { return; }
+    const size_t b0 = b * kPB;
+    const size_t end = min(b0 + kPB, n);
+    size_t p = b0 + block_entry[b];
+    uint64_t k = offset[b];
+    while (p < end) {
+        const uint32_t w = table[p];
+        const uint32_t len = w >> 16;
+        uint32_t t, step;
+        if (len >= min_len) { t = w; step = len; }
+        else                { t = shard[p]; step = 1; }
+        if (k < cap) { tokens[k] = t; }
+        k++;
+        p += step;
+    }
+}
+
+}  // namespace parse
+
+// ---------------------------------------------------------------------------
+// launchers (device-buffer ABI)
+// ---------------------------------------------------------------------------
+static int check_rules(uint32_t min_len, uint32_t max_len, uint32_t max_dist) {
+    if (min_len < 1 || max_len < min_len || max_len > sqz_gpu_max_len_limit ||
+        max_dist < 1 || max_dist > sqz_gpu_max_dist_limit) {
+        return fail(EINVAL, "rule parameters out of range (1 <= min_len <= max_len <= 512, 1 <= max_dist <= 65535)");
+    }
+    return 0;
+}
+
+// --- optional CUDA-event timing of the match kernel (bench.py roofline leg) ---
+static std::mutex g_time_mu;
+static bool g_timing = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_pending;
+static double g_match_seconds = 0;
+static uint64_t g_match_launches = 0;
+
+static void timing_drain_locked() {
+    for (auto& pr : g_pending) {
+        float ms = 0;
+        if (cudaEventSynchronize(pr.second) == cudaSuccess &&
+            cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+            g_match_seconds += 1e-3 * (double)ms;
+            g_match_launches++;
+        }
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    g_pending.clear();
+}
+
+extern "C" void sqz_gpu_set_timing(int on) {
+    std::lock_guard<std::mutex> lk(g_time_mu);
+    g_timing = on != 0;
+}
+
+extern "C" double sqz_gpu_match_kernel_seconds(int reset, uint64_t* launches) {
+    std::lock_guard<std::mutex> lk(g_time_mu);
+    timing_drain_locked();
+    const double avg = g_match_launches ? g_match_seconds / (double)g_match_launches : 0.0;
+    if (launches != nullptr) { *launches = g_match_launches; }
+    if (reset) { g_match_seconds = 0; g_match_launches = 0; }
+    return avg;
+}
+
+extern "C" int sqz_gpu_match_table_device(const uint8_t* d_shard, size_t back, size_t n,
+                                          size_t ahead, uint32_t min_len, uint32_t max_len,
+                                          uint32_t max_dist, uint32_t* d_table, void* stream) {
+    if (int r = check_rules(min_len, max_len, max_dist)) { return r; }
+    if (n == 0) { return 0; }
+    cudaStream_t s = (cudaStream_t)stream;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(v1::match_table, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)v1::smem_bytes(sqz_gpu_max_len_limit, sqz_gpu_max_dist_limit));
+    });
+    if (attr_err != cudaSuccess) { return fail(cuda_code(attr_err), "cudaFuncSetAttribute", attr_err); }
+    const size_t tiles = (n + v1::kThreads - 1) / v1::kThreads;
+    if (tiles > 0x7FFFFFFFull) { return fail(EINVAL, "shard too large for one launch"); }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    bool timed = false;
+    {
+        std::lock_guard<std::mutex> lk(g_time_mu);
+        timed = g_timing;
+        if (timed && g_pending.size() > 4096) { timing_drain_locked(); }
+    }
+    if (timed) {
+        CU(cudaEventCreate(&e0));
+        CU(cudaEventCreate(&e1));
+        CU(cudaEventRecord(e0, s));
+    }
+    v1::match_table<<<(unsigned)tiles, v1::kThreads, v1::smem_bytes(max_len, max_dist), s>>>(
+        d_shard, (long long)back, (long long)n, (long long)ahead, min_len, max_len, max_dist, d_table);
+    LAUNCHED("match_table");
+    if (timed) {
+        CU(cudaEventRecord(e1, s));
+        std::lock_guard<std::mutex> lk(g_time_mu);
+        g_pending.emplace_back(e0, e1);
+    }
+    return 0;
+}
+
+extern "C" int sqz_gpu_unpack_table_device(const uint32_t* d_table, size_t n,
+                                           uint16_t* d_len, uint16_t* d_dist, void* stream) {
+    if (n == 0) { return 0; }
+    const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 16);
+    unpack_table<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_table, n, d_len, d_dist);
+    LAUNCHED("unpack_table");
+    return 0;
+}
+
+extern "C" size_t sqz_gpu_parse_workspace(size_t n) { return parse::workspace(n); }
+
+static int parse_maps(const uint32_t* d_table, size_t n, uint32_t min_len, uint32_t max_len,
+                      const parse::Work& w, cudaStream_t s) {
+    parse::parse_exit_map<<<(unsigned)w.blocks, 256, 0, s>>>(d_table, n, min_len, max_len, w.exit_map);
+    LAUNCHED("parse_exit_map");
+    parse::chain_groups<<<(unsigned)w.groups, 256, 0, s>>>(w.exit_map, w.blocks, max_len, w.group_map);
+    LAUNCHED("chain_groups");
+    return 0;
+}
+
+// entry either from device memory (d_entry != null) or immediate
+static int parse_launch(const uint8_t* d_shard, const uint32_t* d_table, size_t n,
+                        const uint32_t* d_entry, uint32_t entry, uint32_t min_len,
+                        uint32_t max_len, uint32_t* d_tokens, size_t cap, void* d_work,
+                        uint64_t* d_result, cudaStream_t s) {
+    if (n == 0) {
+        // nothing to parse: count 0, overshoot = entry
+        CU(cudaMemsetAsync(d_result, 0, 16, s));
+        if (d_entry != nullptr) {
+            CU(cudaMemcpyAsync(d_result + 1, d_entry, 4, cudaMemcpyDeviceToDevice, s));
+        } else if (entry != 0) {
+            return fail(EINVAL, "entry into an empty shard");
+        }
+        return 0;
+    }
+    parse::Work w = parse::carve(d_work, n);
+    if (w.blocks > 0x7FFFFFFFull) { return fail(EINVAL, "shard too large for one launch"); }
+    if (int r = parse_maps(d_table, n, min_len, max_len, w, s)) { return r; }
+    parse::chain_top<<<1, 1, 0, s>>>(w.group_map, w.groups, d_entry, entry, w.group_entry, d_result);
+    LAUNCHED("chain_top");
+    parse::chain_expand<<<(unsigned)((w.groups + 127) / 128), 128, 0, s>>>(
+        w.exit_map, w.blocks, w.groups, w.group_entry, w.block_entry);
+    LAUNCHED("chain_expand");
+    const unsigned wb = (unsigned)((w.blocks + 63) / 64);
+    parse::parse_count<<<wb, 64, 0, s>>>(d_table, n, w.blocks, min_len, w.block_entry, w.count);
+    LAUNCHED("parse_count");
+    parse::scan_counts<<<1, 1024, 0, s>>>(w.count, w.blocks, w.offset, d_result);
+    LAUNCHED("scan_counts");
+    parse::parse_emit<<<wb, 64, 0, s>>>(d_shard, d_table, n, w.blocks, min_len, w.block_entry,
+                                        w.offset, d_tokens, cap);
+    LAUNCHED("parse_emit");
+    return 0;
+}
+
+extern "C" int sqz_gpu_parse_device(const uint8_t* d_shard, const uint32_t* d_table, size_t n,
+                                    uint32_t entry, uint32_t min_len, uint32_t max_len,
+                                    uint32_t* d_tokens, size_t tokens_cap, void* d_work,
+                                    uint64_t* d_result, void* stream) {
+    if (int r = check_rules(min_len, max_len, 1)) { return r; }
+    if (entry >= max_len) { return fail(EINVAL, "entry must be < max_len"); }
+    return parse_launch(d_shard, d_table, n, nullptr, entry, min_len, max_len, d_tokens,
+                        tokens_cap, d_work, d_result, (cudaStream_t)stream);
+}
+
+extern "C" int sqz_gpu_parse_exit_map_device(const uint32_t* d_table, size_t n,
+                                             uint32_t min_len, uint32_t max_len, void* d_work,
+                                             uint16_t* d_exit_map, void* stream) {
+    if (int r = check_rules(min_len, max_len, 1)) { return r; }
+    if (n == 0) { return fail(EINVAL, "empty shard"); }
+    cudaStream_t s = (cudaStream_t)stream;
+    parse::Work w = parse::carve(d_work, n);
+    if (int r = parse_maps(d_table, n, min_len, max_len, w, s)) { return r; }
+    parse::chain_total<<<1, 512, 0, s>>>(w.group_map, w.groups, max_len, d_exit_map);
+    LAUNCHED("chain_total");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// host-buffer ABI: chunked, double-buffered pipeline
+// ---------------------------------------------------------------------------
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;       // everything of the chunk has been issued and finished
+    uint8_t* d_data = nullptr;        // back halo + chunk + ahead halo
+    uint32_t* d_table = nullptr;
+    uint32_t* d_tokens = nullptr;
+    uint16_t* d_len = nullptr;        // table mode only
+    uint16_t* d_dist = nullptr;
+    void* d_work = nullptr;
+    uint64_t* d_result = nullptr;     // [0] tokens, [1] overshoot (next chunk's entry)
+    uint64_t* h_result = nullptr;     // pinned
+    uint32_t* h_tokens = nullptr;     // pinned
+    size_t first = 0, n = 0;          // chunk = [first, first + n) of the input
+    bool busy = false;
+};
+
+struct sqz_gpu_stream {
+    int device = 0;
+    const uint8_t* data = nullptr;
+    size_t bytes = 0;
+    uint32_t min_len = 0, max_len = 0, max_dist = 0;
+    size_t chunk = 0;
+    size_t launched = 0;              // input bytes handed to the device so far
+    size_t delivered = 0;             // input bytes whose tokens were returned
+    int next_slot = 0, read_slot = 0;
+    bool want_tokens = true;
+    Slot slot[2];
+    const uint64_t* prev_result = nullptr;   // device: previous chunk's result (entry hand-off)
+    cudaEvent_t prev_parsed = nullptr;
+};
+
+static void slot_free(Slot& s) {
+    if (s.stream) { cudaStreamSynchronize(s.stream); }
+    cudaFree(s.d_data); cudaFree(s.d_table); cudaFree(s.d_tokens); cudaFree(s.d_len);
+    cudaFree(s.d_dist); cudaFree(s.d_work); cudaFree(s.d_result);
+    cudaFreeHost(s.h_result); cudaFreeHost(s.h_tokens);
+    if (s.done) { cudaEventDestroy(s.done); }
+    if (s.stream) { cudaStreamDestroy(s.stream); }
+    s = Slot();
+}
+
+static int slot_alloc(Slot& s, size_t chunk, uint32_t max_len, uint32_t max_dist, bool tokens) {
+    CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    CU(cudaMalloc(&s.d_data, (size_t)max_dist + chunk + max_len + 64));
+    CU(cudaMalloc(&s.d_table, chunk * 4));
+    CU(cudaMalloc(&s.d_result, 16));
+    CU(cudaHostAlloc(&s.h_result, 16, cudaHostAllocDefault));
+    if (tokens) {
+        CU(cudaMalloc(&s.d_tokens, chunk * 4));
+        CU(cudaMalloc(&s.d_work, parse::workspace(chunk)));
+        CU(cudaHostAlloc(&s.h_tokens, chunk * 4, cudaHostAllocDefault));
+    } else {
+        CU(cudaMalloc(&s.d_len, chunk * 2));
+        CU(cudaMalloc(&s.d_dist, chunk * 2));
+    }
+    return 0;
+}
+
+static int ensure_device(int device) {
+    int count = 0;
+    cudaError_t ce = cudaGetDeviceCount(&count);
+    if (ce != cudaSuccess || count == 0) {
+        return fail(ENODEV, "no CUDA device: the match search has no CPU fallback", ce);
+    }
+    if (device < 0 || device >= count) { return fail(ENODEV, "no such CUDA device"); }
+    CU(cudaSetDevice(device));
+    return 0;
+}
+
+// issue everything for the next chunk on its slot; returns without waiting
+static int stream_launch_next(sqz_gpu_stream* st, uint16_t* len_out, uint16_t* dist_out) {
+    Slot& s = st->slot[st->next_slot];
+    const size_t first = st->launched;
+    const size_t n = std::min(st->chunk, st->bytes - first);
+    const size_t back = std::min<size_t>(first, st->max_dist);
+    const size_t ahead = std::min<size_t>(st->bytes - (first + n), st->max_len);
+    s.first = first;
+    s.n = n;
+    CU(cudaMemcpyAsync(s.d_data, st->data + first - back, back + n + ahead,
+                       cudaMemcpyHostToDevice, s.stream));
+    const uint8_t* d_shard = s.d_data + back;
+    if (int r = sqz_gpu_match_table_device(d_shard, back, n, ahead, st->min_len, st->max_len,
+                                           st->max_dist, s.d_table, s.stream)) { return r; }
+    if (st->want_tokens) {
+        const uint32_t* d_entry = nullptr;
+        if (st->prev_result != nullptr) {
+            CU(cudaStreamWaitEvent(s.stream, st->prev_parsed, 0));
+            d_entry = reinterpret_cast<const uint32_t*>(st->prev_result + 1);  // low half of overshoot
+        }
+        if (int r = parse_launch(d_shard, s.d_table, n, d_entry, 0, st->min_len, st->max_len,
+                                 s.d_tokens, n, s.d_work, s.d_result, s.stream)) { return r; }
+        CU(cudaMemcpyAsync(s.h_result, s.d_result, 16, cudaMemcpyDeviceToHost, s.stream));
+        if (st->prev_parsed == nullptr) {
+            CU(cudaEventCreateWithFlags(&st->prev_parsed, cudaEventDisableTiming));
+        }
+        CU(cudaEventRecord(st->prev_parsed, s.stream));
+        st->prev_result = s.d_result;
+    } else {
+        if (int r = sqz_gpu_unpack_table_device(s.d_table, n, s.d_len, s.d_dist, s.stream)) { return r; }
+        CU(cudaMemcpyAsync(len_out + first, s.d_len, n * 2, cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaMemcpyAsync(dist_out + first, s.d_dist, n * 2, cudaMemcpyDeviceToHost, s.stream));
+    }
+    CU(cudaEventRecord(s.done, s.stream));
+    s.busy = true;
+    st->launched = first + n;
+    st->next_slot ^= 1;
+    return 0;
+}
+
+static size_t default_chunk(size_t bytes) {
+    const size_t kDefault = (size_t)32 << 20;
+    return std::max<size_t>(std::min(bytes, kDefault), 1);
+}
+
+static int stream_open(sqz_gpu_stream** out, int device, const uint8_t* data, size_t bytes,
+                       uint32_t window, uint32_t min_len, uint32_t max_len, uint32_t max_dist,
+                       size_t chunk, bool tokens) {
+    *out = nullptr;
+    if (int r = check_rules(min_len, max_len, max_dist)) { return r; }
+    if (window == 0 || (window & (window - 1)) != 0 || max_dist > window) {
+        return fail(EINVAL, "window must be a power of two and max_dist <= window");
+    }
+    if (data == nullptr && bytes != 0) { return fail(EINVAL, "null input"); }
+    if (int r = ensure_device(device)) { return r; }
+    sqz_gpu_stream* st = new (std::nothrow) sqz_gpu_stream();
+    if (st == nullptr) { return fail(ENOMEM, "out of host memory"); }
+    st->device = device;
+    st->data = data;
+    st->bytes = bytes;
+    st->min_len = min_len; st->max_len = max_len; st->max_dist = max_dist;
+    st->chunk = chunk ? chunk : default_chunk(bytes);
+    st->want_tokens = tokens;
+    const int slots = bytes > st->chunk ? 2 : 1;
+    for (int k = 0; k < slots && bytes > 0; k++) {
+        if (int r = slot_alloc(st->slot[k], st->chunk, max_len, max_dist, tokens)) {
+            sqz_gpu_stream_close(st);
+            return r;
+        }
+    }
+    *out = st;
+    return 0;
+}
+
+extern "C" int sqz_gpu_stream_open(sqz_gpu_stream** st, int device, const uint8_t* data,
+                                   size_t bytes, uint32_t window, uint32_t min_len,
+                                   uint32_t max_len, uint32_t max_dist, size_t chunk_bytes) {
+    if (st == nullptr) { return fail(EINVAL, "null stream handle"); }
+    if (int r = stream_open(st, device, data, bytes, window, min_len, max_len, max_dist,
+                            chunk_bytes, true)) { return r; }
+    if (bytes > 0) {
+        if (int r = stream_launch_next(*st, nullptr, nullptr)) {
+            sqz_gpu_stream_close(*st);
+            *st = nullptr;
+            return r;
+        }
+    }
+    return 0;
+}
+
+extern "C" int sqz_gpu_stream_next(sqz_gpu_stream* st, const uint32_t** tokens, size_t* count) {
+    if (st == nullptr || tokens == nullptr || count == nullptr) { return fail(EINVAL, "null argument"); }
+    *tokens = nullptr;
+    *count = 0;
+    if (st->delivered >= st->bytes) { return 0; }
+    CU(cudaSetDevice(st->device));
+    // keep the device busy: the slot the caller has just finished reading is free now
+    if (st->launched < st->bytes) {
+        if (int r = stream_launch_next(st, nullptr, nullptr)) { return r; }
+    }
+    Slot& s = st->slot[st->read_slot];
+    CU(cudaEventSynchronize(s.done));
+    const uint64_t n_tok = s.h_result[0];
+    if (n_tok > s.n) { return fail(EIO, "parse produced more tokens than positions"); }
+    CU(cudaMemcpyAsync(s.h_tokens, s.d_tokens, n_tok * 4, cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+    s.busy = false;
+    st->delivered = s.first + s.n;
+    st->read_slot ^= 1;
+    *tokens = s.h_tokens;
+    *count = (size_t)n_tok;
+    return 0;
+}
+
+extern "C" void sqz_gpu_stream_close(sqz_gpu_stream* st) {
+    if (st == nullptr) { return; }
+    cudaSetDevice(st->device);
+    slot_free(st->slot[0]);
+    slot_free(st->slot[1]);
+    if (st->prev_parsed) { cudaEventDestroy(st->prev_parsed); }
+    delete st;
+}
+
+extern "C" int sqz_gpu_tokens(const uint8_t* data, size_t bytes, uint32_t window,
+                              uint32_t min_len, uint32_t max_len, uint32_t max_dist,
+                              uint32_t* tokens_out, size_t tokens_cap, size_t* n_tokens) {
+    if (n_tokens == nullptr) { return fail(EINVAL, "null n_tokens"); }
+    *n_tokens = 0;
+    sqz_gpu_stream* st = nullptr;
+    if (int r = sqz_gpu_stream_open(&st, 0, data, bytes, window, min_len, max_len, max_dist, 0)) {
+        return r;
+    }
+    size_t total = 0;
+    int rc = 0;
+    for (;;) {
+        const uint32_t* t = nullptr;
+        size_t c = 0;
+        rc = sqz_gpu_stream_next(st, &t, &c);
+        if (rc != 0 || c == 0) { break; }
+        if (total < tokens_cap && tokens_out != nullptr) {
+            memcpy(tokens_out + total, t, std::min(c, tokens_cap - total) * 4);
+        }
+        total += c;
+    }
+    sqz_gpu_stream_close(st);
+    *n_tokens = total;
+    if (rc == 0 && total > tokens_cap) { rc = fail(E2BIG, "token buffer too small"); }
+    return rc;
+}
+
+extern "C" int sqz_gpu_match_table(const uint8_t* data, size_t bytes, uint32_t window,
+                                   uint32_t min_len, uint32_t max_len, uint32_t max_dist,
+                                   uint16_t* len_out, uint16_t* dist_out) {
+    if (bytes != 0 && (len_out == nullptr || dist_out == nullptr)) {
+        return fail(EINVAL, "null output");
+    }
+    sqz_gpu_stream* st = nullptr;
+    if (int r = stream_open(&st, 0, data, bytes, window, min_len, max_len, max_dist, 0, false)) {
+        return r;
+    }
+    int rc = 0;
+    while (rc == 0 && st->launched < st->bytes) {
+        Slot& s = st->slot[st->next_slot];
+        if (s.busy) {                      // reuse only after its copies have landed
+            cudaError_t ce = cudaEventSynchronize(s.done);
+            if (ce != cudaSuccess) { rc = fail(cuda_code(ce), "cudaEventSynchronize", ce); break; }
+            s.busy = false;
+        }
+        rc = stream_launch_next(st, len_out, dist_out);
+    }
+    for (int k = 0; k < 2; k++) {
+        if (st->slot[k].stream != nullptr) {
+            cudaError_t ce = cudaStreamSynchronize(st->slot[k].stream);
+            if (ce != cudaSuccess && rc == 0) { rc = fail(cuda_code(ce), "cudaStreamSynchronize", ce); }
+        }
+    }
+    sqz_gpu_stream_close(st);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------
+// utilities
+// ---------------------------------------------------------------------------
+extern "C" int sqz_gpu_abi_version(void) { return SQZ_GPU_ABI_VERSION; }
+
+extern "C" int sqz_gpu_device_count(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return count;
+}
+
+extern "C" const char* sqz_gpu_last_error(void) { return g_err; }
+
+extern "C" void* sqz_gpu_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+extern "C" void sqz_gpu_host_free(void* p) {
+    if (p != nullptr) { cudaFreeHost(p); }
+}
+
+extern "C" uint64_t sqz_gpu_launch_count(void) { return g_launches.load(); }

@@ -1,0 +1,53 @@
+"""GPU parity: the CUDA path through the C-ABI against the oracle, the golden
+digests made with the unmodified reference, and the reference decoder."""
+import numpy as np
+import pytest
+
+import sqz_b200 as sq
+from conftest import fnv
+
+pytestmark = pytest.mark.gpu
+
+FILES = ["laozi.txt", "confucius.txt", "x64.elf", "arm64.elf", "mandrill.bmp", "mandrill.png"]
+KATS = ["zeros4096", "pat1234x1024", "hello", "abc40", "lorem3", "empty", "one", "two", "aaa", "aaaa"]
+
+
+@pytest.mark.parametrize("name", KATS + FILES)
+@pytest.mark.parametrize("wb", [10, 15])
+def test_match_table_golden(name, wb, inputs, golden, oracle):
+    """Full table == digest of the oracle's table (oracle pinned to the reference)."""
+    d = inputs[name]
+    ln, ds = sq.match_table(d, 1 << wb)
+    g = golden[name]["win"][str(wb)]
+    if d.size <= 70000:   # small enough for the brute-force oracle: element-wise report
+        oln, ods = oracle.match_table(d, 1 << wb)
+        bad = np.nonzero((ln != oln) | (ds != ods))[0]
+        assert bad.size == 0, (name, wb, bad[:5], ln[bad[:5]], oln[bad[:5]], ds[bad[:5]], ods[bad[:5]])
+    assert fnv(oracle, ln) == g["fnv_len"]
+    assert fnv(oracle, ds) == g["fnv_dist"]
+
+
+@pytest.mark.parametrize("name", KATS + FILES)
+@pytest.mark.parametrize("wb", [10, 15])
+def test_tokens_and_bitstream_golden(name, wb, inputs, golden, oracle):
+    d = inputs[name]
+    g = golden[name]["win"][str(wb)]
+    t = sq.tokens(d, 1 << wb)
+    assert t.size == g["tokens"]
+    assert int((t >> 16 != 0).sum()) == g["matches"]
+    assert fnv(oracle, t) == g["fnv_tokens"]
+    comp = sq.compress(d, wb)
+    assert len(comp) == g["compressed_bytes"]
+    assert fnv(oracle, np.frombuffer(comp, np.uint8)) == g["fnv_mem"]
+    assert sq.decompress(comp) == d.tobytes()
+
+
+@pytest.mark.parametrize("name", ["hello", "laozi.txt", "arm64.elf"])
+def test_reference_decoder_accepts_our_stream(name, inputs, reference):
+    d = inputs[name]
+    comp = sq.compress(d, 15)
+    assert reference.decompress(comp) == d.tobytes()
+    comp_f = sq.compress(d, 15, file_mode=True)
+    # file mode = the same 64-bit words in host byte order
+    a = np.frombuffer(comp, np.uint8).reshape(-1, 8)[:, ::-1].reshape(-1)
+    assert a.tobytes() == comp_f
