@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py -- match-search throughput of sqz-b200 on B200, beside the reference CPU codec.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size BYTES]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[4]): the synthetic corpus
+-- the reference's six test/ files concatenated and repeated with seeded mutations -- cut
+into contiguous shards, one per GPU, each with a max_dist look-back halo and a max_len
+look-ahead halo.  Every rank holds --size bytes (1 GiB by default), so the job is
+N x 1 GiB ("weak" scaling) and no data-path collective exists; the only exchange is one
+integer per seam (the parse entry offset), handed over through torch.distributed.
+
+A step = one pass of the hot path over the rank's shard: match table for every position
+(squeeze.h:338-358 at every i) + greedy parse to the token stream (squeeze.h:377-394),
+inputs and outputs resident in HBM.  `value` = input MB/s (1 MB = 1e6 B) of the whole
+job, timed with CUDA events on the launching stream, max over ranks.  `e2e` = the same
+pass through the host-buffer C-ABI sqz_gpu_match_table() from pinned host memory,
+host<->device copies inside the timed region.
+
+--impl reference times the UNMODIFIED reference codec (oracle/_ref, squeeze.compress)
+on the host cores, on bounded samples of the same stream.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WINDOW = 1 << 15
+MIN_LEN, MAX_LEN, MAX_DIST = 3, 257, WINDOW - 1      # reference G1 rules, squeeze.h:13-15,342
+SMEM_BYTES_PER_CLK_PER_SM = 128
+SMS = 148
+METRIC = "match_search_input_MBps"
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def cc_count(g0: int, n: int, md: int) -> int:
+    """Candidate-compares for positions [g0, g0+n): sum of min(i, max_dist)  (SURVEY 8d)."""
+    a, b = g0, g0 + n
+    k = min(max(md, a), b)              # positions below k have i < md
+    tri = (k - 1) * k // 2 - (a - 1) * a // 2 if k > a else 0
+    return tri + (b - k) * md
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.path = tempfile.mktemp(prefix="sqz_clocks_", suffix=".csv")
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                 "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.fh, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+                except ValueError:
+                    continue
+                for k, nm in enumerate(names):
+                    if f[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if sm:
+            busy = [c for c in sm if c > 0.5 * max(sm)] or sm
+            out.update(sm_mhz=statistics.median(busy), sm_max_mhz=max(mx), reasons=sorted(reasons),
+                       samples=len(sm), power_w_max=max(power) if power else None)
+        return out
+
+
+# ----------------------------------------------------------------------------- reference arm
+def reference_arm(args) -> None:
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    from oracle import Reference
+    from sqz_b200 import corpus
+    ref = Reference.get(release=True)
+    cores = os.cpu_count() or 1
+    slice_bytes = 128 << 10
+    n_slices = 2 * cores
+    total = args.size * args.gpus
+    stride = max(total // n_slices, 1)
+    slices = [corpus.synthetic(slice_bytes, (k * stride) // 4096 * 4096) for k in range(n_slices)]
+
+    def one_step() -> float:
+        todo = list(range(n_slices))
+        lock = threading.Lock()
+
+        def worker():
+            from oracle import Reference as R
+            r = R(release=True)            # own ctypes handle; the C call releases the GIL
+            while True:
+                with lock:
+                    if not todo:
+                        return
+                    k = todo.pop()
+                r.compress(slices[k], 15)
+
+        th = [threading.Thread(target=worker) for _ in range(cores)]
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        return time.perf_counter() - t0
+
+    for _ in range(args.warmup):
+        pass                                # a CPU loop has nothing to warm that matters; keep W for the record
+    times = [one_step() for _ in range(args.steps)]
+    sec = sum(times) / len(times)
+    mbps = n_slices * slice_bytes / 1e6 / sec
+    sample = ("%d slices x %d KiB of the synthetic stream, evenly spaced over %d GiB, one squeeze.compress "
+              "(window 2^15) per slice, work queue over %d threads; slices start with an empty window, "
+              "which favours the reference by ~12%%" % (n_slices, slice_bytes >> 10, total >> 30, cores))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": mbps, "unit": "MB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": mbps, "unit": "MB/s", "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": mbps, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args) -> dict:
+    return {
+        "workload": "synthetic corpus (6 reference test/ files repeated + seeded mutations, SURVEY 8d config 5), "
+                    "%d MiB per GPU, window 2^15, min_len 3, max_len 257, max_dist 32767" % (args.size >> 20),
+        "bytes_per_gpu": args.size, "window": WINDOW, "min_len": MIN_LEN, "max_len": MAX_LEN,
+        "max_dist": MAX_DIST, "parallelism": "shard%d" % args.gpus,
+        "cache": "inputs (>= 1 GiB per GPU) are larger than the 126 MB L2; no explicit flush",
+    }
+
+
+# ----------------------------------------------------------------------------- our arm
+def ours(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    from sqz_b200 import _lib, corpus
+    L = _lib.load()
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d: launch with torch.distributed.run" % (args.gpus, world))
+    if not torch.cuda.is_available() or L.sqz_gpu_device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: sqz_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = args.size
+    g0 = rank * n                               # global offset of this rank's shard
+    total = world * n
+    back = min(g0, MAX_DIST)
+    ahead = min(total - (g0 + n), MAX_LEN)
+    host = corpus.synthetic(back + n + ahead, g0 - back)
+
+    def check(rc, what):
+        if rc != 0:
+            raise RuntimeError("%s failed: %d %s" % (what, rc, L.sqz_gpu_last_error()))
+
+    # pinned host buffers for the end-to-end leg
+    def pinned(nbytes, dtype):
+        p = L.sqz_gpu_host_alloc(nbytes)
+        if not p:
+            raise MemoryError("sqz_gpu_host_alloc(%d)" % nbytes)
+        buf = (C.c_uint8 * nbytes).from_address(p)
+        return p, np.frombuffer(buf, dtype=dtype)
+
+    p_in, h_in = pinned(back + n + ahead, np.uint8)
+    h_in[:] = host
+    p_len, h_len = pinned(2 * (back + n + ahead), np.uint16)
+    p_dist, h_dist = pinned(2 * (back + n + ahead), np.uint16)
+
+    d_data = torch.empty(back + n + ahead + 64, dtype=torch.uint8, device=dev)
+    d_data[: back + n + ahead].copy_(torch.from_numpy(host))
+    d_table = torch.empty(n, dtype=torch.int32, device=dev)
+    d_tokens = torch.empty(n, dtype=torch.int32, device=dev)
+    d_work = torch.empty(L.sqz_gpu_parse_workspace(n), dtype=torch.uint8, device=dev)
+    d_result = torch.zeros(2, dtype=torch.int64, device=dev)
+    d_map = torch.zeros(512, dtype=torch.int16, device=dev)
+    shard_ptr = d_data.data_ptr() + back
+    stream = torch.cuda.current_stream()
+
+    def step() -> None:
+        s = stream.cuda_stream
+        check(L.sqz_gpu_match_table_device(shard_ptr, back, n, ahead, MIN_LEN, MAX_LEN, MAX_DIST,
+                                           d_table.data_ptr(), s), "match_table")
+        entry = 0
+        if world > 1:
+            # seam hand-off: every shard publishes overshoot(entry) for all entries; a <= 8 step
+            # chain on the host picks the real one.  One integer per seam, no payload collective.
+            check(L.sqz_gpu_parse_exit_map_device(d_table.data_ptr(), n, MIN_LEN, MAX_LEN,
+                                                  d_work.data_ptr(), d_map.data_ptr(), s), "exit_map")
+            maps = [torch.empty_like(d_map) for _ in range(world)]
+            dist.all_gather(maps, d_map)
+            hm = torch.stack(maps).cpu().numpy().astype(np.int64) & 0xFFFF
+            for r in range(rank):
+                entry = int(hm[r, entry])
+        check(L.sqz_gpu_parse_device(shard_ptr, d_table.data_ptr(), n, entry, MIN_LEN, MAX_LEN,
+                                     d_tokens.data_ptr(), n, d_work.data_ptr(), d_result.data_ptr(), s), "parse")
+
+    def e2e_step() -> None:
+        check(L.sqz_gpu_match_table(C.cast(p_in, _lib.u8p), back + n + ahead, WINDOW, MIN_LEN, MAX_LEN, MAX_DIST,
+                                    C.cast(p_len, _lib.u16p), C.cast(p_dist, _lib.u16p)), "sqz_gpu_match_table")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident leg -------------------------------------------------
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    L.sqz_gpu_set_timing(1)
+    L.sqz_gpu_match_kernel_seconds(1, None)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.sqz_gpu_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    sec = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3)
+    launches = L.sqz_gpu_launch_count() - launches0
+    nl = C.c_uint64()
+    t_match = L.sqz_gpu_match_kernel_seconds(1, C.byref(nl))
+    L.sqz_gpu_set_timing(0)
+    clocks = sampler.stop() if rank == 0 else {}
+    n_tokens = int(d_result[0].item())
+
+    # ---- end-to-end leg (host buffers through the C-ABI) -----------------------
+    for _ in range(min(args.warmup, 1)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_sec = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps)
+
+    # spot check: the host-ABI table equals the device-resident one (same kernels, different plumbing)
+    tab = d_table[: 1 << 20].cpu().numpy().view(np.uint32)
+    assert ((tab >> 16) == h_len[back: back + (1 << 20)]).all() and \
+           ((tab & 0xFFFF) == h_dist[back: back + (1 << 20)]).all(), "host ABI and device ABI disagree"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline: the unmodified reference on one core, bounded sample -----
+    cpu = None
+    try:
+        from oracle import Reference
+        ref = Reference.get(release=True)
+        sample_bytes = args.cpu_sample
+        sample = corpus.synthetic(sample_bytes, 0)
+        ref.compress(sample, 15)
+        cpu = {"value": sample_bytes / 1e6 / ref.last_seconds, "unit": "MB/s", "cores": 1, "kind": "reference",
+               "sample": "first %d KiB of the same stream through the unmodified reference's squeeze.compress "
+                         "(oracle/_ref, -O3 -DNDEBUG), window 2^15, %.1f s on 1 of %d host cores"
+                         % (sample_bytes >> 10, ref.last_seconds, os.cpu_count() or 1)}
+    except Exception as e:  # the oracle is only the yardstick; never let it sink the measurement
+        cpu = {"value": None, "unit": "MB/s", "cores": 0, "kind": "reference", "sample": "unavailable: %r" % (e,)}
+
+    ms_per_step = sec / args.steps * 1e3
+    value = total / 1e6 / (sec / args.steps)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    f_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0
+    smem_peak = SMEM_BYTES_PER_CLK_PER_SM * SMS * f_mhz * 1e6 / 1e9            # GB/s at the clock seen under load
+    cc = cc_count(g0, n, MAX_DIST)
+    achieved = cc * 4 / t_match / 1e9 if t_match > 0 else None
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_bytes = n * (1 + 4)                                                    # input read + table write
+    line = {
+        "metric": METRIC, "value": value, "unit": "MB/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(args),
+        "e2e": {"value": total / 1e6 / e2e_sec, "unit": "MB/s",
+                "h2d_bytes_per_step": int(back + n + ahead), "d2h_bytes_per_step": int(4 * (back + n + ahead)),
+                "call": "sqz_gpu_match_table(host pinned in, host pinned len/dist out)", "steps": args.e2e_steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {
+            "bound": "smem", "kernel": "match_table",
+            "achieved": achieved, "peak": smem_peak, "unit": "GB/s",
+            "frac": achieved / smem_peak if achieved else None, "traffic": None,
+            "note": "algorithmic shared-memory bytes = 4 B per candidate-compare (SURVEY 8d), %d CC per launch; "
+                    "peak = 128 B/clk/SM x 148 SMs x %.0f MHz (SM clock sampled under this load); "
+                    "north_star fixes the smem compare bound, HBM is shown in 'hbm'" % (cc, f_mhz),
+            "cc_per_launch": cc, "kernel_ms": t_match * 1e3, "kernel_launches_timed": int(nl.value),
+            "kernel_share_of_step": (t_match * 1e3) / ms_per_step if ms_per_step else None,
+        },
+        "hbm": {"achieved": hbm_bytes / t_match / 1e9 if t_match > 0 else None, "peak": hbm_peak, "unit": "GB/s",
+                "frac": hbm_bytes / t_match / 1e9 / hbm_peak if t_match > 0 else None,
+                "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
+        "cpu_baseline": cpu,
+        "tokens_per_shard": n_tokens,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=1 << 30, help="bytes per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-sample", type=int, default=512 << 10)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()
