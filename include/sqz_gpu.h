@@ -114,6 +114,11 @@ int         sqz_gpu_device_count(void);          /* 0 when no driver / device */
 const char* sqz_gpu_last_error(void);            /* thread-local text */
 void*       sqz_gpu_host_alloc(size_t bytes);    /* pinned host memory (NULL on failure) */
 void        sqz_gpu_host_free(void* p);
+/* Which match-table kernel serves sqz_gpu_match_table_device: 0 = automatic
+ * (bit-sliced kernel for min_len 2 or 3, thread-per-position kernel otherwise),
+ * 1 = thread-per-position, 2 = bit-sliced where applicable.  Both are exact;
+ * the switch exists for A/B measurements and tests.                          */
+int         sqz_gpu_select_kernel(int which);
 /* kernels launched by this library in this process so far (for bench.py)    */
 uint64_t    sqz_gpu_launch_count(void);
 /* average device time of the match-table kernel over the launches since the

@@ -6,7 +6,7 @@ the token stream unchanged (csrc/sqz_codec.c), and this thin ctypes mirror of
 the reference's codec interface.  See DESIGN.md.
 """
 from .api import (SqzError, compress, decompress, device_count, encode_tokens, launch_count,
-                  match_table, read_header, tokens)
+                  match_table, read_header, select_kernel, tokens)
 
 __all__ = ["SqzError", "compress", "decompress", "device_count", "encode_tokens", "launch_count",
-           "match_table", "read_header", "tokens"]
+           "match_table", "read_header", "select_kernel", "tokens"]

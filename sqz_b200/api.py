@@ -45,6 +45,11 @@ def device_count() -> int:
     return int(_lib.load().sqz_gpu_device_count())
 
 
+def select_kernel(which: int) -> None:
+    """0 = automatic, 1 = thread-per-position kernel, 2 = bit-sliced kernel (A/B tests)."""
+    _check(_lib.load().sqz_gpu_select_kernel(int(which)), "sqz_gpu_select_kernel")
+
+
 def launch_count() -> int:
     return int(_lib.load().sqz_gpu_launch_count())
 

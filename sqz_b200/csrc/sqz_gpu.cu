@@ -15,6 +15,8 @@
 
 #include <cuda_runtime.h>
 
+#include "match_bitsliced.cuh"
+
 #include <atomic>
 #include <cerrno>
 #include <cstdio>
@@ -463,12 +465,16 @@ extern "C" double sqz_gpu_match_kernel_seconds(int reset, uint64_t* launches) {
     return avg;
 }
 
-extern "C" int sqz_gpu_match_table_device(const uint8_t* d_shard, size_t back, size_t n,
-                                          size_t ahead, uint32_t min_len, uint32_t max_len,
-                                          uint32_t max_dist, uint32_t* d_table, void* stream) {
-    if (int r = check_rules(min_len, max_len, max_dist)) { return r; }
-    if (n == 0) { return 0; }
-    cudaStream_t s = (cudaStream_t)stream;
+static std::atomic<int> g_kernel_choice{0};   // 0 auto, 1 thread-per-position (v1), 2 bit-sliced (v2)
+
+extern "C" int sqz_gpu_select_kernel(int which) {
+    if (which < 0 || which > 2) { return fail(EINVAL, "kernel choice must be 0, 1 or 2"); }
+    g_kernel_choice.store(which);
+    return 0;
+}
+
+static int launch_v1(const uint8_t* d_shard, size_t back, size_t n, size_t ahead, uint32_t min_len,
+                     uint32_t max_len, uint32_t max_dist, uint32_t* d_table, cudaStream_t s) {
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
@@ -478,6 +484,66 @@ extern "C" int sqz_gpu_match_table_device(const uint8_t* d_shard, size_t back, s
     if (attr_err != cudaSuccess) { return fail(cuda_code(attr_err), "cudaFuncSetAttribute", attr_err); }
     const size_t tiles = (n + v1::kThreads - 1) / v1::kThreads;
     if (tiles > 0x7FFFFFFFull) { return fail(EINVAL, "shard too large for one launch"); }
+    v1::match_table<<<(unsigned)tiles, v1::kThreads, v1::smem_bytes(max_len, max_dist), s>>>(
+        d_shard, (long long)back, (long long)n, (long long)ahead, min_len, max_len, max_dist, d_table);
+    LAUNCHED("match_table_v1");
+    return 0;
+}
+
+template <int kMinLen>
+static int launch_v2(const uint8_t* d_shard, size_t back, size_t n, size_t ahead, uint32_t max_len,
+                     uint32_t max_dist, uint32_t* d_table, cudaStream_t s) {
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        const int big = v2::geometry(sqz_gpu_max_len_limit, sqz_gpu_max_dist_limit, true).smem_bytes;
+        attr_err = cudaFuncSetAttribute(v2::match_table<kMinLen, false>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        if (attr_err == cudaSuccess) {
+            attr_err = cudaFuncSetAttribute(v2::match_table<kMinLen, true>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        }
+    });
+    if (attr_err != cudaSuccess) { return fail(cuda_code(attr_err), "cudaFuncSetAttribute", attr_err); }
+    // Tiles whose every position sees the full max_dist window and max_len of
+    // look-ahead run the plain variant; the rest (start of the first shard, end
+    // of the last one, a partial last tile) run the variant with a validity plane.
+    const long long tp = v2::kTilePos;
+    const long long tiles = ((long long)n + tp - 1) / tp;
+    if (tiles > 0x7FFFFFFFll) { return fail(EINVAL, "shard too large for one launch"); }
+    long long t_lo = back >= max_dist ? 0 : ((long long)max_dist - (long long)back + tp - 1) / tp;
+    long long tail = (long long)n + (long long)std::min<size_t>(ahead, max_len) - (long long)max_len;
+    long long t_hi = tail <= 0 ? 0 : tail / tp;
+    t_lo = std::min(t_lo, tiles);
+    t_hi = std::max(std::min(t_hi, tiles), t_lo);
+    const int smem_main = v2::geometry(max_len, max_dist, false).smem_bytes;
+    const int smem_edge = v2::geometry(max_len, max_dist, true).smem_bytes;
+    if (t_lo > 0) {
+        v2::match_table<kMinLen, true><<<(unsigned)t_lo, v2::kThreads, smem_edge, s>>>(
+            d_shard, (long long)back, (long long)n, (long long)ahead, max_len, max_dist, d_table, nullptr, 0);
+        LAUNCHED("match_table_v2_edge");
+    }
+    if (t_hi > t_lo) {
+        v2::match_table<kMinLen, false><<<(unsigned)(t_hi - t_lo), v2::kThreads, smem_main, s>>>(
+            d_shard, (long long)back, (long long)n, (long long)ahead, max_len, max_dist, d_table, nullptr,
+            (int)t_lo);
+        LAUNCHED("match_table_v2");
+    }
+    if (tiles > t_hi) {
+        v2::match_table<kMinLen, true><<<(unsigned)(tiles - t_hi), v2::kThreads, smem_edge, s>>>(
+            d_shard, (long long)back, (long long)n, (long long)ahead, max_len, max_dist, d_table, nullptr,
+            (int)t_hi);
+        LAUNCHED("match_table_v2_edge");
+    }
+    return 0;
+}
+
+extern "C" int sqz_gpu_match_table_device(const uint8_t* d_shard, size_t back, size_t n,
+                                          size_t ahead, uint32_t min_len, uint32_t max_len,
+                                          uint32_t max_dist, uint32_t* d_table, void* stream) {
+    if (int r = check_rules(min_len, max_len, max_dist)) { return r; }
+    if (n == 0) { return 0; }
+    cudaStream_t s = (cudaStream_t)stream;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     bool timed = false;
     {
@@ -490,9 +556,12 @@ extern "C" int sqz_gpu_match_table_device(const uint8_t* d_shard, size_t back, s
         CU(cudaEventCreate(&e1));
         CU(cudaEventRecord(e0, s));
     }
-    v1::match_table<<<(unsigned)tiles, v1::kThreads, v1::smem_bytes(max_len, max_dist), s>>>(
-        d_shard, (long long)back, (long long)n, (long long)ahead, min_len, max_len, max_dist, d_table);
-    LAUNCHED("match_table");
+    const int choice = g_kernel_choice.load();
+    int r;
+    if (choice != 1 && min_len == 3)      { r = launch_v2<3>(d_shard, back, n, ahead, max_len, max_dist, d_table, s); }
+    else if (choice != 1 && min_len == 2) { r = launch_v2<2>(d_shard, back, n, ahead, max_len, max_dist, d_table, s); }
+    else { r = launch_v1(d_shard, back, n, ahead, min_len, max_len, max_dist, d_table, s); }
+    if (r != 0) { return r; }
     if (timed) {
         CU(cudaEventRecord(e1, s));
         std::lock_guard<std::mutex> lk(g_time_mu);

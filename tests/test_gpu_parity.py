@@ -12,9 +12,17 @@ FILES = ["laozi.txt", "confucius.txt", "x64.elf", "arm64.elf", "mandrill.bmp", "
 KATS = ["zeros4096", "pat1234x1024", "hello", "abc40", "lorem3", "empty", "one", "two", "aaa", "aaaa"]
 
 
+@pytest.fixture(params=[2, 1], ids=["bitsliced", "per_position"])
+def kernel(request):
+    """Both match-table kernels must be exact; 0/auto is restored afterwards."""
+    sq.select_kernel(request.param)
+    yield request.param
+    sq.select_kernel(0)
+
+
 @pytest.mark.parametrize("name", KATS + FILES)
 @pytest.mark.parametrize("wb", [10, 15])
-def test_match_table_golden(name, wb, inputs, golden, oracle):
+def test_match_table_golden(name, wb, inputs, golden, oracle, kernel):
     """Full table == digest of the oracle's table (oracle pinned to the reference)."""
     d = inputs[name]
     ln, ds = sq.match_table(d, 1 << wb)
