@@ -465,6 +465,10 @@ extern "C" double sqz_gpu_match_kernel_seconds(int reset, uint64_t* launches) {
     return avg;
 }
 
+static unsigned long long* g_tile_cycles = nullptr;   // debugging aid, see sqz_gpu_debug_tile_cycles
+
+extern "C" void sqz_gpu_debug_tile_cycles(unsigned long long* d_buf) { g_tile_cycles = d_buf; }
+
 static std::atomic<int> g_kernel_choice{0};   // 0 auto, 1 thread-per-position (v1), 2 bit-sliced (v2)
 
 extern "C" int sqz_gpu_select_kernel(int which) {
@@ -503,6 +507,11 @@ static int launch_v2(const uint8_t* d_shard, size_t back, size_t n, size_t ahead
             attr_err = cudaFuncSetAttribute(v2::match_table<kMinLen, true>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         }
+        // several CTAs per SM only fit when the L1/shared split favours shared memory
+        cudaFuncSetAttribute(v2::match_table<kMinLen, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(v2::match_table<kMinLen, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
     });
     if (attr_err != cudaSuccess) { return fail(cuda_code(attr_err), "cudaFuncSetAttribute", attr_err); }
     // Tiles whose every position sees the full max_dist window and max_len of
@@ -520,19 +529,17 @@ static int launch_v2(const uint8_t* d_shard, size_t back, size_t n, size_t ahead
     const int smem_edge = v2::geometry(max_len, max_dist, true).smem_bytes;
     if (t_lo > 0) {
         v2::match_table<kMinLen, true><<<(unsigned)t_lo, v2::kThreads, smem_edge, s>>>(
-            d_shard, (long long)back, (long long)n, (long long)ahead, max_len, max_dist, d_table, nullptr, 0);
+            d_shard, (long long)back, (long long)n, (long long)ahead, max_len, max_dist, d_table, 0, g_tile_cycles);
         LAUNCHED("match_table_v2_edge");
     }
     if (t_hi > t_lo) {
         v2::match_table<kMinLen, false><<<(unsigned)(t_hi - t_lo), v2::kThreads, smem_main, s>>>(
-            d_shard, (long long)back, (long long)n, (long long)ahead, max_len, max_dist, d_table, nullptr,
-            (int)t_lo);
+            d_shard, (long long)back, (long long)n, (long long)ahead, max_len, max_dist, d_table, (int)t_lo, g_tile_cycles);
         LAUNCHED("match_table_v2");
     }
     if (tiles > t_hi) {
         v2::match_table<kMinLen, true><<<(unsigned)(tiles - t_hi), v2::kThreads, smem_edge, s>>>(
-            d_shard, (long long)back, (long long)n, (long long)ahead, max_len, max_dist, d_table, nullptr,
-            (int)t_hi);
+            d_shard, (long long)back, (long long)n, (long long)ahead, max_len, max_dist, d_table, (int)t_hi, g_tile_cycles);
         LAUNCHED("match_table_v2_edge");
     }
     return 0;

@@ -1,0 +1,35 @@
+"""Debugging aid: per-tile duration of the bit-sliced match kernel on one input."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from sqz_b200 import _lib, corpus
+L = _lib.load()
+size = int(sys.argv[1]) if len(sys.argv) > 1 else 32 << 20
+data = corpus.synthetic(size, 0)
+d = torch.from_numpy(data).cuda()
+pad = torch.zeros(size + 1024, dtype=torch.uint8, device="cuda"); pad[:size] = d
+table = torch.empty(size, dtype=torch.int32, device="cuda")
+TP = 15872
+tiles = (size + TP - 1) // TP
+cyc = torch.zeros(tiles, dtype=torch.int64, device="cuda")
+L.sqz_gpu_debug_tile_cycles(cyc.data_ptr())
+for it in range(2):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = L.sqz_gpu_match_table_device(pad.data_ptr(), 0, size, 0, 3, 257, 32767, table.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    e1.record(); torch.cuda.synchronize()
+    print("rc", rc, "ms", e0.elapsed_time(e1))
+c = cyc.cpu().numpy()
+print("tiles", tiles, "sum Gcyc", c.sum() / 1e9, "median", np.median(c), "p90", np.percentile(c, 90), "max", c.max())
+order = np.argsort(-c)[:12]
+B = corpus.base().size
+names = corpus.ORDER; sizes = [corpus.fixtures()[n].size for n in names]
+def where(pos):
+    o = pos % B
+    for n, s in zip(names, sizes):
+        if o < s: return "%s+%d" % (n, o)
+        o -= s
+for t in order:
+    print(t, c[t], "Mcyc %.1f" % (c[t] / 1e6), where(t * TP))
+np.save("gpurun_out/tile_cycles.npy", c)
