@@ -2,8 +2,9 @@
 //
 // Same result as the reference's brute-force scan
 // (/root/reference/attic/map_experiment/squeeze.h:338-358 at every position),
-// computed 32 positions at a time with bit-parallel logic:
+// computed 32 positions at a time with bit-parallel logic.
 //
+// Phase 1 (all 32767 distances, every position, bit-sliced):
 //   * The input is transposed into 8 bit-planes in shared memory: bit i of
 //     plane b is bit b of byte i.  For a block of 32 consecutive positions and a
 //     distance d, "byte i equals byte i-d" for all 32 positions is
@@ -11,24 +12,33 @@
 //     i.e. one funnel shift + one LOP3 per plane: 17 integer instructions for
 //     32 candidate-compares, where a thread-per-position kernel needs 32 loads
 //     and 32 compares.
-//   * "A match of >= 3 starts at i" is E & E>>1 & E>>2 (bits shifted in from the
-//     next block); >= 5, 9, 17, 33, 65 follow by doubling (R_2k-1 = R_k & R_k>>(k-1)).
+//   * "A run of >= k equal bytes starts at i" is R_k = E & E>>1 & ... & E>>(k-1),
+//     built incrementally for k = min_len .. min_len+6 (bits shifted in from the
+//     next block).
 //   * Per-position state is bit-sliced too: three code planes hold, for each of
-//     the 32 positions, which of the six run-length classes a candidate has to
-//     reach to beat the position's current best (codes 6/7 = closed: the
-//     position already holds max_len, or is not owned by this thread).  A 6-way
-//     bit-wise multiplexer picks the matching run mask for every position.
+//     the 32 positions, the run length a candidate has to reach to beat the
+//     position's current best: need = best+1, exact for need <= min_len+6
+//     (codes 0..6, code 6 also stands for anything longer); code 7 = closed.  An
+//     8-way bit-wise multiplexer picks R_need for every position at once, so
+//     a candidate that merely ties or falls short never leaves the fast path.
 //   * Distances are visited in ascending order, exactly like the reference, so
 //     "strictly longer wins" keeps the nearest candidate among equals.
-//   * Only positions that survive the multiplexer reach the scalar path, which
-//     measures the run exactly from the same E bits, compares it with the
-//     position's current best (kept in the output table itself) and records
-//     (len, dist).
+//   * Survivors of the multiplexer take a scalar path: the run is measured from
+//     the same E bits (32-bit window), compared with the position's current
+//     best and recorded as (len, dist).
 //
-// Work split: a thread owns kQ consecutive blocks (32*kQ positions) for the
-// whole scan, so all per-position state is private to one thread: no atomics,
-// no inter-thread ordering.  Lane 31 of every warp recomputes the first kQ
-// blocks of the next warp as look-ahead only (its positions are closed).
+// Phase 2 (few positions, warp per position, same CTA):
+//   Positions whose run leaves the 32-bit window (matches of >= 32 bytes, the
+//   ends of long byte runs) or that keep producing near-ties are handed over:
+//   the CTA restages the raw bytes of its window over the bit planes and every
+//   such position is finished by one warp with the classic exact search --
+//   32 lanes x 4 candidates per step, 4-byte compare at the offset a candidate
+//   must match to win, ballot for the nearest hit, cooperative verify.
+//
+// Work split in phase 1: a thread owns kQ consecutive blocks (32*kQ positions)
+// for the whole scan, so all per-position state is private to one thread: no
+// atomics, no inter-thread ordering.  Lane 31 of every warp recomputes the
+// first kQ blocks of the next warp as look-ahead only (its positions are closed).
 #pragma once
 
 #include <cstdint>
@@ -42,22 +52,27 @@ constexpr int kQ = 4;                     // blocks of 32 positions per thread
 constexpr int kWarpOwned = 31 * kQ;       // blocks a warp owns (lane 31 is look-ahead)
 constexpr int kTileBlocks = kWarps * kWarpOwned;      // owned blocks per CTA
 constexpr int kTilePos = kTileBlocks * 32;            // positions per CTA
-constexpr int kLevels = 6;
+constexpr uint8_t kHandOver = 0xFF;       // best_len mark: finish this position in phase 2
+constexpr uint8_t kFinished = 0xFE;       // best_len mark: holds max_len, nothing left to do
 
 struct Geometry {            // identical for all CTAs of a launch
     int back_blocks;         // plane blocks staged before the tile: ceil(max_dist/32) + 1
-    int ahead_blocks;        // after the tile: look-ahead lane + long-run extension
+    int ahead_blocks;        // after the tile: look-ahead lane + slack
     int plane_blocks;
+    int region_bytes;        // planes (phase 1) / raw bytes (phase 2) share this region
     int smem_bytes;
 };
 
 __host__ __device__ inline Geometry geometry(uint32_t max_len, uint32_t max_dist, bool edge) {
     Geometry g;
     g.back_blocks = (int)((max_dist + 31) / 32) + 1;
-    g.ahead_blocks = kQ + (int)((max_len + 31) / 32) + 3;
+    g.ahead_blocks = kQ + 2;
     g.plane_blocks = g.back_blocks + kTileBlocks + g.ahead_blocks;
-    int bytes = g.plane_blocks * 32;                  // 8 planes x 4 B per block
-    if (edge) { bytes += g.plane_blocks * 4; }        // validity plane
+    const int plane_bytes = g.plane_blocks * 32;                           // 8 planes x 4 B per block
+    const int raw_bytes = (int)max_dist + kTilePos + (int)max_len + 64;    // phase 2 image
+    g.region_bytes = ((plane_bytes > raw_bytes ? plane_bytes : raw_bytes) + 15) & ~15;
+    int bytes = g.region_bytes + kTilePos + 32;                            // + u8 best length per position
+    if (edge) { bytes += g.plane_blocks * 4; }                             // validity plane
     g.smem_bytes = (bytes + 15) & ~15;
     return g;
 }
@@ -71,34 +86,66 @@ __device__ __forceinline__ uint32_t mux(uint32_t sel, uint32_t a, uint32_t b) {
     return (a & ~sel) | (b & sel);
 }
 
-// E-bar (1 = bytes differ) of plane block `blk` at distance 32*m - sh, straight
-// from shared memory.  Scalar path only.
-template <bool kEdge>
-__device__ __noinline__ uint32_t ebar_from_smem(const uint4* __restrict__ PL,
-                                                const uint32_t* __restrict__ VL,
-                                                int blk, int m, int sh) {
-    const uint4 qa = PL[2 * blk], qb = PL[2 * blk + 1];
-    const uint4 la = PL[2 * (blk - m)], lb = PL[2 * (blk - m) + 1];
-    const uint4 ha = PL[2 * (blk - m + 1)], hb = PL[2 * (blk - m + 1) + 1];
-    uint32_t e = fsr(la.x, ha.x, sh) ^ qa.x;
-    e |= fsr(la.y, ha.y, sh) ^ qa.y;
-    e |= fsr(la.z, ha.z, sh) ^ qa.z;
-    e |= fsr(la.w, ha.w, sh) ^ qa.w;
-    e |= fsr(lb.x, hb.x, sh) ^ qb.x;
-    e |= fsr(lb.y, hb.y, sh) ^ qb.y;
-    e |= fsr(lb.z, hb.z, sh) ^ qb.z;
-    e |= fsr(lb.w, hb.w, sh) ^ qb.w;
-    if (kEdge) { e |= ~VL[blk] | ~fsr(VL[blk - m], VL[blk - m + 1], sh); }
-    return e;
-}
-
-// class a position is in once it holds a match of length `best`:
-// thresholds kMinLen, then (T-1)*2+1 each: 3,5,9,17,33,65 (or 2,3,5,9,17,33)
-template <int kMinLen>
-__device__ __forceinline__ int level_of(uint32_t best) {
-    if (best < 2) { return 0; }
-    const int lg = 31 - __clz((int)best);
-    return min(kLevels - 1, max(0, lg - (kMinLen - 2)));
+// ---------------------------------------------------------------------------
+// phase 2: one warp finishes one position with the exact search on raw bytes.
+// S = byte image, S[xi] = the position's first byte; candidates S[xi-d], d in
+// [d_from, reach]; `room` = min(max_len, bytes left).  (best, bdist) enter with
+// what phase 1 found (all distances <= bdist are settled) and leave final.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void finish_position(const uint8_t* __restrict__ S, int xi,
+                                                uint32_t reach, uint32_t room, uint32_t min_len,
+                                                uint32_t& best, uint32_t& bdist, int lane) {
+    const uint32_t* W = reinterpret_cast<const uint32_t*>(S);
+    uint32_t d0 = bdist + 1;
+    while (d0 <= reach && best < room) {
+        const uint32_t need = max(best + 1, min_len);
+        if (need > room) { break; }
+        const uint32_t o = need >= 4 ? need - 4 : 0;
+        const uint32_t mask = need >= 4 ? 0xFFFFFFFFu : (0xFFFFFFFFu >> (8 * (4 - need)));
+        const int a = xi + (int)o;                         // anchor: candidate d starts at a - d
+        const int wa = a >> 2;
+        const uint32_t key = fsr(W[wa], W[wa + 1], (a & 3) * 8) & mask;
+        // lanes walk aligned words downward from the one holding candidate d0
+        const int c_hi = a - (int)d0;                      // nearest candidate still open
+        const int c_lo = a - (int)reach;                   // farthest candidate
+        int w = (c_hi >> 2) - lane;
+        uint32_t hit_d = 0;
+        for (;;) {
+            uint32_t hb = 0;
+            if ((w << 2) + 3 >= c_lo) {
+                const uint32_t low = W[w], hiw = W[w + 1];
+                const uint32_t t0 = (low ^ key) & mask;
+                const uint32_t t1 = (__byte_perm(low, hiw, 0x4321) ^ key) & mask;
+                const uint32_t t2 = (__byte_perm(low, hiw, 0x5432) ^ key) & mask;
+                const uint32_t t3 = (__byte_perm(low, hiw, 0x6543) ^ key) & mask;
+                hb = (t0 == 0 ? 1u : 0u) | (t1 == 0 ? 2u : 0u) | (t2 == 0 ? 4u : 0u) | (t3 == 0 ? 8u : 0u);
+                const int kmax = min(3, c_hi - (w << 2));  // only lane 0's word can be cut at the top
+                const int kmin = max(0, c_lo - (w << 2));
+                hb &= (2u << kmax) - 1u;
+                hb &= ~((1u << kmin) - 1u);
+            }
+            const uint32_t any = __ballot_sync(0xFFFFFFFFu, hb != 0);
+            if (any != 0) {
+                const int src = __ffs((int)any) - 1;                        // lowest lane = nearest word
+                const int c = (w << 2) + (31 - __clz((int)hb | 1));         // nearest candidate in my word
+                hit_d = (uint32_t)(a - __shfl_sync(0xFFFFFFFFu, c, src));
+                break;
+            }
+            w -= 32;
+            if (((w + lane) << 2) + 3 < c_lo) { break; }                    // lane 0's word is past the end
+        }
+        if (hit_d == 0) { break; }
+        // cooperative verify: common prefix of S[xi..] and S[xi-hit_d..], capped at room
+        uint32_t m = room;
+        for (uint32_t base = 0; base < room; base += 32) {
+            const uint32_t k = base + (uint32_t)lane;
+            const bool diff = k < room && S[xi + (int)k] != S[xi - (int)hit_d + (int)k];
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, diff);
+            if (bal != 0) { m = base + (uint32_t)(__ffs((int)bal) - 1); break; }
+        }
+        if (m >= need) { best = m; bdist = hit_d; }
+        d0 = hit_d + 1;
+    }
 }
 
 template <int kMinLen, bool kEdge>
@@ -110,7 +157,8 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const Geometry geo = geometry(max_len, max_dist, kEdge);
     const uint4* PL = reinterpret_cast<const uint4*>(smem_raw);           // [plane_blocks][2]
-    uint32_t* VL = reinterpret_cast<uint32_t*>(smem_raw + geo.plane_blocks * 32);
+    uint8_t* best_len = smem_raw + geo.region_bytes;                      // [kTilePos + 32]
+    uint32_t* VL = reinterpret_cast<uint32_t*>(smem_raw + geo.region_bytes + kTilePos + 32);
 
     const int tile = tile_first + (int)blockIdx.x;
     const long long tile_pos0 = (long long)tile * kTilePos;              // shard-relative
@@ -136,6 +184,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                 if (lane == 0) { VL[blk] = v; }
             }
         }
+        for (int k = threadIdx.x; k < kTilePos + 32; k += kThreads) { best_len[k] = 0; }
         for (int k = threadIdx.x; k < kTilePos; k += kThreads) {
             const long long p = tile_pos0 + k;
             if (p < n) { table[p] = 0; }
@@ -143,12 +192,13 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
     }
     __syncthreads();
 
-    // ---- per-thread state ------------------------------------------------------
+    // ---- phase 1: per-thread state ---------------------------------------------
     const int own0 = warp * kWarpOwned + lane * kQ;         // first block of this thread (tile-relative)
     const int blk0 = geo.back_blocks + own0;                // same, as plane block index
     uint32_t qv[kQ][8];
     uint32_t vq[kQ];
-    uint32_t L0[kQ], L1[kQ], L2[kQ];                        // bit-sliced class code per position
+    uint32_t L0[kQ], L1[kQ], L2[kQ];                        // bit-sliced need code per position
+    int handed = 0;                                         // this thread left work for phase 2
 #pragma unroll
     for (int q = 0; q < kQ; q++) {
         const uint4 a = PL[2 * (blk0 + q)], b = PL[2 * (blk0 + q) + 1];
@@ -159,7 +209,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
         uint32_t closed = 0;
         if (lane == 31) { closed = 0xFFFFFFFFu; }
         else if (p0 + 32 > n) { closed = p0 >= n ? 0xFFFFFFFFu : (0xFFFFFFFFu << (int)(n - p0)); }
-        L0[q] = 0; L1[q] = closed; L2[q] = closed;          // code 6 = closed
+        L0[q] = closed; L1[q] = closed; L2[q] = closed;     // code 7 = closed
         vq[q] = kEdge ? VL[blk0 + q] : 0xFFFFFFFFu;
     }
 
@@ -182,8 +232,8 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
         for (int sh = 31; sh >= 0; sh--) {
             const uint32_t d = (uint32_t)(32 * m - sh);
             if (d > reach) { break; }
-            // r[k][q]: bit p set = NO run of at least T_k equal bytes starts at position p
-            uint32_t eb[kQ + 1], r0[kQ + 1], r1[kQ + 1], r2[kQ + 1], r3[kQ + 1], r4[kQ + 1];
+            // eb: bit p set = byte p differs.  r[k]: bit p set = NO run of kMinLen+k equal bytes at p
+            uint32_t eb[kQ + 1];
 #pragma unroll
             for (int q = 0; q < kQ; q++) {
                 uint32_t ea = fsr(cw[q][0], cw[q + 1][0], sh) ^ qv[q][0];
@@ -198,36 +248,26 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                 eb[q] = e;
             }
             eb[kQ] = __shfl_down_sync(0xFFFFFFFFu, eb[0], 1);
-#pragma unroll
-            for (int q = 0; q < kQ; q++) {
-                uint32_t r = eb[q] | fsr(eb[q], eb[q + 1], 1);
-                if (kMinLen >= 3) { r |= fsr(eb[q], eb[q + 1], 2); }
-                r0[q] = r;
-            }
-            r0[kQ] = __shfl_down_sync(0xFFFFFFFFu, r0[0], 1);
-            constexpr int S1 = kMinLen - 1, S2 = 2 * S1, S3 = 2 * S2, S4 = 2 * S3, S5 = 2 * S4;
-#pragma unroll
-            for (int q = 0; q < kQ; q++) { r1[q] = r0[q] | fsr(r0[q], r0[q + 1], S1); }
-            r1[kQ] = __shfl_down_sync(0xFFFFFFFFu, r1[0], 1);
-#pragma unroll
-            for (int q = 0; q < kQ; q++) { r2[q] = r1[q] | fsr(r1[q], r1[q + 1], S2); }
-            r2[kQ] = __shfl_down_sync(0xFFFFFFFFu, r2[0], 1);
-#pragma unroll
-            for (int q = 0; q < kQ; q++) { r3[q] = r2[q] | fsr(r2[q], r2[q + 1], S3); }
-            r3[kQ] = __shfl_down_sync(0xFFFFFFFFu, r3[0], 1);
-#pragma unroll
-            for (int q = 0; q < kQ; q++) { r4[q] = r3[q] | fsr(r3[q], r3[q + 1], S4); }
-            r4[kQ] = __shfl_down_sync(0xFFFFFFFFu, r4[0], 1);
             uint32_t ib[kQ];
             uint32_t none = 0xFFFFFFFFu;
 #pragma unroll
             for (int q = 0; q < kQ; q++) {
-                const uint32_t r5 = r4[q] | (S5 >= 32 ? r4[q + 1] : fsr(r4[q], r4[q + 1], S5 & 31));
-                const uint32_t m01 = mux(L0[q], r0[q], r1[q]);
-                const uint32_t m23 = mux(L0[q], r2[q], r3[q]);
-                const uint32_t m45 = mux(L0[q], r4[q], r5) | L1[q];      // codes 6,7: closed
+                uint32_t r[7];
+                uint32_t acc = eb[q] | fsr(eb[q], eb[q + 1], 1);
+                if (kMinLen >= 3) { acc |= fsr(eb[q], eb[q + 1], 2); }
+                r[0] = acc;
+#pragma unroll
+                for (int k = 1; k < 7; k++) {
+                    acc |= fsr(eb[q], eb[q + 1], kMinLen - 1 + k);
+                    r[k] = acc;
+                }
+                const uint32_t m01 = mux(L0[q], r[0], r[1]);
+                const uint32_t m23 = mux(L0[q], r[2], r[3]);
+                const uint32_t m45 = mux(L0[q], r[4], r[5]);
+                const uint32_t m67 = r[6] | L0[q];                        // code 7: closed
                 const uint32_t m03 = mux(L1[q], m01, m23);
-                ib[q] = mux(L2[q], m03, m45);
+                const uint32_t m47 = mux(L1[q], m45, m67);
+                ib[q] = mux(L2[q], m03, m47);
                 none &= ib[q];
             }
             if (none != 0xFFFFFFFFu) {
@@ -238,38 +278,34 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                     while (todo != 0) {
                         const int p = __ffs((int)todo) - 1;
                         todo &= todo - 1;
-                        uint32_t* slot = table + tile_pos0 + (long long)(own0 + q) * 32 + p;
-                        const uint32_t have = *slot >> 16;
-                        const uint32_t win = fsr(eb[q], eb[q + 1], p);  // E-bar from position p on
-                        uint32_t run;
-                        if (win != 0) {
-                            run = (uint32_t)(__ffs((int)win) - 1);      // run ends inside the window
-                            if (run <= have) { continue; }
-                        } else {
-                            // the run leaves the 32-bit window
-                            if (have >= 32) {
-                                // cheap reject first: the byte at offset `have` has to match too
-                                const int off = p + (int)have;
-                                const uint32_t e = ebar_from_smem<kEdge>(PL, VL, blk0 + q + (off >> 5), m, sh);
-                                if ((e >> (off & 31)) & 1u) { continue; }
-                            }
-                            run = 32;
-                            int blk = blk0 + q + 1;
-                            uint32_t ea = ebar_from_smem<kEdge>(PL, VL, blk, m, sh);
-                            while (run < max_len) {
-                                const uint32_t ec = ebar_from_smem<kEdge>(PL, VL, blk + 1, m, sh);
-                                const uint32_t w2 = fsr(ea, ec, p);
-                                if (w2 != 0) { run += (uint32_t)(__ffs((int)w2) - 1); break; }
-                                run += 32;
-                                blk++;
-                                ea = ec;
-                            }
-                        }
-                        run = min(run, max_len);
-                        if (run <= have) { continue; }
-                        *slot = (run << 16) | d;
                         const uint32_t bit = 1u << p;
-                        const int code = run >= max_len ? 6 : level_of<kMinLen>(run);
+                        const int k = (own0 + q) * 32 + p;              // tile-relative position
+                        const uint32_t state = best_len[k];             // low 5 bits: best, high 3: near-ties seen
+                        const uint32_t have = state & 31u;
+                        const uint32_t win = fsr(eb[q], eb[q + 1], p);  // E-bar from position p on
+                        uint32_t run = win != 0 ? (uint32_t)(__ffs((int)win) - 1) : 32u;
+                        int code;
+                        if (run >= max_len) {
+                            // cannot be beaten any more: record and close
+                            best_len[k] = kFinished;
+                            table[tile_pos0 + k] = (max_len << 16) | d;
+                            code = 7;
+                        } else if (win == 0) {
+                            // at least 32 equal bytes: longer than the window, finish in phase 2
+                            best_len[k] = kHandOver;
+                            handed = 1;
+                            code = 7;
+                        } else if (run > have) {
+                            best_len[k] = (uint8_t)run;
+                            table[tile_pos0 + k] = (run << 16) | d;
+                            code = min((int)run + 1 - kMinLen, 6);
+                        } else {
+                            // a candidate that only ties: count a sample of them; a position that
+                            // keeps attracting them is cheaper to finish in phase 2
+                            if ((d & 15u) != 0) { continue; }
+                            if (state >= 0xC0u) { best_len[k] = kHandOver; handed = 1; code = 7; }
+                            else { best_len[k] = (uint8_t)(state + 32u); continue; }
+                        }
                         L0[q] = (code & 1) ? (L0[q] | bit) : (L0[q] & ~bit);
                         L1[q] = (code & 2) ? (L1[q] | bit) : (L1[q] & ~bit);
                         L2[q] = (code & 4) ? (L2[q] | bit) : (L2[q] & ~bit);
@@ -277,6 +313,36 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                 }
             }
         }
+    }
+
+    // ---- phase 2: finish the handed-over positions on raw bytes -------------------
+    if (__syncthreads_or(handed) != 0) {               // everybody is done with the planes
+    const long long raw_lo = max(tile_pos0 - (long long)max_dist, -back);         // first byte staged
+    const long long raw_hi = min(tile_pos0 + kTilePos + (long long)max_len, n + ahead);
+    const int shift = (int)(reinterpret_cast<uintptr_t>(shard + raw_lo) & 3);     // keep word alignment
+    uint8_t* S = smem_raw;
+    {
+        const int span = shift + (int)(raw_hi - raw_lo);
+        for (int k = threadIdx.x; k < span + 8; k += kThreads) {
+            const int g = k - shift;
+            S[k] = (g >= 0 && k < span) ? __ldg(shard + raw_lo + g) : (uint8_t)0;
+        }
+    }
+    __syncthreads();
+    for (int base = warp * 32; base < kTilePos; base += kWarps * 32) {
+        uint32_t marks = __ballot_sync(0xFFFFFFFFu, best_len[base + lane] == kHandOver);
+        while (marks != 0) {
+            const int k = base + __ffs((int)marks) - 1;
+            marks &= marks - 1;
+            const long long p = tile_pos0 + k;
+            const uint32_t word = table[p];
+            uint32_t best = word >> 16, bdist = word & 0xFFFFu;
+            const uint32_t room = (uint32_t)min((long long)max_len, n + ahead - p);
+            const uint32_t far = (uint32_t)min((long long)max_dist, p + back);
+            finish_position(S, shift + (int)(p - raw_lo), far, room, (uint32_t)kMinLen, best, bdist, lane);
+            if (lane == 0) { table[p] = best >= (uint32_t)kMinLen ? ((best << 16) | bdist) : 0u; }
+        }
+    }
     }
     if (tile_cycles != nullptr) {          // debugging aid: per-tile duration
         __syncthreads();
