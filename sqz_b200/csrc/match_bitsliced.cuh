@@ -88,14 +88,25 @@ __device__ __forceinline__ uint32_t mux(uint32_t sel, uint32_t a, uint32_t b) {
 
 // ---------------------------------------------------------------------------
 // phase 2: one warp finishes one position with the exact search on raw bytes.
-// S = byte image, S[xi] = the position's first byte; candidates S[xi-d], d in
-// [d_from, reach]; `room` = min(max_len, bytes left).  (best, bdist) enter with
-// what phase 1 found (all distances <= bdist are settled) and leave final.
+// S = 4-byte aligned byte image (shared or global), S[xi] = the position's first
+// byte, x_end = one past the last readable byte; candidates S[xi-d] for d up to
+// `reach`; `room` = min(max_len, bytes left).  (best, bdist) enter with what
+// phase 1 found (all distances <= bdist are settled) and leave final.
+//
+// 32 lanes x 4 candidates per step: every lane takes one aligned word and tests
+// the four byte offsets in it against the 4 bytes a candidate has to match to
+// win (the word ending at offset need-1; the first `need` bytes while
+// need < 4).  Hits are verified nearest first by all lanes together.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void finish_position(const uint8_t* __restrict__ S, int xi,
-                                                uint32_t reach, uint32_t room, uint32_t min_len,
-                                                uint32_t& best, uint32_t& bdist, int lane) {
+__device__ __forceinline__ uint32_t word_at(const uint32_t* __restrict__ W, int w, int w_last) {
+    return w <= w_last ? W[w] : 0u;
+}
+
+__device__ __noinline__ void finish_position(const uint8_t* __restrict__ S, int xi, int x_end,
+                                             uint32_t reach, uint32_t room, uint32_t min_len,
+                                             uint32_t& best, uint32_t& bdist, int lane) {
     const uint32_t* W = reinterpret_cast<const uint32_t*>(S);
+    const int w_last = (x_end - 1) >> 2;
     uint32_t d0 = bdist + 1;
     while (d0 <= reach && best < room) {
         const uint32_t need = max(best + 1, min_len);
@@ -104,47 +115,46 @@ __device__ __forceinline__ void finish_position(const uint8_t* __restrict__ S, i
         const uint32_t mask = need >= 4 ? 0xFFFFFFFFu : (0xFFFFFFFFu >> (8 * (4 - need)));
         const int a = xi + (int)o;                         // anchor: candidate d starts at a - d
         const int wa = a >> 2;
-        const uint32_t key = fsr(W[wa], W[wa + 1], (a & 3) * 8) & mask;
-        // lanes walk aligned words downward from the one holding candidate d0
+        const uint32_t key = fsr(word_at(W, wa, w_last), word_at(W, wa + 1, w_last), (a & 3) * 8) & mask;
         const int c_hi = a - (int)d0;                      // nearest candidate still open
         const int c_lo = a - (int)reach;                   // farthest candidate
-        int w = (c_hi >> 2) - lane;
-        uint32_t hit_d = 0;
-        for (;;) {
+        bool improved = false;
+        for (int wtop = c_hi >> 2; (wtop << 2) + 3 >= c_lo && !improved; wtop -= 32) {
+            const int w = wtop - lane;                     // lane 0 holds the nearest word
             uint32_t hb = 0;
             if ((w << 2) + 3 >= c_lo) {
-                const uint32_t low = W[w], hiw = W[w + 1];
+                const uint32_t low = W[w], hiw = word_at(W, w + 1, w_last);
                 const uint32_t t0 = (low ^ key) & mask;
                 const uint32_t t1 = (__byte_perm(low, hiw, 0x4321) ^ key) & mask;
                 const uint32_t t2 = (__byte_perm(low, hiw, 0x5432) ^ key) & mask;
                 const uint32_t t3 = (__byte_perm(low, hiw, 0x6543) ^ key) & mask;
                 hb = (t0 == 0 ? 1u : 0u) | (t1 == 0 ? 2u : 0u) | (t2 == 0 ? 4u : 0u) | (t3 == 0 ? 8u : 0u);
-                const int kmax = min(3, c_hi - (w << 2));  // only lane 0's word can be cut at the top
+                const int kmax = min(3, c_hi - (w << 2));  // only the very first word is cut at the top
                 const int kmin = max(0, c_lo - (w << 2));
                 hb &= (2u << kmax) - 1u;
                 hb &= ~((1u << kmin) - 1u);
             }
-            const uint32_t any = __ballot_sync(0xFFFFFFFFu, hb != 0);
-            if (any != 0) {
-                const int src = __ffs((int)any) - 1;                        // lowest lane = nearest word
-                const int c = (w << 2) + (31 - __clz((int)hb | 1));         // nearest candidate in my word
-                hit_d = (uint32_t)(a - __shfl_sync(0xFFFFFFFFu, c, src));
-                break;
+            for (;;) {
+                const uint32_t any = __ballot_sync(0xFFFFFFFFu, hb != 0);
+                if (any == 0) { break; }
+                const int src = __ffs((int)any) - 1;                       // lowest lane = nearest word
+                const int kk = 31 - __clz((int)(hb | 1u));                 // nearest candidate in my word
+                const int c = __shfl_sync(0xFFFFFFFFu, (w << 2) + kk, src);
+                const uint32_t hit_d = (uint32_t)(a - c);
+                // cooperative verify: common prefix of S[xi..] and S[xi-hit_d..], capped at room
+                uint32_t m = room;
+                for (uint32_t base = 0; base < room; base += 32) {
+                    const uint32_t k = base + (uint32_t)lane;
+                    const bool diff = k < room && S[xi + (int)k] != S[xi - (int)hit_d + (int)k];
+                    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, diff);
+                    if (bal != 0) { m = base + (uint32_t)(__ffs((int)bal) - 1); break; }
+                }
+                if (m >= need) { best = m; bdist = hit_d; improved = true; break; }
+                if (lane == src) { hb &= ~(1u << kk); }
             }
-            w -= 32;
-            if (((w + lane) << 2) + 3 < c_lo) { break; }                    // lane 0's word is past the end
         }
-        if (hit_d == 0) { break; }
-        // cooperative verify: common prefix of S[xi..] and S[xi-hit_d..], capped at room
-        uint32_t m = room;
-        for (uint32_t base = 0; base < room; base += 32) {
-            const uint32_t k = base + (uint32_t)lane;
-            const bool diff = k < room && S[xi + (int)k] != S[xi - (int)hit_d + (int)k];
-            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, diff);
-            if (bal != 0) { m = base + (uint32_t)(__ffs((int)bal) - 1); break; }
-        }
-        if (m >= need) { best = m; bdist = hit_d; }
-        d0 = hit_d + 1;
+        if (!improved) { break; }
+        d0 = bdist + 1;
     }
 }
 
@@ -152,6 +162,7 @@ template <int kMinLen, bool kEdge>
 __global__ void __launch_bounds__(kThreads)
 match_table(const uint8_t* __restrict__ shard, long long back, long long n, long long ahead,
             uint32_t max_len, uint32_t max_dist, uint32_t* __restrict__ table, int tile_first,
+            uint32_t* __restrict__ list, unsigned int* __restrict__ list_count, uint32_t list_cap,
             unsigned long long* __restrict__ tile_cycles) {
     const long long t_begin = clock64();
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -315,38 +326,84 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
         }
     }
 
-    // ---- phase 2: finish the handed-over positions on raw bytes -------------------
+    // ---- hand-over: queue the marked positions for the finish kernel -------------
     if (__syncthreads_or(handed) != 0) {               // everybody is done with the planes
-    const long long raw_lo = max(tile_pos0 - (long long)max_dist, -back);         // first byte staged
-    const long long raw_hi = min(tile_pos0 + kTilePos + (long long)max_len, n + ahead);
-    const int shift = (int)(reinterpret_cast<uintptr_t>(shard + raw_lo) & 3);     // keep word alignment
-    uint8_t* S = smem_raw;
-    {
-        const int span = shift + (int)(raw_hi - raw_lo);
-        for (int k = threadIdx.x; k < span + 8; k += kThreads) {
-            const int g = k - shift;
-            S[k] = (g >= 0 && k < span) ? __ldg(shard + raw_lo + g) : (uint8_t)0;
+        int failed = 0;
+        for (int base = warp * 32; base < kTilePos; base += kWarps * 32) {
+            const bool mark = best_len[base + lane] == kHandOver;
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, mark);
+            if (bal == 0) { continue; }
+            uint32_t idx0 = 0;
+            if (lane == 0) { idx0 = atomicAdd(list_count, (unsigned int)__popc(bal)); }
+            idx0 = __shfl_sync(0xFFFFFFFFu, idx0, 0);
+            const uint32_t mine = idx0 + (uint32_t)__popc(bal & ((1u << lane) - 1u));
+            if (mark) {
+                if (mine < list_cap) {
+                    list[mine] = (uint32_t)(tile_pos0 + base + lane);
+                    best_len[base + lane] = kFinished;
+                } else {
+                    failed = 1;                        // queue full: finish it right here
+                }
+            }
         }
-    }
-    __syncthreads();
-    for (int base = warp * 32; base < kTilePos; base += kWarps * 32) {
-        uint32_t marks = __ballot_sync(0xFFFFFFFFu, best_len[base + lane] == kHandOver);
-        while (marks != 0) {
-            const int k = base + __ffs((int)marks) - 1;
-            marks &= marks - 1;
-            const long long p = tile_pos0 + k;
-            const uint32_t word = table[p];
-            uint32_t best = word >> 16, bdist = word & 0xFFFFu;
-            const uint32_t room = (uint32_t)min((long long)max_len, n + ahead - p);
-            const uint32_t far = (uint32_t)min((long long)max_dist, p + back);
-            finish_position(S, shift + (int)(p - raw_lo), far, room, (uint32_t)kMinLen, best, bdist, lane);
-            if (lane == 0) { table[p] = best >= (uint32_t)kMinLen ? ((best << 16) | bdist) : 0u; }
+        if (__syncthreads_or(failed) != 0) {
+            // fallback: restage the raw bytes of the window over the planes and finish in place
+            const long long raw_lo = max(tile_pos0 - (long long)max_dist, -back);
+            const long long raw_hi = min(tile_pos0 + kTilePos + (long long)max_len, n + ahead);
+            uint8_t* S = smem_raw;
+            const int span = (int)(raw_hi - raw_lo);
+            for (int k = threadIdx.x; k < span; k += kThreads) { S[k] = __ldg(shard + raw_lo + k); }
+            __syncthreads();
+            for (int base = warp * 32; base < kTilePos; base += kWarps * 32) {
+                uint32_t marks = __ballot_sync(0xFFFFFFFFu, best_len[base + lane] == kHandOver);
+                while (marks != 0) {
+                    const int k = base + __ffs((int)marks) - 1;
+                    marks &= marks - 1;
+                    const long long p = tile_pos0 + k;
+                    const uint32_t word = table[p];
+                    uint32_t best = word >> 16, bdist = word & 0xFFFFu;
+                    const uint32_t room = (uint32_t)min((long long)max_len, n + ahead - p);
+                    const uint32_t far = (uint32_t)min((long long)max_dist, p + back);
+                    finish_position(S, (int)(p - raw_lo), span, far, room, (uint32_t)kMinLen, best, bdist, lane);
+                    if (lane == 0) { table[p] = best >= (uint32_t)kMinLen ? ((best << 16) | bdist) : 0u; }
+                }
+            }
         }
-    }
     }
     if (tile_cycles != nullptr) {          // debugging aid: per-tile duration
         __syncthreads();
         if (threadIdx.x == 0) { tile_cycles[tile] = (unsigned long long)(clock64() - t_begin); }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// phase 2 kernel: the queued positions, one warp each, bytes read from global
+// memory (the queue is short and its entries cluster, so L1/L2 serve them).
+// counters[0] = entries queued (may exceed the capacity), counters[1] = cursor.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+finish_list(const uint8_t* __restrict__ shard, long long back, long long n, long long ahead,
+            uint32_t min_len, uint32_t max_len, uint32_t max_dist, uint32_t* __restrict__ table,
+            const uint32_t* __restrict__ list, unsigned int* __restrict__ counters, uint32_t list_cap) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t total = min(counters[0], list_cap);
+    for (;;) {
+        uint32_t idx = 0;
+        if (lane == 0) { idx = atomicAdd(counters + 1, 1u); }
+        idx = __shfl_sync(0xFFFFFFFFu, idx, 0);
+        if (idx >= total) { break; }
+        const long long p = (long long)list[idx];
+        const uint32_t word = table[p];
+        uint32_t best = word >> 16, bdist = word & 0xFFFFu;
+        const uint32_t room = (uint32_t)min((long long)max_len, n + ahead - p);
+        const uint32_t far = (uint32_t)min((long long)max_dist, p + back);
+        // local byte image: starts at the farthest candidate, rounded down to a word
+        const uint8_t* lo = shard + p - (long long)far;
+        const int mis = (int)(reinterpret_cast<uintptr_t>(lo) & 3);
+        const long long left = n + ahead - p;
+        const int x_end = mis + (int)far + (int)min(left, (long long)max_len + 8);
+        finish_position(lo - mis, mis + (int)far, x_end, far, room, min_len, best, bdist, lane);
+        if (lane == 0) { table[p] = best >= min_len ? ((best << 16) | bdist) : 0u; }
     }
 }
 
