@@ -243,9 +243,10 @@ def ours(args) -> None:
             # chain on the host picks the real one.  One integer per seam, no payload collective.
             check(L.sqz_gpu_parse_exit_map_device(d_table.data_ptr(), n, MIN_LEN, MAX_LEN,
                                                   d_work.data_ptr(), d_map.data_ptr(), s), "exit_map")
-            maps = [torch.empty_like(d_map) for _ in range(world)]
-            dist.all_gather(maps, d_map)
-            hm = torch.stack(maps).cpu().numpy().astype(np.int64) & 0xFFFF
+            # 512 x u16 travel as 256 x i32 (NCCL has no 16-bit integer type)
+            maps = [torch.empty(256, dtype=torch.int32, device=dev) for _ in range(world)]
+            dist.all_gather(maps, d_map.view(torch.int32))
+            hm = torch.stack(maps).cpu().numpy().view(np.uint16)
             for r in range(rank):
                 entry = int(hm[r, entry])
         check(L.sqz_gpu_parse_device(shard_ptr, d_table.data_ptr(), n, entry, MIN_LEN, MAX_LEN,

@@ -104,9 +104,11 @@ __device__ __forceinline__ uint32_t word_at(const uint32_t* __restrict__ W, int 
 
 __device__ __noinline__ void finish_position(const uint8_t* __restrict__ S, int xi, int x_end,
                                              uint32_t reach, uint32_t room, uint32_t min_len,
-                                             uint32_t& best, uint32_t& bdist, int lane) {
+                                             uint32_t& best, uint32_t& bdist, int lane,
+                                             unsigned long long* dbg = nullptr) {
     const uint32_t* W = reinterpret_cast<const uint32_t*>(S);
     const int w_last = (x_end - 1) >> 2;
+    unsigned int n_steps = 0, n_verify = 0, n_rounds = 0, n_improve = 0;
     uint32_t d0 = bdist + 1;
     while (d0 <= reach && best < room) {
         const uint32_t need = max(best + 1, min_len);
@@ -122,6 +124,7 @@ __device__ __noinline__ void finish_position(const uint8_t* __restrict__ S, int 
         for (int wtop = c_hi >> 2; (wtop << 2) + 3 >= c_lo && !improved; wtop -= 32) {
             const int w = wtop - lane;                     // lane 0 holds the nearest word
             uint32_t hb = 0;
+            n_steps++;
             if ((w << 2) + 3 >= c_lo) {
                 const uint32_t low = W[w], hiw = word_at(W, w + 1, w_last);
                 const uint32_t t0 = (low ^ key) & mask;
@@ -143,18 +146,25 @@ __device__ __noinline__ void finish_position(const uint8_t* __restrict__ S, int 
                 const uint32_t hit_d = (uint32_t)(a - c);
                 // cooperative verify: common prefix of S[xi..] and S[xi-hit_d..], capped at room
                 uint32_t m = room;
+                n_verify++;
                 for (uint32_t base = 0; base < room; base += 32) {
+                    n_rounds++;
                     const uint32_t k = base + (uint32_t)lane;
                     const bool diff = k < room && S[xi + (int)k] != S[xi - (int)hit_d + (int)k];
                     const uint32_t bal = __ballot_sync(0xFFFFFFFFu, diff);
                     if (bal != 0) { m = base + (uint32_t)(__ffs((int)bal) - 1); break; }
                 }
-                if (m >= need) { best = m; bdist = hit_d; improved = true; break; }
+                if (m >= need) { best = m; bdist = hit_d; improved = true; n_improve++; break; }
                 if (lane == src) { hb &= ~(1u << kk); }
             }
         }
         if (!improved) { break; }
         d0 = bdist + 1;
+    }
+    if (dbg != nullptr && lane == 0) {
+        atomicAdd(dbg + 0, 1ull); atomicAdd(dbg + 1, (unsigned long long)n_steps);
+        atomicAdd(dbg + 2, (unsigned long long)n_verify); atomicAdd(dbg + 3, (unsigned long long)n_improve);
+        atomicAdd(dbg + 4, (unsigned long long)n_rounds);
     }
 }
 
@@ -384,7 +394,8 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
 __global__ void __launch_bounds__(kThreads)
 finish_list(const uint8_t* __restrict__ shard, long long back, long long n, long long ahead,
             uint32_t min_len, uint32_t max_len, uint32_t max_dist, uint32_t* __restrict__ table,
-            const uint32_t* __restrict__ list, unsigned int* __restrict__ counters, uint32_t list_cap) {
+            const uint32_t* __restrict__ list, unsigned int* __restrict__ counters, uint32_t list_cap,
+            unsigned long long* __restrict__ dbg) {
     const int lane = threadIdx.x & 31;
     const uint32_t total = min(counters[0], list_cap);
     for (;;) {
@@ -402,7 +413,7 @@ finish_list(const uint8_t* __restrict__ shard, long long back, long long n, long
         const int mis = (int)(reinterpret_cast<uintptr_t>(lo) & 3);
         const long long left = n + ahead - p;
         const int x_end = mis + (int)far + (int)min(left, (long long)max_len + 8);
-        finish_position(lo - mis, mis + (int)far, x_end, far, room, min_len, best, bdist, lane);
+        finish_position(lo - mis, mis + (int)far, x_end, far, room, min_len, best, bdist, lane, dbg);
         if (lane == 0) { table[p] = best >= min_len ? ((best << 16) | bdist) : 0u; }
     }
 }

@@ -551,7 +551,7 @@ static int launch_v2(const uint8_t* d_shard, size_t back, size_t n, size_t ahead
     }
     v2::finish_list<<<148 * 8, v2::kThreads, 0, s>>>(d_shard, (long long)back, (long long)n, (long long)ahead,
                                                    (uint32_t)kMinLen, max_len, max_dist, d_table, d_list,
-                                                   d_counters, list_cap);
+                                                   d_counters, list_cap, g_tile_cycles ? g_tile_cycles + (1 << 20) : nullptr);
     LAUNCHED("match_finish_list");
     CU(cudaFreeAsync(d_list, s));
     return 0;

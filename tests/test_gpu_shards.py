@@ -1,0 +1,181 @@
+"""GPU parity beyond whole files: rule sets, shards with halos through the device ABI, the
+chunked streaming pipeline, seam hand-off, and size-independent properties at larger sizes."""
+import numpy as np
+import pytest
+
+import sqz_b200 as sq
+from sqz_b200 import corpus, shard
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(params=[2, 1], ids=["bitsliced", "per_position"])
+def kernel(request):
+    sq.select_kernel(request.param)
+    yield request.param
+    sq.select_kernel(0)
+
+
+def unpack(t):
+    w = t.cpu().numpy().view(np.uint32)
+    return (w >> 16).astype(np.uint16), (w & 0xFFFF).astype(np.uint16)
+
+
+RULES = [(3, 257, None), (2, 254, None), (2, 254, "window"), (3, 20, None), (3, 40, 100), (2, 31, 5),
+         (4, 16, None), (1, 8, 300), (3, 512, None)]
+
+
+@pytest.mark.parametrize("rules", RULES)
+@pytest.mark.parametrize("name,lo,hi", [("laozi.txt", 0, 20760), ("x64.elf", 902000, 926536), ("arm64.elf", 100000, 140000)])
+def test_rule_sets(rules, name, lo, hi, inputs, oracle, kernel):
+    """min_len / max_len / max_dist are runtime parameters (three rule sets in the reference)."""
+    d = np.ascontiguousarray(inputs[name][lo:hi])
+    mn, mx, md = rules
+    for window in (1 << 10, 1 << 15):
+        dist = window if md == "window" else (window - 1 if md is None else md)
+        ln, ds = sq.match_table(d, window, mn, mx, dist)
+        oln, ods = oracle.match_table(d, window, fast=True, min_len=mn, max_len=mx, max_dist=dist)
+        bad = np.nonzero((ln != oln) | (ds != ods))[0]
+        assert bad.size == 0, (rules, window, bad[:5], ln[bad[:5]], oln[bad[:5]], ds[bad[:5]], ods[bad[:5]])
+        t = sq.tokens(d, window, mn, mx, dist)
+        ot, end = oracle.tokens_from_table(d, oln, ods, mn)
+        assert end == d.size and t.size == ot.size and (t == ot).all()
+
+
+def test_rule_set_iii_against_bst_c(inputs, reference):
+    d = np.ascontiguousarray(inputs["x64.elf"][904000:909000])
+    rl, rd = reference.bst_table(d, 1024)
+    ln, ds = sq.match_table(d, 1 << 16, 2, 254, 1024)
+    assert (rl == ln).all() and (rd == ds).all()
+
+
+def test_bad_rules_are_einval():
+    import errno
+    for args in [(1 << 15, 3, 2, 100), (1 << 15, 0, 10, 100), (1 << 15, 3, 513, 100), (1 << 15, 3, 257, 0),
+                 (1 << 16, 3, 257, 65536), (1000, 3, 257, 999), (1 << 10, 3, 257, 2000)]:
+        with pytest.raises(sq.SqzError) as e:
+            sq.match_table(b"abcabcabcabc", *args)
+        assert e.value.errno == errno.EINVAL
+
+
+@pytest.mark.parametrize("first,n", [(0, 1), (0, 31), (0, 15872), (5, 15873), (40000, 70001), (32767, 4000),
+                                     (100001, 15872 * 3), (250000, 33), (299000, 1000)])
+def test_shard_with_halos_device_abi(first, n, oracle, kernel):
+    """A shard sees only its bytes + halos and must reproduce the whole-buffer table."""
+    from sqz_b200 import device
+    total = 300000
+    data = corpus.synthetic(total, 3276897 - 150000)
+    oln, ods = oracle.match_table(data, 1 << 15, fast=True)
+    back, ahead = min(first, 32767), min(total - first - n, 257)
+    lo, hi = first - back, first + n + ahead
+    # hand the kernel nothing but the shard + halos, at an odd address
+    buf = torch.zeros(hi - lo + 3 + 64, dtype=torch.uint8, device="cuda")
+    buf[3:3 + hi - lo] = torch.from_numpy(data[lo:hi]).cuda()
+    t = device.match_table(buf, 3 + back, n, back, ahead)
+    ln, ds = unpack(t)
+    bad = np.nonzero((ln != oln[first:first + n]) | (ds != ods[first:first + n]))[0]
+    assert bad.size == 0, (first, n, bad[:5], ln[bad[:5]], oln[first:first + n][bad[:5]])
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_seam_hand_off_between_shards(world, oracle):
+    """Shards parsed independently + exit-map chain == one parse of the whole input."""
+    from sqz_b200 import device
+    total = 200000
+    data = corpus.synthetic(total, 1000)
+    whole = oracle.tokens_from_table(data, *oracle.match_table(data, 1 << 15, fast=True))[0]
+    dev = torch.from_numpy(data).cuda()
+    dev = torch.cat([dev, torch.zeros(64, dtype=torch.uint8, device="cuda")])
+    plan = shard.plan(total, world, 32767, 257)
+    tables = [device.match_table(dev, s.first, s.n, s.back, s.ahead) for s in plan]
+    maps = [device.exit_map(t, s.n).cpu().numpy().view(np.uint16) for t, s in zip(tables, plan)]
+    entries = shard.chain_entries(maps)
+    assert entries[-1] == 0
+    parts = []
+    for s, t, e in zip(plan, tables, entries):
+        tok, over = device.parse(dev, s.first, t, s.n, e)
+        assert over == entries[s.rank + 1]
+        parts.append(tok.cpu().numpy().view(np.uint32))
+    cat = np.concatenate(parts)
+    assert cat.size == whole.size and (cat == whole).all()
+
+
+@pytest.mark.parametrize("chunk", [4096, 50001, 65536, 1 << 20])
+def test_streaming_pipeline_chunk_sizes(chunk, inputs, oracle):
+    """sqz_gpu_stream_*: any chunking of the input gives the same token stream."""
+    import ctypes as C
+    from sqz_b200 import _lib
+    L = _lib.load()
+    d = np.concatenate([inputs["confucius.txt"], inputs["x64.elf"][:200000], inputs["mandrill.bmp"][:50000]])
+    want = oracle.tokens_from_table(d, *oracle.match_table(d, 1 << 15, fast=True))[0]
+    st = C.c_void_p()
+    rc = L.sqz_gpu_stream_open(C.byref(st), 0, d.ctypes.data_as(_lib.u8p), d.size, 1 << 15, 3, 257, 32767, chunk)
+    assert rc == 0, L.sqz_gpu_last_error()
+    got = []
+    while True:
+        p, n = _lib.u32p(), C.c_size_t()
+        rc = L.sqz_gpu_stream_next(st, C.byref(p), C.byref(n))
+        assert rc == 0, L.sqz_gpu_last_error()
+        if n.value == 0:
+            break
+        got.append(np.ctypeslib.as_array(p, shape=(n.value,)).copy())
+    L.sqz_gpu_stream_close(st)
+    got = np.concatenate(got)
+    assert got.size == want.size and (got == want).all()
+
+
+def lz77_decode(tokens, n):
+    """Independent check of a token stream: plain LZ77 expansion."""
+    out = np.zeros(n, np.uint8)
+    i = 0
+    for t in tokens.tolist():
+        ln, ds = t >> 16, t & 0xFFFF
+        if ln == 0:
+            out[i] = t
+            i += 1
+        else:
+            for k in range(ln):
+                out[i + k] = out[i + k - ds]
+            i += ln
+    assert i == n
+    return out
+
+
+def test_tokens_expand_to_the_input(inputs):
+    d = np.concatenate([inputs["laozi.txt"], inputs["arm64.elf"][820000:]])
+    assert (lz77_decode(sq.tokens(d), d.size) == d).all()
+
+
+def test_large_synthetic_full_table_and_round_trip(oracle, reference):
+    """48 MiB of the bench corpus (two pipeline chunks): full table == oracle B, the compressed
+    stream round-trips through OUR decoder and through the REFERENCE decoder, and its size is
+    the size the reference's own encoder produces for the oracle's tokens."""
+    n = 48 << 20
+    d = corpus.synthetic(n, 0)
+    ln, ds = sq.match_table(d)
+    oln, ods = oracle.match_table(d, 1 << 15, fast=True)
+    assert (ln == oln).all() and (ds == ods).all()
+    t = sq.tokens(d)
+    ot, end = oracle.tokens_from_table(d, oln, ods)
+    assert end == n and t.size == ot.size and (t == ot).all()
+    part = np.ascontiguousarray(d[: 6 << 20])
+    stats = {}
+    comp = sq.compress(part, 15, stats=stats)
+    assert stats["tokens"] > 0 and sq.decompress(comp) == part.tobytes()
+    assert reference.decompress(comp) == part.tobytes()
+    pt = sq.tokens(part)
+    assert reference.encode_tokens(pt, part.size, 15) == comp
+
+
+def test_sampled_positions_against_the_brute_force_oracle(oracle):
+    """Oracle A (the restated reference loop) on seeded-random positions and around seams."""
+    n = 8 << 20
+    d = corpus.synthetic(n, 5 * 3276897 - (4 << 20))
+    ln, ds = sq.match_table(d)
+    rng = np.random.default_rng(3)
+    pos = np.unique(np.concatenate([rng.integers(0, n, 1500), np.arange(0, 300), np.arange(n - 300, n),
+                                    np.arange((4 << 20) - 150, (4 << 20) + 150)]))
+    for i in pos.tolist():
+        assert oracle.best(d, i, 1 << 15) == (int(ln[i]), int(ds[i])), i

@@ -11,7 +11,7 @@ pad = torch.zeros(size + 1024, dtype=torch.uint8, device="cuda"); pad[:size] = d
 table = torch.empty(size, dtype=torch.int32, device="cuda")
 TP = 15872
 tiles = (size + TP - 1) // TP
-cyc = torch.zeros(tiles, dtype=torch.int64, device="cuda")
+cyc = torch.zeros((1 << 20) + 16, dtype=torch.int64, device="cuda")
 L.sqz_gpu_debug_tile_cycles(cyc.data_ptr())
 for it in range(2):
     torch.cuda.synchronize()
@@ -20,7 +20,8 @@ for it in range(2):
     rc = L.sqz_gpu_match_table_device(pad.data_ptr(), 0, size, 0, 3, 257, 32767, table.data_ptr(), torch.cuda.current_stream().cuda_stream)
     e1.record(); torch.cuda.synchronize()
     print("rc", rc, "ms", e0.elapsed_time(e1))
-c = cyc.cpu().numpy()
+call = cyc.cpu().numpy(); c = call[:tiles]; dbg = call[1 << 20:] // 2
+print('finish: positions %d (%.2f%%), word-steps/pos %.1f, verifies/pos %.1f, improvements/pos %.2f, verify rounds/pos %.1f' % (dbg[0], 100.0*dbg[0]/size, dbg[1]/max(dbg[0],1), dbg[2]/max(dbg[0],1), dbg[3]/max(dbg[0],1), dbg[4]/max(dbg[0],1)))
 print("tiles", tiles, "sum Gcyc", c.sum() / 1e9, "median", np.median(c), "p90", np.percentile(c, 90), "max", c.max())
 order = np.argsort(-c)[:12]
 B = corpus.base().size
