@@ -102,6 +102,30 @@ __device__ __forceinline__ uint32_t word_at(const uint32_t* __restrict__ W, int 
     return w <= w_last ? W[w] : 0u;
 }
 
+// 4 bytes starting at byte index x of the image
+__device__ __forceinline__ uint32_t bytes_at(const uint32_t* __restrict__ W, int x, int w_last) {
+    const int w = x >> 2;
+    return fsr(word_at(W, w, w_last), word_at(W, w + 1, w_last), (x & 3) * 8);
+}
+
+// Among the 4-byte windows inside the first `best` bytes of the position pick the one a
+// random candidate is least likely to share: most distinct byte values, earliest on ties
+// (far from the window at the end that the main filter already tests).  -1 if none fits.
+__device__ __forceinline__ int pick_second_window(const uint32_t* __restrict__ W, int xi, uint32_t best,
+                                                  int w_last, int lane) {
+    if (best < 4) { return -1; }
+    uint32_t mine = 0;
+    for (int k = lane; k + 4 <= (int)best; k += 32) {
+        const uint32_t x = bytes_at(W, xi + k, w_last);
+        const uint32_t b0 = x & 0xFF, b1 = (x >> 8) & 0xFF, b2 = (x >> 16) & 0xFF, b3 = x >> 24;
+        const uint32_t score = (b0 != b1) + (b0 != b2) + (b0 != b3) + (b1 != b2) + (b1 != b3) + (b2 != b3);
+        mine = max(mine, ((score + 1) << 16) | (uint32_t)(0xFFFF - k));
+    }
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) { mine = max(mine, __shfl_xor_sync(0xFFFFFFFFu, mine, sft)); }
+    return 0xFFFF - (int)(mine & 0xFFFFu);
+}
+
 __device__ __noinline__ void finish_position(const uint8_t* __restrict__ S, int xi, int x_end,
                                              uint32_t reach, uint32_t room, uint32_t min_len,
                                              uint32_t& best, uint32_t& bdist, int lane,
@@ -113,11 +137,17 @@ __device__ __noinline__ void finish_position(const uint8_t* __restrict__ S, int 
     while (d0 <= reach && best < room) {
         const uint32_t need = max(best + 1, min_len);
         if (need > room) { break; }
+        // main filter: the 4 bytes ending at offset need-1 (exact dominance; a tie fails it)
         const uint32_t o = need >= 4 ? need - 4 : 0;
         const uint32_t mask = need >= 4 ? 0xFFFFFFFFu : (0xFFFFFFFFu >> (8 * (4 - need)));
         const int a = xi + (int)o;                         // anchor: candidate d starts at a - d
-        const int wa = a >> 2;
-        const uint32_t key = fsr(word_at(W, wa, w_last), word_at(W, wa + 1, w_last), (a & 3) * 8) & mask;
+        const uint32_t key = bytes_at(W, a, w_last) & mask;
+        // second filter: a distinctive window inside the bytes already matched
+        const int so = pick_second_window(W, xi, best, w_last, lane);
+        const uint32_t key2 = so >= 0 ? bytes_at(W, xi + so, w_last) : 0u;
+        const int delta = (int)o - so;                     // second window sits delta bytes before the first
+        const int dq = delta >> 2, dr = delta & 3;
+        const int back_words = dq + (dr ? 1 : 0), sh8 = dr ? 8 * (4 - dr) : 0;
         const int c_hi = a - (int)d0;                      // nearest candidate still open
         const int c_lo = a - (int)reach;                   // farthest candidate
         bool improved = false;
@@ -136,6 +166,19 @@ __device__ __noinline__ void finish_position(const uint8_t* __restrict__ S, int 
                 const int kmin = max(0, c_lo - (w << 2));
                 hb &= (2u << kmax) - 1u;
                 hb &= ~((1u << kmin) - 1u);
+                if (hb != 0 && so >= 0) {
+                    const int w2 = w - back_words;         // >= 0: the window lies inside the match
+                    // words below the image start can only feed candidates that are cut off anyway
+                    const uint32_t x0 = w2 >= 0 ? W[w2] : 0u;
+                    const uint32_t x1 = w2 + 1 >= 0 ? word_at(W, w2 + 1, w_last) : 0u;
+                    const uint32_t x2 = w2 + 2 >= 0 ? word_at(W, w2 + 2, w_last) : 0u;
+                    const uint32_t lo2 = fsr(x0, x1, sh8), hi2 = fsr(x1, x2, sh8);
+                    const uint32_t u0 = lo2 ^ key2;
+                    const uint32_t u1 = __byte_perm(lo2, hi2, 0x4321) ^ key2;
+                    const uint32_t u2 = __byte_perm(lo2, hi2, 0x5432) ^ key2;
+                    const uint32_t u3 = __byte_perm(lo2, hi2, 0x6543) ^ key2;
+                    hb &= (u0 == 0 ? 1u : 0u) | (u1 == 0 ? 2u : 0u) | (u2 == 0 ? 4u : 0u) | (u3 == 0 ? 8u : 0u);
+                }
             }
             for (;;) {
                 const uint32_t any = __ballot_sync(0xFFFFFFFFu, hb != 0);
