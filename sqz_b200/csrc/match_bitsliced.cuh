@@ -12,15 +12,14 @@
 //     i.e. one funnel shift + one LOP3 per plane: 17 integer instructions for
 //     32 candidate-compares, where a thread-per-position kernel needs 32 loads
 //     and 32 compares.
-//   * "A run of >= k equal bytes starts at i" is R_k = E & E>>1 & ... & E>>(k-1),
-//     built incrementally for k = min_len .. min_len+6 (bits shifted in from the
-//     next block).
-//   * Per-position state is bit-sliced too: three code planes hold, for each of
-//     the 32 positions, the run length a candidate has to reach to beat the
-//     position's current best: need = best+1, exact for need <= min_len+6
-//     (codes 0..6, code 6 also stands for anything longer); code 7 = closed.  An
-//     8-way bit-wise multiplexer picks R_need for every position at once, so
-//     a candidate that merely ties or falls short never leaves the fast path.
+//   * Per-position state is bit-sliced too: the run length a candidate has to
+//     reach to beat the position's current best, need = best+1 (exact up to
+//     min_len+6, anything longer counts as min_len+6), is kept as a thermometer
+//     of six masks G_k = "byte offset min_len+k has to match as well".  A
+//     candidate fails at position p iff one of its first need(p) bytes differs:
+//         fail = E' | E'>>1 | E'>>2 | (E'>>3 & G_0) | ... | (E'>>8 & G_5) | closed
+//     (E' = ~E, bits shifted in from the next block), so a candidate that merely
+//     ties or falls short never leaves the fast path.
 //   * Distances are visited in ascending order, exactly like the reference, so
 //     "strictly longer wins" keeps the nearest candidate among equals.
 //   * Survivors of the multiplexer take a scalar path: the run is measured from
@@ -261,7 +260,9 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
     const int blk0 = geo.back_blocks + own0;                // same, as plane block index
     uint32_t qv[kQ][8];
     uint32_t vq[kQ];
-    uint32_t L0[kQ], L1[kQ], L2[kQ];                        // bit-sliced need code per position
+    // need = best+1 per position, bit-sliced as a thermometer: G[k] bit p set = byte offset
+    // kMinLen+k has to match as well (need > kMinLen+k); closed = never a candidate again
+    uint32_t G[6][kQ], closed_m[kQ];
     int handed = 0;                                         // this thread left work for phase 2
 #pragma unroll
     for (int q = 0; q < kQ; q++) {
@@ -273,7 +274,9 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
         uint32_t closed = 0;
         if (lane == 31) { closed = 0xFFFFFFFFu; }
         else if (p0 + 32 > n) { closed = p0 >= n ? 0xFFFFFFFFu : (0xFFFFFFFFu << (int)(n - p0)); }
-        L0[q] = closed; L1[q] = closed; L2[q] = closed;     // code 7 = closed
+        closed_m[q] = closed;
+#pragma unroll
+        for (int k = 0; k < 6; k++) { G[k][q] = 0; }
         vq[q] = kEdge ? VL[blk0 + q] : 0xFFFFFFFFu;
     }
 
@@ -300,14 +303,9 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
             uint32_t eb[kQ + 1];
 #pragma unroll
             for (int q = 0; q < kQ; q++) {
-                uint32_t ea = fsr(cw[q][0], cw[q + 1][0], sh) ^ qv[q][0];
-                uint32_t ec = fsr(cw[q][4], cw[q + 1][4], sh) ^ qv[q][4];
+                uint32_t e = fsr(cw[q][0], cw[q + 1][0], sh) ^ qv[q][0];
 #pragma unroll
-                for (int b = 1; b < 4; b++) {
-                    ea |= fsr(cw[q][b], cw[q + 1][b], sh) ^ qv[q][b];
-                    ec |= fsr(cw[q][b + 4], cw[q + 1][b + 4], sh) ^ qv[q][b + 4];
-                }
-                uint32_t e = ea | ec;
+                for (int b = 1; b < 8; b++) { e |= fsr(cw[q][b], cw[q + 1][b], sh) ^ qv[q][b]; }
                 if (kEdge) { e |= ~vq[q] | ~fsr(vc[q], vc[q + 1], sh); }
                 eb[q] = e;
             }
@@ -316,22 +314,12 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
             uint32_t none = 0xFFFFFFFFu;
 #pragma unroll
             for (int q = 0; q < kQ; q++) {
-                uint32_t r[7];
+                // a candidate fails at position p if any of the first need(p) bytes differs
                 uint32_t acc = eb[q] | fsr(eb[q], eb[q + 1], 1);
                 if (kMinLen >= 3) { acc |= fsr(eb[q], eb[q + 1], 2); }
-                r[0] = acc;
 #pragma unroll
-                for (int k = 1; k < 7; k++) {
-                    acc |= fsr(eb[q], eb[q + 1], kMinLen - 1 + k);
-                    r[k] = acc;
-                }
-                const uint32_t m01 = mux(L0[q], r[0], r[1]);
-                const uint32_t m23 = mux(L0[q], r[2], r[3]);
-                const uint32_t m45 = mux(L0[q], r[4], r[5]);
-                const uint32_t m67 = r[6] | L0[q];                        // code 7: closed
-                const uint32_t m03 = mux(L1[q], m01, m23);
-                const uint32_t m47 = mux(L1[q], m45, m67);
-                ib[q] = mux(L2[q], m03, m47);
+                for (int k = 0; k < 6; k++) { acc |= fsr(eb[q], eb[q + 1], kMinLen + k) & G[k][q]; }
+                ib[q] = acc | closed_m[q];
                 none &= ib[q];
             }
             if (none != 0xFFFFFFFFu) {
@@ -348,31 +336,30 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                         const uint32_t have = state & 31u;
                         const uint32_t win = fsr(eb[q], eb[q + 1], p);  // E-bar from position p on
                         uint32_t run = win != 0 ? (uint32_t)(__ffs((int)win) - 1) : 32u;
-                        int code;
                         if (run >= max_len) {
                             // cannot be beaten any more: record and close
                             best_len[k] = kFinished;
                             table[tile_pos0 + k] = (max_len << 16) | d;
-                            code = 7;
+                            closed_m[q] |= bit;
                         } else if (win == 0) {
                             // at least 32 equal bytes: longer than the window, finish in phase 2
                             best_len[k] = kHandOver;
                             handed = 1;
-                            code = 7;
+                            closed_m[q] |= bit;
                         } else if (run > have) {
                             best_len[k] = (uint8_t)run;
                             table[tile_pos0 + k] = (run << 16) | d;
-                            code = min((int)run + 1 - kMinLen, 6);
+#pragma unroll
+                            for (int t = 0; t < 6; t++) {
+                                if (run >= (uint32_t)(kMinLen + t)) { G[t][q] |= bit; }
+                            }
                         } else {
                             // a candidate that only ties: count a sample of them; a position that
                             // keeps attracting them is cheaper to finish in phase 2
                             if ((d & 15u) != 0) { continue; }
-                            if (state >= 0xC0u) { best_len[k] = kHandOver; handed = 1; code = 7; }
-                            else { best_len[k] = (uint8_t)(state + 32u); continue; }
+                            if (state >= 0xC0u) { best_len[k] = kHandOver; handed = 1; closed_m[q] |= bit; }
+                            else { best_len[k] = (uint8_t)(state + 32u); }
                         }
-                        L0[q] = (code & 1) ? (L0[q] | bit) : (L0[q] & ~bit);
-                        L1[q] = (code & 2) ? (L1[q] | bit) : (L1[q] & ~bit);
-                        L2[q] = (code & 4) ? (L2[q] | bit) : (L2[q] & ~bit);
                     }
                 }
             }
