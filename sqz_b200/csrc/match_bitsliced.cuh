@@ -211,7 +211,7 @@ __device__ __noinline__ void finish_position(const uint8_t* __restrict__ S, int 
 }
 
 template <int kMinLen, bool kEdge>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 match_table(const uint8_t* __restrict__ shard, long long back, long long n, long long ahead,
             uint32_t max_len, uint32_t max_dist, uint32_t* __restrict__ table, int tile_first,
             uint32_t* __restrict__ list, unsigned int* __restrict__ list_count, uint32_t list_cap,
