@@ -26,13 +26,15 @@
 //     the same E bits (32-bit window), compared with the position's current
 //     best and recorded as (len, dist).
 //
-// Phase 2 (few positions, warp per position, same CTA):
+// Phase 2 (few positions, separate kernel finish_marked):
 //   Positions whose run leaves the 32-bit window (matches of >= 32 bytes, the
-//   ends of long byte runs) or that keep producing near-ties are handed over:
-//   the CTA restages the raw bytes of its window over the bit planes and every
-//   such position is finished by one warp with the classic exact search --
-//   32 lanes x 4 candidates per step, 4-byte compare at the offset a candidate
-//   must match to win, ballot for the nearest hit, cooperative verify.
+//   ends of long byte runs) or that keep producing near-ties are marked in the
+//   table and closed afterwards: by inheritance from the position above where
+//   that is provably exact (every position inside a long match but its last),
+//   else by the classic exact search with one warp per position -- 32 lanes x 4
+//   candidates per step, 4-byte compares at the offset a candidate must match to
+//   win and at the most distinctive window of the bytes already matched, ballot
+//   for the nearest hit, cooperative verify.
 //
 // Work split in phase 1: a thread owns kQ consecutive blocks (32*kQ positions)
 // for the whole scan, so all per-position state is private to one thread: no
@@ -53,6 +55,7 @@ constexpr int kTileBlocks = kWarps * kWarpOwned;      // owned blocks per CTA
 constexpr int kTilePos = kTileBlocks * 32;            // positions per CTA
 constexpr uint8_t kHandOver = 0xFF;       // best_len mark: finish this position in phase 2
 constexpr uint8_t kFinished = 0xFE;       // best_len mark: holds max_len, nothing left to do
+constexpr uint32_t kOpenBit = 0x80000000u; // table word mark: position is finished by the phase 2 kernel
 
 struct Geometry {            // identical for all CTAs of a launch
     int back_blocks;         // plane blocks staged before the tile: ceil(max_dist/32) + 1
@@ -214,7 +217,6 @@ template <int kMinLen, bool kEdge>
 __global__ void __launch_bounds__(kThreads, 3)
 match_table(const uint8_t* __restrict__ shard, long long back, long long n, long long ahead,
             uint32_t max_len, uint32_t max_dist, uint32_t* __restrict__ table, int tile_first,
-            uint32_t* __restrict__ list, unsigned int* __restrict__ list_count, uint32_t list_cap,
             unsigned long long* __restrict__ tile_cycles) {
     const long long t_begin = clock64();
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -263,7 +265,6 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
     // need = best+1 per position, bit-sliced as a thermometer: G[k] bit p set = byte offset
     // kMinLen+k has to match as well (need > kMinLen+k); closed = never a candidate again
     uint32_t G[6][kQ], closed_m[kQ];
-    int handed = 0;                                         // this thread left work for phase 2
 #pragma unroll
     for (int q = 0; q < kQ; q++) {
         const uint4 a = PL[2 * (blk0 + q)], b = PL[2 * (blk0 + q) + 1];
@@ -344,7 +345,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                         } else if (win == 0) {
                             // at least 32 equal bytes: longer than the window, finish in phase 2
                             best_len[k] = kHandOver;
-                            handed = 1;
+                            table[tile_pos0 + k] |= kOpenBit;
                             closed_m[q] |= bit;
                         } else if (run > have) {
                             best_len[k] = (uint8_t)run;
@@ -357,7 +358,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                             // a candidate that only ties: count a sample of them; a position that
                             // keeps attracting them is cheaper to finish in phase 2
                             if ((d & 15u) != 0) { continue; }
-                            if (state >= 0xC0u) { best_len[k] = kHandOver; handed = 1; closed_m[q] |= bit; }
+                            if (state >= 0xC0u) { best_len[k] = kHandOver; table[tile_pos0 + k] |= kOpenBit; closed_m[q] |= bit; }
                             else { best_len[k] = (uint8_t)(state + 32u); }
                         }
                     }
@@ -366,50 +367,6 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
         }
     }
 
-    // ---- hand-over: queue the marked positions for the finish kernel -------------
-    if (__syncthreads_or(handed) != 0) {               // everybody is done with the planes
-        int failed = 0;
-        for (int base = warp * 32; base < kTilePos; base += kWarps * 32) {
-            const bool mark = best_len[base + lane] == kHandOver;
-            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, mark);
-            if (bal == 0) { continue; }
-            uint32_t idx0 = 0;
-            if (lane == 0) { idx0 = atomicAdd(list_count, (unsigned int)__popc(bal)); }
-            idx0 = __shfl_sync(0xFFFFFFFFu, idx0, 0);
-            const uint32_t mine = idx0 + (uint32_t)__popc(bal & ((1u << lane) - 1u));
-            if (mark) {
-                if (mine < list_cap) {
-                    list[mine] = (uint32_t)(tile_pos0 + base + lane);
-                    best_len[base + lane] = kFinished;
-                } else {
-                    failed = 1;                        // queue full: finish it right here
-                }
-            }
-        }
-        if (__syncthreads_or(failed) != 0) {
-            // fallback: restage the raw bytes of the window over the planes and finish in place
-            const long long raw_lo = max(tile_pos0 - (long long)max_dist, -back);
-            const long long raw_hi = min(tile_pos0 + kTilePos + (long long)max_len, n + ahead);
-            uint8_t* S = smem_raw;
-            const int span = (int)(raw_hi - raw_lo);
-            for (int k = threadIdx.x; k < span; k += kThreads) { S[k] = __ldg(shard + raw_lo + k); }
-            __syncthreads();
-            for (int base = warp * 32; base < kTilePos; base += kWarps * 32) {
-                uint32_t marks = __ballot_sync(0xFFFFFFFFu, best_len[base + lane] == kHandOver);
-                while (marks != 0) {
-                    const int k = base + __ffs((int)marks) - 1;
-                    marks &= marks - 1;
-                    const long long p = tile_pos0 + k;
-                    const uint32_t word = table[p];
-                    uint32_t best = word >> 16, bdist = word & 0xFFFFu;
-                    const uint32_t room = (uint32_t)min((long long)max_len, n + ahead - p);
-                    const uint32_t far = (uint32_t)min((long long)max_dist, p + back);
-                    finish_position(S, (int)(p - raw_lo), span, far, room, (uint32_t)kMinLen, best, bdist, lane);
-                    if (lane == 0) { table[p] = best >= (uint32_t)kMinLen ? ((best << 16) | bdist) : 0u; }
-                }
-            }
-        }
-    }
     if (tile_cycles != nullptr) {          // debugging aid: per-tile duration
         __syncthreads();
         if (threadIdx.x == 0) { tile_cycles[tile] = (unsigned long long)(clock64() - t_begin); }
@@ -417,34 +374,77 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
 }
 
 // ---------------------------------------------------------------------------
-// phase 2 kernel: the queued positions, one warp each, bytes read from global
-// memory (the queue is short and its entries cluster, so L1/L2 serve them).
-// counters[0] = entries queued (may exceed the capacity), counters[1] = cursor.
+// phase 2 kernel.  Phase 1 left the open positions marked in the table itself
+// (bit 31).  A warp takes a segment of the table, walks it from the top down
+// and closes every marked position:
+//
+//   inheritance -- if position p+1 ended with (b', d'), b' < max_len, and byte p
+//     equals byte p-d', then position p ends with exactly (b'+1, d'): no
+//     candidate can give p more than b'+1 (it would give p+1 more than b'), and a
+//     nearer one with b'+1 would have been p+1's nearest b'.  Inside a long match
+//     every position but the last inherits, so a match costs one search, not one
+//     per position.
+//   search -- otherwise the exact warp-wide search (finish_position).
+//
+// counters[0] is the segment cursor.
 // ---------------------------------------------------------------------------
+constexpr int kSegment = 1024;            // positions per work item of phase 2
+
 __global__ void __launch_bounds__(kThreads)
-finish_list(const uint8_t* __restrict__ shard, long long back, long long n, long long ahead,
-            uint32_t min_len, uint32_t max_len, uint32_t max_dist, uint32_t* __restrict__ table,
-            const uint32_t* __restrict__ list, unsigned int* __restrict__ counters, uint32_t list_cap,
-            unsigned long long* __restrict__ dbg) {
+finish_marked(const uint8_t* __restrict__ shard, long long back, long long n, long long ahead,
+              uint32_t min_len, uint32_t max_len, uint32_t max_dist, uint32_t* __restrict__ table,
+              unsigned int* __restrict__ counters, unsigned long long* __restrict__ dbg) {
     const int lane = threadIdx.x & 31;
-    const uint32_t total = min(counters[0], list_cap);
+    const long long segments = (n + kSegment - 1) / kSegment;
     for (;;) {
-        uint32_t idx = 0;
-        if (lane == 0) { idx = atomicAdd(counters + 1, 1u); }
-        idx = __shfl_sync(0xFFFFFFFFu, idx, 0);
-        if (idx >= total) { break; }
-        const long long p = (long long)list[idx];
-        const uint32_t word = table[p];
-        uint32_t best = word >> 16, bdist = word & 0xFFFFu;
-        const uint32_t room = (uint32_t)min((long long)max_len, n + ahead - p);
-        const uint32_t far = (uint32_t)min((long long)max_dist, p + back);
-        // local byte image: starts at the farthest candidate, rounded down to a word
-        const uint8_t* lo = shard + p - (long long)far;
-        const int mis = (int)(reinterpret_cast<uintptr_t>(lo) & 3);
-        const long long left = n + ahead - p;
-        const int x_end = mis + (int)far + (int)min(left, (long long)max_len + 8);
-        finish_position(lo - mis, mis + (int)far, x_end, far, room, min_len, best, bdist, lane, dbg);
-        if (lane == 0) { table[p] = best >= min_len ? ((best << 16) | bdist) : 0u; }
+        unsigned int seg = 0;
+        if (lane == 0) { seg = atomicAdd(counters, 1u); }
+        seg = __shfl_sync(0xFFFFFFFFu, seg, 0);
+        if ((long long)seg >= segments) { break; }
+        const long long s0 = (long long)seg * kSegment;
+        const long long s1 = min(s0 + kSegment, n);
+        long long known_pos = -1;                      // position closed last by this warp ...
+        uint32_t known_word = 0;                       // ... and its final word
+        for (long long top = s1; top > s0; top -= 32) {
+            const long long i = top - 32 + lane;       // lanes ascend with position
+            const uint32_t mine = i >= s0 ? table[i] : 0u;
+            uint32_t marks = __ballot_sync(0xFFFFFFFFu, (mine & kOpenBit) != 0);
+            while (marks != 0) {
+                const int src = 31 - __clz((int)marks);             // highest position first
+                marks &= ~(1u << src);
+                const long long p = top - 32 + src;
+                const uint32_t word = __shfl_sync(0xFFFFFFFFu, mine, src) & ~kOpenBit;
+                uint32_t best = word >> 16, bdist = word & 0xFFFFu;
+                const uint32_t room = (uint32_t)min((long long)max_len, n + ahead - p);
+                const uint32_t far = (uint32_t)min((long long)max_dist, p + back);
+                // the neighbour above: closed by this warp a moment ago, or read from the table
+                uint32_t nb = 0;
+                if (p + 1 < n) { nb = (p + 1 == known_pos) ? known_word : table[p + 1]; }
+                const uint32_t nlen = (nb >> 16) & 0x7FFFu, ndist = nb & 0xFFFFu;
+                bool inherited = false;
+                if ((nb & kOpenBit) == 0 && nlen >= min_len && nlen < max_len && ndist <= far &&
+                    nlen + 1 <= room) {
+                    if (shard[p] == shard[p - (long long)ndist]) {
+                        best = nlen + 1;
+                        bdist = ndist;
+                        inherited = true;
+                    }
+                }
+                if (!inherited) {
+                    // local byte image: starts at the farthest candidate, rounded down to a word
+                    const uint8_t* lo = shard + p - (long long)far;
+                    const int mis = (int)(reinterpret_cast<uintptr_t>(lo) & 3);
+                    const long long left = n + ahead - p;
+                    const int x_end = mis + (int)far + (int)min(left, (long long)max_len + 8);
+                    finish_position(lo - mis, mis + (int)far, x_end, far, room, min_len, best, bdist, lane, dbg);
+                } else if (dbg != nullptr && lane == 0) {
+                    atomicAdd(dbg + 5, 1ull);
+                }
+                known_pos = p;
+                known_word = best >= min_len ? ((best << 16) | bdist) : 0u;
+                if (lane == 0) { table[p] = known_word; }
+            }
+        }
     }
 }
 

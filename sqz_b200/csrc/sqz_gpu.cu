@@ -526,34 +526,31 @@ static int launch_v2(const uint8_t* d_shard, size_t back, size_t n, size_t ahead
     t_lo = std::min(t_lo, tiles);
     t_hi = std::max(std::min(t_hi, tiles), t_lo);
     if ((unsigned long long)n > 0xFFFFFFFFull) { return fail(EINVAL, "shard too large for one launch"); }
-    // work queue of phase 2 (positions with long matches): stream-ordered scratch
-    const uint32_t list_cap = (uint32_t)std::min<size_t>(n / 8 + 4096, 0x7FFFFFFFu);
-    uint32_t* d_list = nullptr;
-    CU(cudaMallocAsync((void**)&d_list, (size_t)list_cap * 4 + 16, s));
-    unsigned int* d_counters = reinterpret_cast<unsigned int*>(d_list + list_cap);
-    CU(cudaMemsetAsync(d_counters, 0, 8, s));
+    unsigned int* d_counters = nullptr;               // segment cursor of phase 2 (stream-ordered scratch)
+    CU(cudaMallocAsync((void**)&d_counters, 16, s));
+    CU(cudaMemsetAsync(d_counters, 0, 16, s));
     const int smem_main = v2::geometry(max_len, max_dist, false).smem_bytes;
     const int smem_edge = v2::geometry(max_len, max_dist, true).smem_bytes;
     if (t_lo > 0) {
         v2::match_table<kMinLen, true><<<(unsigned)t_lo, v2::kThreads, smem_edge, s>>>(
-            d_shard, (long long)back, (long long)n, (long long)ahead, max_len, max_dist, d_table, 0, d_list, d_counters, list_cap, g_tile_cycles);
+            d_shard, (long long)back, (long long)n, (long long)ahead, max_len, max_dist, d_table, 0, g_tile_cycles);
         LAUNCHED("match_table_v2_edge");
     }
     if (t_hi > t_lo) {
         v2::match_table<kMinLen, false><<<(unsigned)(t_hi - t_lo), v2::kThreads, smem_main, s>>>(
-            d_shard, (long long)back, (long long)n, (long long)ahead, max_len, max_dist, d_table, (int)t_lo, d_list, d_counters, list_cap, g_tile_cycles);
+            d_shard, (long long)back, (long long)n, (long long)ahead, max_len, max_dist, d_table, (int)t_lo, g_tile_cycles);
         LAUNCHED("match_table_v2");
     }
     if (tiles > t_hi) {
         v2::match_table<kMinLen, true><<<(unsigned)(tiles - t_hi), v2::kThreads, smem_edge, s>>>(
-            d_shard, (long long)back, (long long)n, (long long)ahead, max_len, max_dist, d_table, (int)t_hi, d_list, d_counters, list_cap, g_tile_cycles);
+            d_shard, (long long)back, (long long)n, (long long)ahead, max_len, max_dist, d_table, (int)t_hi, g_tile_cycles);
         LAUNCHED("match_table_v2_edge");
     }
-    v2::finish_list<<<148 * 8, v2::kThreads, 0, s>>>(d_shard, (long long)back, (long long)n, (long long)ahead,
-                                                   (uint32_t)kMinLen, max_len, max_dist, d_table, d_list,
-                                                   d_counters, list_cap, g_tile_cycles ? g_tile_cycles + (1 << 20) : nullptr);
-    LAUNCHED("match_finish_list");
-    CU(cudaFreeAsync(d_list, s));
+    v2::finish_marked<<<148 * 8, v2::kThreads, 0, s>>>(d_shard, (long long)back, (long long)n, (long long)ahead,
+                                                     (uint32_t)kMinLen, max_len, max_dist, d_table, d_counters,
+                                                     g_tile_cycles ? g_tile_cycles + (1 << 20) : nullptr);
+    LAUNCHED("match_finish_marked");
+    CU(cudaFreeAsync(d_counters, s));
     return 0;
 }
 

@@ -21,7 +21,7 @@ for it in range(2):
     e1.record(); torch.cuda.synchronize()
     print("rc", rc, "ms", e0.elapsed_time(e1))
 call = cyc.cpu().numpy(); c = call[:tiles]; dbg = call[1 << 20:] // 2
-print('finish: positions %d (%.2f%%), word-steps/pos %.1f, verifies/pos %.1f, improvements/pos %.2f, verify rounds/pos %.1f' % (dbg[0], 100.0*dbg[0]/size, dbg[1]/max(dbg[0],1), dbg[2]/max(dbg[0],1), dbg[3]/max(dbg[0],1), dbg[4]/max(dbg[0],1)))
+print('finish: searched %d (%.3f%%), inherited %d (%.3f%%), word-steps/search %.1f, verifies/search %.1f, improvements/search %.2f' % (dbg[0], 100.0*dbg[0]/size, dbg[5], 100.0*dbg[5]/size, dbg[1]/max(dbg[0],1), dbg[2]/max(dbg[0],1), dbg[3]/max(dbg[0],1)))
 print("tiles", tiles, "sum Gcyc", c.sum() / 1e9, "median", np.median(c), "p90", np.percentile(c, 90), "max", c.max())
 order = np.argsort(-c)[:12]
 B = corpus.base().size
