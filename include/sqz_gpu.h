@@ -119,7 +119,7 @@ void        sqz_gpu_host_free(void* p);
  * 1 = thread-per-position, 2 = bit-sliced where applicable.  Both are exact;
  * the switch exists for A/B measurements and tests.                          */
 int         sqz_gpu_select_kernel(int which);
-/* Debugging aid: when d_buf (device, one u64 per tile of 15872 positions) is not
+/* Debugging aid: when d_buf (device, one u64 per tile of 16256 positions) is not
  * NULL the bit-sliced kernel stores every tile's duration in SM cycles.      */
 void        sqz_gpu_debug_tile_cycles(unsigned long long* d_buf);
 /* kernels launched by this library in this process so far (for bench.py)    */

@@ -50,7 +50,7 @@ namespace v2 {
 constexpr int kWarps = 4;                 // warps per CTA
 constexpr int kThreads = kWarps * 32;
 constexpr int kQ = 4;                     // blocks of 32 positions per thread
-constexpr int kWarpOwned = 31 * kQ;       // blocks a warp owns (lane 31 is look-ahead)
+constexpr int kWarpOwned = 32 * kQ - 1;   // blocks a warp owns; its last block is look-ahead only
 constexpr int kTileBlocks = kWarps * kWarpOwned;      // owned blocks per CTA
 constexpr int kTilePos = kTileBlocks * 32;            // positions per CTA
 constexpr uint8_t kHandOver = 0xFF;       // best_len mark: finish this position in phase 2
@@ -270,10 +270,10 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
         const uint4 a = PL[2 * (blk0 + q)], b = PL[2 * (blk0 + q) + 1];
         qv[q][0] = a.x; qv[q][1] = a.y; qv[q][2] = a.z; qv[q][3] = a.w;
         qv[q][4] = b.x; qv[q][5] = b.y; qv[q][6] = b.z; qv[q][7] = b.w;
-        // closed from the start: the look-ahead lane and positions past the shard
+        // closed from the start: the look-ahead block and positions past the shard
         const long long p0 = tile_pos0 + (long long)(own0 + q) * 32;
         uint32_t closed = 0;
-        if (lane == 31) { closed = 0xFFFFFFFFu; }
+        if (lane == 31 && q == kQ - 1) { closed = 0xFFFFFFFFu; }
         else if (p0 + 32 > n) { closed = p0 >= n ? 0xFFFFFFFFu : (0xFFFFFFFFu << (int)(n - p0)); }
         closed_m[q] = closed;
 #pragma unroll

@@ -531,9 +531,27 @@ static int launch_v2(const uint8_t* d_shard, size_t back, size_t n, size_t ahead
     CU(cudaMemsetAsync(d_counters, 0, 16, s));
     const int smem_main = v2::geometry(max_len, max_dist, false).smem_bytes;
     const int smem_edge = v2::geometry(max_len, max_dist, true).smem_bytes;
+    // The few edge tiles run on a side stream, concurrently with the interior tiles.
+    static cudaStream_t side = nullptr;
+    static std::once_flag side_once;
+    std::call_once(side_once, [] { cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking); });
+    const bool edges = t_lo > 0 || tiles > t_hi;
+    cudaStream_t es = side != nullptr ? side : s;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    if (edges && es != s) {
+        CU(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+        CU(cudaEventRecord(fork, s));
+        CU(cudaStreamWaitEvent(es, fork, 0));
+    }
     if (t_lo > 0) {
-        v2::match_table<kMinLen, true><<<(unsigned)t_lo, v2::kThreads, smem_edge, s>>>(
+        v2::match_table<kMinLen, true><<<(unsigned)t_lo, v2::kThreads, smem_edge, es>>>(
             d_shard, (long long)back, (long long)n, (long long)ahead, max_len, max_dist, d_table, 0, g_tile_cycles);
+        LAUNCHED("match_table_v2_edge");
+    }
+    if (tiles > t_hi) {
+        v2::match_table<kMinLen, true><<<(unsigned)(tiles - t_hi), v2::kThreads, smem_edge, es>>>(
+            d_shard, (long long)back, (long long)n, (long long)ahead, max_len, max_dist, d_table, (int)t_hi, g_tile_cycles);
         LAUNCHED("match_table_v2_edge");
     }
     if (t_hi > t_lo) {
@@ -541,10 +559,11 @@ static int launch_v2(const uint8_t* d_shard, size_t back, size_t n, size_t ahead
             d_shard, (long long)back, (long long)n, (long long)ahead, max_len, max_dist, d_table, (int)t_lo, g_tile_cycles);
         LAUNCHED("match_table_v2");
     }
-    if (tiles > t_hi) {
-        v2::match_table<kMinLen, true><<<(unsigned)(tiles - t_hi), v2::kThreads, smem_edge, s>>>(
-            d_shard, (long long)back, (long long)n, (long long)ahead, max_len, max_dist, d_table, (int)t_hi, g_tile_cycles);
-        LAUNCHED("match_table_v2_edge");
+    if (edges && es != s) {
+        CU(cudaEventRecord(join, es));
+        CU(cudaStreamWaitEvent(s, join, 0));
+        CU(cudaEventDestroy(fork));
+        CU(cudaEventDestroy(join));
     }
     v2::finish_marked<<<148 * 8, v2::kThreads, 0, s>>>(d_shard, (long long)back, (long long)n, (long long)ahead,
                                                      (uint32_t)kMinLen, max_len, max_dist, d_table, d_counters,

@@ -9,7 +9,7 @@ data = corpus.synthetic(size, 0)
 d = torch.from_numpy(data).cuda()
 pad = torch.zeros(size + 1024, dtype=torch.uint8, device="cuda"); pad[:size] = d
 table = torch.empty(size, dtype=torch.int32, device="cuda")
-TP = 15872
+TP = 4 * (32 * 4 - 1) * 32      # v2::kTilePos
 tiles = (size + TP - 1) // TP
 cyc = torch.zeros((1 << 20) + 16, dtype=torch.int64, device="cuda")
 L.sqz_gpu_debug_tile_cycles(cyc.data_ptr())
