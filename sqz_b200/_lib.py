@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libsqz_b200.so")
+# SQZ_B200_LIB points experiments at another build of the same ABI (tools/variants)
+LIB_PATH = os.environ.get("SQZ_B200_LIB") or os.path.join(HERE, "lib", "libsqz_b200.so")
 
 u8p = C.POINTER(C.c_uint8)
 u16p = C.POINTER(C.c_uint16)

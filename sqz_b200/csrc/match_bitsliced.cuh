@@ -14,10 +14,10 @@
 //     and 32 compares.
 //   * Per-position state is bit-sliced too: the run length a candidate has to
 //     reach to beat the position's current best, need = best+1 (exact up to
-//     min_len+6, anything longer counts as min_len+6), is kept as a thermometer
-//     of six masks G_k = "byte offset min_len+k has to match as well".  A
+//     min_len+4, anything longer counts as min_len+4), is kept as a thermometer
+//     of four masks G_k = "byte offset min_len+k has to match as well".  A
 //     candidate fails at position p iff one of its first need(p) bytes differs:
-//         fail = E' | E'>>1 | E'>>2 | (E'>>3 & G_0) | ... | (E'>>8 & G_5) | closed
+//         fail = E' | E'>>1 | E'>>2 | (E'>>3 & G_0) | ... | (E'>>6 & G_3) | closed
 //     (E' = ~E, bits shifted in from the next block), so a candidate that merely
 //     ties or falls short never leaves the fast path.
 //   * Distances are visited in ascending order, exactly like the reference, so
@@ -53,6 +53,10 @@ constexpr int kQ = 4;                     // blocks of 32 positions per thread
 constexpr int kWarpOwned = 32 * kQ - 1;   // blocks a warp owns; its last block is look-ahead only
 constexpr int kTileBlocks = kWarps * kWarpOwned;      // owned blocks per CTA
 constexpr int kTilePos = kTileBlocks * 32;            // positions per CTA
+#ifndef SQZ_GATED
+#define SQZ_GATED 4
+#endif
+constexpr int kGated = SQZ_GATED;         // need is tracked exactly up to min_len + kGated
 constexpr uint8_t kHandOver = 0xFF;       // best_len mark: finish this position in phase 2
 constexpr uint8_t kFinished = 0xFE;       // best_len mark: holds max_len, nothing left to do
 constexpr uint32_t kOpenBit = 0x80000000u; // table word mark: position is finished by the phase 2 kernel
@@ -264,7 +268,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
     uint32_t vq[kQ];
     // need = best+1 per position, bit-sliced as a thermometer: G[k] bit p set = byte offset
     // kMinLen+k has to match as well (need > kMinLen+k); closed = never a candidate again
-    uint32_t G[6][kQ], closed_m[kQ];
+    uint32_t G[kGated][kQ], closed_m[kQ];
 #pragma unroll
     for (int q = 0; q < kQ; q++) {
         const uint4 a = PL[2 * (blk0 + q)], b = PL[2 * (blk0 + q) + 1];
@@ -277,7 +281,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
         else if (p0 + 32 > n) { closed = p0 >= n ? 0xFFFFFFFFu : (0xFFFFFFFFu << (int)(n - p0)); }
         closed_m[q] = closed;
 #pragma unroll
-        for (int k = 0; k < 6; k++) { G[k][q] = 0; }
+        for (int k = 0; k < kGated; k++) { G[k][q] = 0; }
         vq[q] = kEdge ? VL[blk0 + q] : 0xFFFFFFFFu;
     }
 
@@ -319,7 +323,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                 uint32_t acc = eb[q] | fsr(eb[q], eb[q + 1], 1);
                 if (kMinLen >= 3) { acc |= fsr(eb[q], eb[q + 1], 2); }
 #pragma unroll
-                for (int k = 0; k < 6; k++) { acc |= fsr(eb[q], eb[q + 1], kMinLen + k) & G[k][q]; }
+                for (int k = 0; k < kGated; k++) { acc |= fsr(eb[q], eb[q + 1], kMinLen + k) & G[k][q]; }
                 ib[q] = acc | closed_m[q];
                 none &= ib[q];
             }
@@ -351,7 +355,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                             best_len[k] = (uint8_t)run;
                             table[tile_pos0 + k] = (run << 16) | d;
 #pragma unroll
-                            for (int t = 0; t < 6; t++) {
+                            for (int t = 0; t < kGated; t++) {
                                 if (run >= (uint32_t)(kMinLen + t)) { G[t][q] |= bit; }
                             }
                         } else {

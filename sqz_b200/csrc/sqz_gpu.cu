@@ -795,8 +795,10 @@ static int stream_launch_next(sqz_gpu_stream* st, uint16_t* len_out, uint16_t* d
     return 0;
 }
 
-static size_t default_chunk(size_t bytes) {
-    const size_t kDefault = (size_t)32 << 20;
+// Token mode feeds a host consumer chunk by chunk: smaller chunks overlap better.
+// Table mode only streams: larger chunks waste less on the last wave of tiles.
+static size_t default_chunk(size_t bytes, bool tokens) {
+    const size_t kDefault = tokens ? (size_t)32 << 20 : (size_t)128 << 20;
     return std::max<size_t>(std::min(bytes, kDefault), 1);
 }
 
@@ -816,7 +818,7 @@ static int stream_open(sqz_gpu_stream** out, int device, const uint8_t* data, si
     st->data = data;
     st->bytes = bytes;
     st->min_len = min_len; st->max_len = max_len; st->max_dist = max_dist;
-    st->chunk = chunk ? chunk : default_chunk(bytes);
+    st->chunk = chunk ? chunk : default_chunk(bytes, tokens);
     st->want_tokens = tokens;
     const int slots = bytes > st->chunk ? 2 : 1;
     for (int k = 0; k < slots && bytes > 0; k++) {
