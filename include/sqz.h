@@ -76,7 +76,7 @@ struct sqz_tree {       /* huffman.h:22-34 */
 
 struct sqz {
     int32_t error;      /* sticky errno: E2BIG, EINVAL, ENODEV, ENOMEM, EIO */
-    int32_t device;     /* CUDA device for the match search, default 0 */
+    int32_t device;     /* CUDA device for the match search; -1 (default) = the current one */
     struct sqz_bitstream* bs;
     struct sqz_tree lit;
     struct sqz_tree pos;

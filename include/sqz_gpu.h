@@ -42,7 +42,10 @@ enum {
     sqz_gpu_max_dist_limit = 65535    /* distances are reported in 16 bits */
 };
 
-/* ---- host-buffer entry points (replace squeeze.h:338-358 / 377-394) ------ */
+/* ---- host-buffer entry points (replace squeeze.h:338-358 / 377-394) ------ *
+ * They run on the calling thread's current CUDA device (device 0 unless the
+ * caller selected another one); sqz_gpu_stream_open takes the device explicitly
+ * (-1 = current).                                                            */
 
 /* Full match table: for every i in [0, bytes) len_out[i] in {0} U
  * [min_len, max_len] and dist_out[i] in [1, max_dist] (0 when len is 0).

@@ -313,6 +313,7 @@ static void bucket_tables(struct sqz* s) {
 
 void sqz_init(struct sqz* s) {
     memset(s, 0, sizeof(*s));
+    s->device = -1;                       /* the caller's current CUDA device */
     tree_init(&s->lit, s->lit_nodes, sqz_lit_symbols);
     tree_init(&s->pos, s->pos_nodes, sqz_pos_symbols);
 }

@@ -479,12 +479,9 @@ extern "C" int sqz_gpu_select_kernel(int which) {
 
 static int launch_v1(const uint8_t* d_shard, size_t back, size_t n, size_t ahead, uint32_t min_len,
                      uint32_t max_len, uint32_t max_dist, uint32_t* d_table, cudaStream_t s) {
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(v1::match_table, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)v1::smem_bytes(sqz_gpu_max_len_limit, sqz_gpu_max_dist_limit));
-    });
+    // (cheap and idempotent: set on every call so that every device's context has it)
+    cudaError_t attr_err = cudaFuncSetAttribute(v1::match_table, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)v1::smem_bytes(sqz_gpu_max_len_limit, sqz_gpu_max_dist_limit));
     if (attr_err != cudaSuccess) { return fail(cuda_code(attr_err), "cudaFuncSetAttribute", attr_err); }
     const size_t tiles = (n + v1::kThreads - 1) / v1::kThreads;
     if (tiles > 0x7FFFFFFFull) { return fail(EINVAL, "shard too large for one launch"); }
@@ -497,22 +494,33 @@ static int launch_v1(const uint8_t* d_shard, size_t back, size_t n, size_t ahead
 template <int kMinLen>
 static int launch_v2(const uint8_t* d_shard, size_t back, size_t n, size_t ahead, uint32_t max_len,
                      uint32_t max_dist, uint32_t* d_table, cudaStream_t s) {
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] {
+    // function attributes and the side stream live in the device's context: set up once per device
+    constexpr int kMaxDevices = 64;
+    static std::once_flag once[kMaxDevices];
+    static cudaError_t attr_errs[kMaxDevices];
+    static cudaStream_t sides[kMaxDevices];
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) { return fail(ENODEV, "device index out of range"); }
+    std::call_once(once[dev], [dev] {
         const int big = v2::geometry(sqz_gpu_max_len_limit, sqz_gpu_max_dist_limit, true).smem_bytes;
-        attr_err = cudaFuncSetAttribute(v2::match_table<kMinLen, false>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-        if (attr_err == cudaSuccess) {
-            attr_err = cudaFuncSetAttribute(v2::match_table<kMinLen, true>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaError_t e = cudaFuncSetAttribute(v2::match_table<kMinLen, false>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        if (e == cudaSuccess) {
+            e = cudaFuncSetAttribute(v2::match_table<kMinLen, true>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         }
         // several CTAs per SM only fit when the L1/shared split favours shared memory
         cudaFuncSetAttribute(v2::match_table<kMinLen, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(v2::match_table<kMinLen, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
+        sides[dev] = nullptr;
+        cudaStreamCreateWithFlags(&sides[dev], cudaStreamNonBlocking);
+        attr_errs[dev] = e;
     });
+    const cudaError_t attr_err = attr_errs[dev];
+    cudaStream_t side = sides[dev];
     if (attr_err != cudaSuccess) { return fail(cuda_code(attr_err), "cudaFuncSetAttribute", attr_err); }
     // Tiles whose every position sees the full max_dist window and max_len of
     // look-ahead run the plain variant; the rest (start of the first shard, end
@@ -532,9 +540,6 @@ static int launch_v2(const uint8_t* d_shard, size_t back, size_t n, size_t ahead
     const int smem_main = v2::geometry(max_len, max_dist, false).smem_bytes;
     const int smem_edge = v2::geometry(max_len, max_dist, true).smem_bytes;
     // The few edge tiles run on a side stream, concurrently with the interior tiles.
-    static cudaStream_t side = nullptr;
-    static std::once_flag side_once;
-    std::call_once(side_once, [] { cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking); });
     const bool edges = t_lo > 0 || tiles > t_hi;
     cudaStream_t es = side != nullptr ? side : s;
     cudaEvent_t fork = nullptr, join = nullptr;
@@ -744,13 +749,15 @@ static int slot_alloc(Slot& s, size_t chunk, uint32_t max_len, uint32_t max_dist
     return 0;
 }
 
-static int ensure_device(int device) {
+// device < 0 = the calling thread's current device
+static int ensure_device(int& device) {
     int count = 0;
     cudaError_t ce = cudaGetDeviceCount(&count);
     if (ce != cudaSuccess || count == 0) {
         return fail(ENODEV, "no CUDA device: the match search has no CPU fallback", ce);
     }
-    if (device < 0 || device >= count) { return fail(ENODEV, "no such CUDA device"); }
+    if (device < 0) { CU(cudaGetDevice(&device)); }
+    if (device >= count) { return fail(ENODEV, "no such CUDA device"); }
     CU(cudaSetDevice(device));
     return 0;
 }
@@ -886,7 +893,7 @@ extern "C" int sqz_gpu_tokens(const uint8_t* data, size_t bytes, uint32_t window
     if (n_tokens == nullptr) { return fail(EINVAL, "null n_tokens"); }
     *n_tokens = 0;
     sqz_gpu_stream* st = nullptr;
-    if (int r = sqz_gpu_stream_open(&st, 0, data, bytes, window, min_len, max_len, max_dist, 0)) {
+    if (int r = sqz_gpu_stream_open(&st, -1, data, bytes, window, min_len, max_len, max_dist, 0)) {
         return r;
     }
     size_t total = 0;
@@ -914,7 +921,7 @@ extern "C" int sqz_gpu_match_table(const uint8_t* data, size_t bytes, uint32_t w
         return fail(EINVAL, "null output");
     }
     sqz_gpu_stream* st = nullptr;
-    if (int r = stream_open(&st, 0, data, bytes, window, min_len, max_len, max_dist, 0, false)) {
+    if (int r = stream_open(&st, -1, data, bytes, window, min_len, max_len, max_dist, 0, false)) {
         return r;
     }
     int rc = 0;
