@@ -44,6 +44,8 @@ MIN_LEN, MAX_LEN, MAX_DIST = 3, 257, WINDOW - 1      # reference G1 rules, squee
 SMEM_BYTES_PER_CLK_PER_SM = 128
 SMS = 148
 METRIC = "match_search_input_MBps"
+KERNEL_ALU_INSTR = 118       # LOP3 + SHF per warp-step of the hot loop (ncu source page, round 1 final kernel)
+KERNEL_CC_PER_STEP = 4064    # 127 owned blocks x 32 positions x 1 distance
 
 
 def env_int(name, default):
@@ -329,6 +331,23 @@ def ours(args) -> None:
     except Exception as e:  # the oracle is only the yardstick; never let it sink the measurement
         cpu = {"value": None, "unit": "MB/s", "cores": 0, "kind": "reference", "sample": "unavailable: %r" % (e,)}
 
+    # ---- whole codec: sqz_compress (GPU search + serial host entropy stage), bounded sample ----
+    comp = None
+    try:
+        import sqz_b200 as sq
+        sample = np.ascontiguousarray(host[back: back + min(n, args.compress_sample)])
+        st = {}
+        t0 = time.perf_counter()
+        blob = sq.compress(sample, 15, stats=st)
+        dt = time.perf_counter() - t0
+        comp = {"value": sample.size / 1e6 / dt, "unit": "MB/s", "sample_bytes": int(sample.size),
+                "compressed_bytes": len(blob), "seconds": dt, "search_wait_seconds": st["search_seconds"],
+                "entropy_seconds": st["entropy_seconds"], "tokens": st["tokens"],
+                "note": "sqz_compress(host in, host bitstream out): the serial adaptive-Huffman stage on one "
+                        "host core bounds it (SURVEY 7 H4); the search runs ahead on the GPU"}
+    except Exception as e:
+        comp = {"value": None, "error": repr(e)}
+
     ms_per_step = sec / args.steps * 1e3
     value = total / 1e6 / (sec / args.steps)
     peaks = {}
@@ -340,6 +359,12 @@ def ours(args) -> None:
     smem_peak = SMEM_BYTES_PER_CLK_PER_SM * SMS * f_mhz * 1e6 / 1e9            # GB/s at the clock seen under load
     cc = cc_count(g0, n, MAX_DIST)
     achieved = cc * 4 / t_match / 1e9 if t_match > 0 else None
+    # The bit-sliced kernel issues no load per candidate-compare, so the shared-memory figure can
+    # exceed 1.  What binds it is the integer ALU pipe: 16 lanes/clk per SM sub-partition, i.e. half
+    # a warp-instruction per clock.  Its fast path is KERNEL_ALU_INSTR ALU instructions per warp-step
+    # of KERNEL_CC_PER_STEP candidate-compares (profiles/r01_match_table_ncu_full.txt).
+    alu_ceiling = 0.5 * 4 * SMS * f_mhz * 1e6 * KERNEL_CC_PER_STEP / KERNEL_ALU_INSTR      # CC/s
+    cc_per_s = cc / t_match if t_match > 0 else None
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_bytes = n * (1 + 4)                                                    # input read + table write
     line = {
@@ -360,11 +385,22 @@ def ours(args) -> None:
                     "north_star fixes the smem compare bound, HBM is shown in 'hbm'" % (cc, f_mhz),
             "cc_per_launch": cc, "kernel_ms": t_match * 1e3, "kernel_launches_timed": int(nl.value),
             "kernel_share_of_step": (t_match * 1e3) / ms_per_step if ms_per_step else None,
+            "binding_resource": {
+                "name": "integer ALU pipe (LOP3/SHF), 0.5 warp-instr/clk per SM sub-partition",
+                "alu_instr_per_warp_step": KERNEL_ALU_INSTR, "cc_per_warp_step": KERNEL_CC_PER_STEP,
+                "ceiling_cc_per_s": alu_ceiling, "achieved_cc_per_s": cc_per_s,
+                "frac": cc_per_s / alu_ceiling if cc_per_s else None,
+                "note": "achieved counts the whole sqz_gpu_match_table_device call: bit-sliced kernel, edge tiles "
+                        "and the finish kernel",
+            },
+            "traffic_note": "ncu --set full on a 16 MiB shard (profiles/r01_match_table_ncu_full.txt): 2.1 B of DRAM "
+                            "traffic per input byte while the table still sits in L2; algorithmic 5 B per input byte",
         },
         "hbm": {"achieved": hbm_bytes / t_match / 1e9 if t_match > 0 else None, "peak": hbm_peak, "unit": "GB/s",
                 "frac": hbm_bytes / t_match / 1e9 / hbm_peak if t_match > 0 else None,
                 "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
         "cpu_baseline": cpu,
+        "sqz_compress_e2e": comp,
         "tokens_per_shard": n_tokens,
     }
     print(json.dumps(line), flush=True)
@@ -381,6 +417,7 @@ def main():
     ap.add_argument("--size", type=int, default=1 << 30, help="bytes per GPU")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-sample", type=int, default=512 << 10)
+    ap.add_argument("--compress-sample", type=int, default=64 << 20)
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
