@@ -20,8 +20,11 @@
 //         fail = E' | E'>>1 | E'>>2 | (E'>>3 & G_0) | ... | (E'>>6 & G_3) | closed
 //     (E' = ~E, bits shifted in from the next block), so a candidate that merely
 //     ties or falls short never leaves the fast path.
-//   * Distances are visited in ascending order, exactly like the reference, so
-//     "strictly longer wins" keeps the nearest candidate among equals.
+//   * Distances ascend group by group (128 at a time) like the reference's scan; the
+//     four distances 32 apart inside a group share their shifted candidate words
+//     (7 funnel shifts per plane for 16 block-distance pairs).  Positions whose
+//     best was set inside the current group accept a nearer equal run, so the
+//     result is still "longest, nearest among equals".
 //   * Survivors of the multiplexer take a scalar path: the run is measured from
 //     the same E bits (32-bit window), compared with the position's current
 //     best and recorded as (len, dist).
@@ -62,7 +65,7 @@ constexpr uint8_t kFinished = 0xFE;       // best_len mark: holds max_len, nothi
 constexpr uint32_t kOpenBit = 0x80000000u; // table word mark: position is finished by the phase 2 kernel
 
 struct Geometry {            // identical for all CTAs of a launch
-    int back_blocks;         // plane blocks staged before the tile: ceil(max_dist/32) + 1
+    int back_blocks;         // plane blocks staged before the tile: ceil(max_dist/32) + 2*kQ
     int ahead_blocks;        // after the tile: look-ahead lane + slack
     int plane_blocks;
     int region_bytes;        // planes (phase 1) / raw bytes (phase 2) share this region
@@ -71,7 +74,7 @@ struct Geometry {            // identical for all CTAs of a launch
 
 __host__ __device__ inline Geometry geometry(uint32_t max_len, uint32_t max_dist, bool edge) {
     Geometry g;
-    g.back_blocks = (int)((max_dist + 31) / 32) + 1;
+    g.back_blocks = (int)((max_dist + 31) / 32) + 2 * kQ;   // a group of kQ word distances + its window
     g.ahead_blocks = kQ + 2;
     g.plane_blocks = g.back_blocks + kTileBlocks + g.ahead_blocks;
     const int plane_bytes = g.plane_blocks * 32;                           // 8 planes x 4 B per block
@@ -290,87 +293,140 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
     const uint32_t reach = (uint32_t)min((long long)max_dist, tile_last + back);
     const int m_end = (int)((reach + 31) / 32);
 
-    for (int m = 1; m <= m_end; m++) {
-        uint32_t cw[kQ + 1][8];
-        uint32_t vc[kQ + 1];
+    // Distances are visited in groups of 128: for each bit offset sh the four distances
+    // d_t = 32*(m0+t) - sh, t = 0..3, are evaluated together, because block q at d_t reads the
+    // same shifted candidate word as block q+1 at d_{t+1}: 7 funnel shifts per plane serve 16
+    // (block, distance) pairs.  Inside a group the order is not ascending, so a position whose
+    // best is `fresh` (set inside the current group) keeps need = best, lets ties through, and
+    // the scalar path prefers the nearer of two equal runs; at the end of the group fresh
+    // positions are promoted to need = best+1.  Across groups distances ascend as in the
+    // reference.
+    uint32_t fresh[kQ];
 #pragma unroll
-        for (int j = 0; j <= kQ; j++) {
-            const uint4 a = PL[2 * (blk0 - m + j)], b = PL[2 * (blk0 - m + j) + 1];
-            cw[j][0] = a.x; cw[j][1] = a.y; cw[j][2] = a.z; cw[j][3] = a.w;
-            cw[j][4] = b.x; cw[j][5] = b.y; cw[j][6] = b.z; cw[j][7] = b.w;
-            vc[j] = kEdge ? VL[blk0 - m + j] : 0xFFFFFFFFu;
+    for (int q = 0; q < kQ; q++) { fresh[q] = 0; }
+
+    for (int m0 = 1; m0 <= m_end; m0 += kQ) {
+        // raw candidate words j = 0..2*kQ-1 <-> plane block blk0 - m0 - (kQ-1) + j
+        uint32_t cr[2 * kQ][8];
+        uint32_t vr[2 * kQ];
+        const int jb = blk0 - m0 - (kQ - 1);
+#pragma unroll
+        for (int j = 0; j < 2 * kQ; j++) {
+            const uint4 a = PL[2 * (jb + j)], b = PL[2 * (jb + j) + 1];
+            cr[j][0] = a.x; cr[j][1] = a.y; cr[j][2] = a.z; cr[j][3] = a.w;
+            cr[j][4] = b.x; cr[j][5] = b.y; cr[j][6] = b.z; cr[j][7] = b.w;
+            vr[j] = kEdge ? VL[jb + j] : 0xFFFFFFFFu;
         }
 #pragma unroll 1
         for (int sh = 31; sh >= 0; sh--) {
-            const uint32_t d = (uint32_t)(32 * m - sh);
-            if (d > reach) { break; }
-            // eb: bit p set = byte p differs.  r[k]: bit p set = NO run of kMinLen+k equal bytes at p
-            uint32_t eb[kQ + 1];
+            // e[q][t]: bit p set = byte p of block q differs from the byte d_t before it
+            uint32_t e[kQ][kQ];
 #pragma unroll
-            for (int q = 0; q < kQ; q++) {
-                uint32_t e = fsr(cw[q][0], cw[q + 1][0], sh) ^ qv[q][0];
+            for (int b = 0; b < 8; b++) {
+                uint32_t sw[2 * kQ - 1];
 #pragma unroll
-                for (int b = 1; b < 8; b++) { e |= fsr(cw[q][b], cw[q + 1][b], sh) ^ qv[q][b]; }
-                if (kEdge) { e |= ~vq[q] | ~fsr(vc[q], vc[q + 1], sh); }
-                eb[q] = e;
+                for (int j = 0; j < 2 * kQ - 1; j++) { sw[j] = fsr(cr[j][b], cr[j + 1][b], sh); }
+#pragma unroll
+                for (int q = 0; q < kQ; q++) {
+#pragma unroll
+                    for (int t = 0; t < kQ; t++) {
+                        const uint32_t x = sw[q - t + kQ - 1] ^ qv[q][b];
+                        e[q][t] = b == 0 ? x : (e[q][t] | x);
+                    }
+                }
             }
-            eb[kQ] = __shfl_down_sync(0xFFFFFFFFu, eb[0], 1);
-            uint32_t ib[kQ];
+            if (kEdge) {
+                uint32_t sv[2 * kQ - 1];
+#pragma unroll
+                for (int j = 0; j < 2 * kQ - 1; j++) { sv[j] = fsr(vr[j], vr[j + 1], sh); }
+#pragma unroll
+                for (int q = 0; q < kQ; q++) {
+#pragma unroll
+                    for (int t = 0; t < kQ; t++) { e[q][t] |= ~vq[q] | ~sv[q - t + kQ - 1]; }
+                }
+            }
+            uint32_t en[kQ];                                  // look-ahead: first block of the next lane
+#pragma unroll
+            for (int t = 0; t < kQ; t++) { en[t] = __shfl_down_sync(0xFFFFFFFFu, e[0][t], 1); }
+            uint32_t ib[kQ][kQ];
             uint32_t none = 0xFFFFFFFFu;
 #pragma unroll
             for (int q = 0; q < kQ; q++) {
-                // a candidate fails at position p if any of the first need(p) bytes differs
-                uint32_t acc = eb[q] | fsr(eb[q], eb[q + 1], 1);
-                if (kMinLen >= 3) { acc |= fsr(eb[q], eb[q + 1], 2); }
 #pragma unroll
-                for (int k = 0; k < kGated; k++) { acc |= fsr(eb[q], eb[q + 1], kMinLen + k) & G[k][q]; }
-                ib[q] = acc | closed_m[q];
-                none &= ib[q];
+                for (int t = 0; t < kQ; t++) {
+                    // a candidate fails at position p if any of the first need(p) bytes differs
+                    const uint32_t lo = e[q][t], hi = q + 1 < kQ ? e[q + 1][t] : en[t];
+                    uint32_t acc = lo | fsr(lo, hi, 1);
+                    if (kMinLen >= 3) { acc |= fsr(lo, hi, 2); }
+#pragma unroll
+                    for (int k = 0; k < kGated; k++) { acc |= fsr(lo, hi, kMinLen + k) & G[k][q]; }
+                    ib[q][t] = acc | closed_m[q];
+                    none &= ib[q][t];
+                }
             }
             if (none != 0xFFFFFFFFu) {
                 // ---- scalar path: exact decision for the few surviving positions ----
 #pragma unroll
-                for (int q = 0; q < kQ; q++) {
-                    uint32_t todo = ~ib[q];
-                    while (todo != 0) {
-                        const int p = __ffs((int)todo) - 1;
-                        todo &= todo - 1;
-                        const uint32_t bit = 1u << p;
-                        const int k = (own0 + q) * 32 + p;              // tile-relative position
-                        const uint32_t state = best_len[k];             // low 5 bits: best, high 3: near-ties seen
-                        const uint32_t have = state & 31u;
-                        const uint32_t win = fsr(eb[q], eb[q + 1], p);  // E-bar from position p on
-                        uint32_t run = win != 0 ? (uint32_t)(__ffs((int)win) - 1) : 32u;
-                        if (run >= max_len) {
-                            // cannot be beaten any more: record and close
-                            best_len[k] = kFinished;
-                            table[tile_pos0 + k] = (max_len << 16) | d;
-                            closed_m[q] |= bit;
-                        } else if (win == 0) {
-                            // at least 32 equal bytes: longer than the window, finish in phase 2
-                            best_len[k] = kHandOver;
-                            table[tile_pos0 + k] |= kOpenBit;
-                            closed_m[q] |= bit;
-                        } else if (run > have) {
-                            best_len[k] = (uint8_t)run;
-                            table[tile_pos0 + k] = (run << 16) | d;
+                for (int t = 0; t < kQ; t++) {
+                    const uint32_t d = (uint32_t)(32 * (m0 + t) - sh);
+                    if (d > reach) { continue; }
 #pragma unroll
-                            for (int t = 0; t < kGated; t++) {
-                                if (run >= (uint32_t)(kMinLen + t)) { G[t][q] |= bit; }
+                    for (int q = 0; q < kQ; q++) {
+                        uint32_t todo = ~ib[q][t] & ~closed_m[q];       // closed since the masks were formed?
+                        while (todo != 0) {
+                            const int p = __ffs((int)todo) - 1;
+                            todo &= todo - 1;
+                            const uint32_t bit = 1u << p;
+                            const int k = (own0 + q) * 32 + p;          // tile-relative position
+                            const uint32_t state = best_len[k];         // low 5 bits: best, high 3: near-ties seen
+                            const uint32_t have = state & 31u;
+                            const uint32_t lo = e[q][t], hi = q + 1 < kQ ? e[q + 1][t] : en[t];
+                            const uint32_t win = fsr(lo, hi, p);        // differing bytes from position p on
+                            uint32_t* slot = table + tile_pos0 + k;
+                            if (win == 0) {
+                                // at least 32 equal bytes: longer than the window, phase 2 finishes it.
+                                // A fresh best may still have a nearer equal: let phase 2 start over.
+                                best_len[k] = kHandOver;
+                                *slot = (fresh[q] & bit) ? kOpenBit : (*slot | kOpenBit);
+                                closed_m[q] |= bit;
+                                continue;
                             }
-                        } else {
-                            // a candidate that only ties: count a sample of them; a position that
-                            // keeps attracting them is cheaper to finish in phase 2
-                            if ((d & 15u) != 0) { continue; }
-                            if (state >= 0xC0u) { best_len[k] = kHandOver; table[tile_pos0 + k] |= kOpenBit; closed_m[q] |= bit; }
-                            else { best_len[k] = (uint8_t)(state + 32u); }
+                            const uint32_t run = (uint32_t)(__ffs((int)win) - 1);
+                            bool better = run > have;
+                            if (run == have && (fresh[q] & bit)) { better = d < (*slot & 0xFFFFu); }
+                            if (better) {
+                                best_len[k] = (uint8_t)run;
+                                *slot = (run << 16) | d;
+                                fresh[q] |= bit;
+#pragma unroll
+                                for (int g = 0; g < kGated; g++) {
+                                    if (run > (uint32_t)(kMinLen + g)) { G[g][q] |= bit; }
+                                }
+                            } else if ((d & 15u) == 0) {
+                                // a candidate that only ties or falls short: count a sample of them; a
+                                // position that keeps attracting them is cheaper to finish in phase 2
+                                if (state >= 0xC0u) {
+                                    best_len[k] = kHandOver;
+                                    *slot = (fresh[q] & bit) ? kOpenBit : (*slot | kOpenBit);
+                                    closed_m[q] |= bit;
+                                } else {
+                                    best_len[k] = (uint8_t)(state + 32u);
+                                }
+                            }
                         }
                     }
                 }
             }
         }
+        // end of the group: every smaller distance has been seen, fresh bests become strict
+#pragma unroll
+        for (int q = 0; q < kQ; q++) {
+#pragma unroll
+            for (int g = kGated - 1; g > 0; g--) { G[g][q] |= G[g - 1][q] & fresh[q]; }
+            G[0][q] |= fresh[q];
+            fresh[q] = 0;
+        }
     }
-
     if (tile_cycles != nullptr) {          // debugging aid: per-tile duration
         __syncthreads();
         if (threadIdx.x == 0) { tile_cycles[tile] = (unsigned long long)(clock64() - t_begin); }

@@ -598,8 +598,9 @@ extern "C" int sqz_gpu_match_table_device(const uint8_t* d_shard, size_t back, s
     }
     const int choice = g_kernel_choice.load();
     int r;
-    if (choice != 1 && min_len == 3)      { r = launch_v2<3>(d_shard, back, n, ahead, max_len, max_dist, d_table, s); }
-    else if (choice != 1 && min_len == 2) { r = launch_v2<2>(d_shard, back, n, ahead, max_len, max_dist, d_table, s); }
+    const bool v2_ok = max_len > 32;      // the bit-sliced kernel measures runs in a 32-bit window
+    if (choice != 1 && v2_ok && min_len == 3)      { r = launch_v2<3>(d_shard, back, n, ahead, max_len, max_dist, d_table, s); }
+    else if (choice != 1 && v2_ok && min_len == 2) { r = launch_v2<2>(d_shard, back, n, ahead, max_len, max_dist, d_table, s); }
     else { r = launch_v1(d_shard, back, n, ahead, min_len, max_len, max_dist, d_table, s); }
     if (r != 0) { return r; }
     if (timed) {
