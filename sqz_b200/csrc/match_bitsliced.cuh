@@ -14,10 +14,10 @@
 //     and 32 compares.
 //   * Per-position state is bit-sliced too: the run length a candidate has to
 //     reach to beat the position's current best, need = best+1 (exact up to
-//     min_len+4, anything longer counts as min_len+4), is kept as a thermometer
-//     of four masks G_k = "byte offset min_len+k has to match as well".  A
+//     min_len+3, anything longer counts as min_len+3), is kept as a thermometer
+//     of three masks G_k = "byte offset min_len+k has to match as well".  A
 //     candidate fails at position p iff one of its first need(p) bytes differs:
-//         fail = E' | E'>>1 | E'>>2 | (E'>>3 & G_0) | ... | (E'>>6 & G_3) | closed
+//         fail = E' | E'>>1 | E'>>2 | (E'>>3 & G_0) | (E'>>4 & G_1) | (E'>>5 & G_2) | closed
 //     (E' = ~E, bits shifted in from the next block), so a candidate that merely
 //     ties or falls short never leaves the fast path.
 //   * Distances ascend group by group (128 at a time) like the reference's scan; the
@@ -57,7 +57,7 @@ constexpr int kWarpOwned = 32 * kQ - 1;   // blocks a warp owns; its last block 
 constexpr int kTileBlocks = kWarps * kWarpOwned;      // owned blocks per CTA
 constexpr int kTilePos = kTileBlocks * 32;            // positions per CTA
 #ifndef SQZ_GATED
-#define SQZ_GATED 4
+#define SQZ_GATED 3
 #endif
 constexpr int kGated = SQZ_GATED;         // need is tracked exactly up to min_len + kGated
 constexpr uint8_t kHandOver = 0xFF;       // best_len mark: finish this position in phase 2
@@ -352,6 +352,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
             uint32_t none = 0xFFFFFFFFu;
 #pragma unroll
             for (int q = 0; q < kQ; q++) {
+                uint32_t all_t = 0xFFFFFFFFu;
 #pragma unroll
                 for (int t = 0; t < kQ; t++) {
                     // a candidate fails at position p if any of the first need(p) bytes differs
@@ -360,9 +361,10 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                     if (kMinLen >= 3) { acc |= fsr(lo, hi, 2); }
 #pragma unroll
                     for (int k = 0; k < kGated; k++) { acc |= fsr(lo, hi, kMinLen + k) & G[k][q]; }
-                    ib[q][t] = acc | closed_m[q];
-                    none &= ib[q][t];
+                    ib[q][t] = acc;
+                    all_t &= acc;
                 }
+                none &= all_t | closed_m[q];                  // closed positions never count
             }
             if (none != 0xFFFFFFFFu) {
                 // ---- scalar path: exact decision for the few surviving positions ----
