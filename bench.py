@@ -44,8 +44,8 @@ MIN_LEN, MAX_LEN, MAX_DIST = 3, 257, WINDOW - 1      # reference G1 rules, squee
 SMEM_BYTES_PER_CLK_PER_SM = 128
 SMS = 148
 METRIC = "match_search_input_MBps"
-KERNEL_ALU_INSTR = 118       # LOP3 + SHF per warp-step of the hot loop (ncu source page, round 1 final kernel)
-KERNEL_CC_PER_STEP = 4064    # 127 owned blocks x 32 positions x 1 distance
+KERNEL_ALU_INSTR = 354       # LOP3 + SHF per iteration of the hot loop (ncu source page, round 1 final kernel)
+KERNEL_CC_PER_STEP = 16256   # 127 owned blocks x 32 positions x 4 distances per warp and iteration
 
 
 def env_int(name, default):
@@ -361,8 +361,8 @@ def ours(args) -> None:
     achieved = cc * 4 / t_match / 1e9 if t_match > 0 else None
     # The bit-sliced kernel issues no load per candidate-compare, so the shared-memory figure can
     # exceed 1.  What binds it is the integer ALU pipe: 16 lanes/clk per SM sub-partition, i.e. half
-    # a warp-instruction per clock.  Its fast path is KERNEL_ALU_INSTR ALU instructions per warp-step
-    # of KERNEL_CC_PER_STEP candidate-compares (profiles/r01_match_table_ncu_full.txt).
+    # a warp-instruction per clock.  Its fast path is KERNEL_ALU_INSTR ALU instructions per loop iteration
+    # of KERNEL_CC_PER_STEP candidate-compares per warp (profiles/r01_match_table_ncu_full.txt).
     alu_ceiling = 0.5 * 4 * SMS * f_mhz * 1e6 * KERNEL_CC_PER_STEP / KERNEL_ALU_INSTR      # CC/s
     cc_per_s = cc / t_match if t_match > 0 else None
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
@@ -387,13 +387,13 @@ def ours(args) -> None:
             "kernel_share_of_step": (t_match * 1e3) / ms_per_step if ms_per_step else None,
             "binding_resource": {
                 "name": "integer ALU pipe (LOP3/SHF), 0.5 warp-instr/clk per SM sub-partition",
-                "alu_instr_per_warp_step": KERNEL_ALU_INSTR, "cc_per_warp_step": KERNEL_CC_PER_STEP,
+                "alu_instr_per_warp_iteration": KERNEL_ALU_INSTR, "cc_per_warp_iteration": KERNEL_CC_PER_STEP,
                 "ceiling_cc_per_s": alu_ceiling, "achieved_cc_per_s": cc_per_s,
                 "frac": cc_per_s / alu_ceiling if cc_per_s else None,
                 "note": "achieved counts the whole sqz_gpu_match_table_device call: bit-sliced kernel, edge tiles "
                         "and the finish kernel",
             },
-            "traffic_note": "ncu --set full on a 16 MiB shard (profiles/r01_match_table_ncu_full.txt): 2.1 B of DRAM "
+            "traffic_note": "ncu --set full on a 16 MiB shard (profiles/r01_match_table_ncu_full.txt): 2.0 B of DRAM "
                             "traffic per input byte while the table still sits in L2; algorithmic 5 B per input byte",
         },
         "hbm": {"achieved": hbm_bytes / t_match / 1e9 if t_match > 0 else None, "peak": hbm_peak, "unit": "GB/s",

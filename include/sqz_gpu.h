@@ -117,6 +117,9 @@ int         sqz_gpu_device_count(void);          /* 0 when no driver / device */
 const char* sqz_gpu_last_error(void);            /* thread-local text */
 void*       sqz_gpu_host_alloc(size_t bytes);    /* pinned host memory (NULL on failure) */
 void        sqz_gpu_host_free(void* p);
+/* The host-buffer entry points keep their device and pinned staging buffers
+ * (up to four slots) for the next call; this frees them.                     */
+void        sqz_gpu_release(void);
 /* Which match-table kernel serves sqz_gpu_match_table_device: 0 = automatic
  * (bit-sliced kernel for min_len 2 or 3, thread-per-position kernel otherwise),
  * 1 = thread-per-position, 2 = bit-sliced where applicable.  Both are exact;

@@ -86,6 +86,7 @@ SYMBOLS = {
     "sqz_gpu_last_error": (C.c_char_p, []),
     "sqz_gpu_host_alloc": (C.c_void_p, [size_t]),
     "sqz_gpu_host_free": (None, [C.c_void_p]),
+    "sqz_gpu_release": (None, []),
     "sqz_gpu_select_kernel": (C.c_int, [C.c_int]),
     "sqz_gpu_debug_tile_cycles": (None, [C.c_void_p]),
     "sqz_gpu_launch_count": (C.c_uint64, []),

@@ -705,6 +705,11 @@ struct Slot {
     uint32_t* h_tokens = nullptr;     // pinned
     size_t first = 0, n = 0;          // chunk = [first, first + n) of the input
     bool busy = false;
+    // what the buffers were sized for (slots are recycled between calls, see slot_take)
+    int device = -1;
+    size_t cap_chunk = 0;
+    uint32_t cap_len = 0, cap_dist = 0;
+    bool cap_tokens = false;
 };
 
 struct sqz_gpu_stream {
@@ -732,7 +737,8 @@ static void slot_free(Slot& s) {
     s = Slot();
 }
 
-static int slot_alloc(Slot& s, size_t chunk, uint32_t max_len, uint32_t max_dist, bool tokens) {
+static int slot_alloc(Slot& s, int device, size_t chunk, uint32_t max_len, uint32_t max_dist, bool tokens) {
+    s.device = device; s.cap_chunk = chunk; s.cap_len = max_len; s.cap_dist = max_dist; s.cap_tokens = tokens;
     CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     CU(cudaMalloc(&s.d_data, (size_t)max_dist + chunk + max_len + 64));
@@ -748,6 +754,57 @@ static int slot_alloc(Slot& s, size_t chunk, uint32_t max_len, uint32_t max_dist
         CU(cudaMalloc(&s.d_dist, chunk * 2));
     }
     return 0;
+}
+
+// Allocating and freeing gigabytes of device and pinned memory per call costs more than the
+// search of a small input and stalls the device; finished calls park their slots here and the
+// next call with the same shape takes them back.  sqz_gpu_release() frees the parked slots.
+static std::mutex g_park_mu;
+static std::vector<Slot> g_parked;
+constexpr size_t kMaxParked = 4;
+
+static int slot_take(Slot& s, int device, size_t chunk, uint32_t max_len, uint32_t max_dist, bool tokens) {
+    {
+        std::lock_guard<std::mutex> lk(g_park_mu);
+        for (size_t k = 0; k < g_parked.size(); k++) {
+            const Slot& c = g_parked[k];
+            if (c.device == device && c.cap_tokens == tokens && c.cap_chunk >= chunk &&
+                c.cap_chunk <= 2 * chunk + (1u << 20) && c.cap_len >= max_len && c.cap_dist >= max_dist) {
+                s = c;
+                g_parked.erase(g_parked.begin() + (long)k);
+                s.first = 0; s.n = 0; s.busy = false;
+                return 0;
+            }
+        }
+    }
+    int r = slot_alloc(s, device, chunk, max_len, max_dist, tokens);
+    if (r != 0) { slot_free(s); }
+    return r;
+}
+
+static void slot_give_back(Slot& s) {
+    if (s.stream == nullptr) { s = Slot(); return; }
+    cudaStreamSynchronize(s.stream);
+    Slot victim;
+    {
+        std::lock_guard<std::mutex> lk(g_park_mu);
+        g_parked.push_back(s);
+        if (g_parked.size() > kMaxParked) { victim = g_parked.front(); g_parked.erase(g_parked.begin()); }
+    }
+    s = Slot();
+    if (victim.stream != nullptr) { cudaSetDevice(victim.device); slot_free(victim); }
+}
+
+extern "C" void sqz_gpu_release(void) {
+    std::vector<Slot> all;
+    {
+        std::lock_guard<std::mutex> lk(g_park_mu);
+        all.swap(g_parked);
+    }
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (Slot& c : all) { cudaSetDevice(c.device); slot_free(c); }
+    cudaSetDevice(cur);
 }
 
 // device < 0 = the calling thread's current device
@@ -830,7 +887,7 @@ static int stream_open(sqz_gpu_stream** out, int device, const uint8_t* data, si
     st->want_tokens = tokens;
     const int slots = bytes > st->chunk ? 2 : 1;
     for (int k = 0; k < slots && bytes > 0; k++) {
-        if (int r = slot_alloc(st->slot[k], st->chunk, max_len, max_dist, tokens)) {
+        if (int r = slot_take(st->slot[k], device, st->chunk, max_len, max_dist, tokens)) {
             sqz_gpu_stream_close(st);
             return r;
         }
@@ -882,8 +939,8 @@ extern "C" int sqz_gpu_stream_next(sqz_gpu_stream* st, const uint32_t** tokens, 
 extern "C" void sqz_gpu_stream_close(sqz_gpu_stream* st) {
     if (st == nullptr) { return; }
     cudaSetDevice(st->device);
-    slot_free(st->slot[0]);
-    slot_free(st->slot[1]);
+    slot_give_back(st->slot[0]);
+    slot_give_back(st->slot[1]);
     if (st->prev_parsed) { cudaEventDestroy(st->prev_parsed); }
     delete st;
 }
@@ -894,7 +951,9 @@ extern "C" int sqz_gpu_tokens(const uint8_t* data, size_t bytes, uint32_t window
     if (n_tokens == nullptr) { return fail(EINVAL, "null n_tokens"); }
     *n_tokens = 0;
     sqz_gpu_stream* st = nullptr;
-    if (int r = sqz_gpu_stream_open(&st, -1, data, bytes, window, min_len, max_len, max_dist, 0)) {
+    // one-shot call: nothing consumes the chunks on the way, so use the larger streaming chunk
+    if (int r = sqz_gpu_stream_open(&st, -1, data, bytes, window, min_len, max_len, max_dist,
+                                    default_chunk(bytes, false))) {
         return r;
     }
     size_t total = 0;
