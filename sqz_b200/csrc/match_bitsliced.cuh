@@ -61,7 +61,6 @@ constexpr int kTilePos = kTileBlocks * 32;            // positions per CTA
 #endif
 constexpr int kGated = SQZ_GATED;         // need is tracked exactly up to min_len + kGated
 constexpr uint8_t kHandOver = 0xFF;       // best_len mark: finish this position in phase 2
-constexpr uint8_t kFinished = 0xFE;       // best_len mark: holds max_len, nothing left to do
 constexpr uint32_t kOpenBit = 0x80000000u; // table word mark: position is finished by the phase 2 kernel
 
 struct Geometry {            // identical for all CTAs of a launch
@@ -88,11 +87,6 @@ __host__ __device__ inline Geometry geometry(uint32_t max_len, uint32_t max_dist
 
 __device__ __forceinline__ uint32_t fsr(uint32_t lo, uint32_t hi, int s) {
     return __funnelshift_r(lo, hi, s);               // bits [s, s+32) of hi:lo
-}
-
-// bit-wise 2:1 multiplexer: sel ? b : a
-__device__ __forceinline__ uint32_t mux(uint32_t sel, uint32_t a, uint32_t b) {
-    return (a & ~sel) | (b & sel);
 }
 
 // ---------------------------------------------------------------------------
