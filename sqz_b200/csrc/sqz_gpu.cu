@@ -498,7 +498,7 @@ static int launch_v2(const uint8_t* d_shard, size_t back, size_t n, size_t ahead
     constexpr int kMaxDevices = 64;
     static std::once_flag once[kMaxDevices];
     static cudaError_t attr_errs[kMaxDevices];
-    static cudaStream_t sides[kMaxDevices];
+    static cudaStream_t sides[kMaxDevices], sides2[kMaxDevices];
     int dev = 0;
     CU(cudaGetDevice(&dev));
     if (dev < 0 || dev >= kMaxDevices) { return fail(ENODEV, "device index out of range"); }
@@ -516,11 +516,13 @@ static int launch_v2(const uint8_t* d_shard, size_t back, size_t n, size_t ahead
         cudaFuncSetAttribute(v2::match_table<kMinLen, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
         sides[dev] = nullptr;
+        sides2[dev] = nullptr;
         cudaStreamCreateWithFlags(&sides[dev], cudaStreamNonBlocking);
+        cudaStreamCreateWithFlags(&sides2[dev], cudaStreamNonBlocking);
         attr_errs[dev] = e;
     });
     const cudaError_t attr_err = attr_errs[dev];
-    cudaStream_t side = sides[dev];
+    cudaStream_t side = sides[dev], side2 = sides2[dev];
     if (attr_err != cudaSuccess) { return fail(cuda_code(attr_err), "cudaFuncSetAttribute", attr_err); }
     // Tiles whose every position sees the full max_dist window and max_len of
     // look-ahead run the plain variant; the rest (start of the first shard, end
@@ -540,36 +542,42 @@ static int launch_v2(const uint8_t* d_shard, size_t back, size_t n, size_t ahead
     const int smem_main = v2::geometry(max_len, max_dist, false).smem_bytes;
     const int smem_edge = v2::geometry(max_len, max_dist, true).smem_bytes;
     // The few edge tiles run on a side stream, concurrently with the interior tiles.
-    const bool edges = t_lo > 0 || tiles > t_hi;
-    cudaStream_t es = side != nullptr ? side : s;
-    cudaEvent_t fork = nullptr, join = nullptr;
-    if (edges && es != s) {
+    // leading and trailing edge tiles each get a side stream of their own
+    const bool lead = t_lo > 0, trail = tiles > t_hi;
+    cudaStream_t es1 = side != nullptr ? side : s, es2 = side2 != nullptr ? side2 : s;
+    cudaEvent_t fork = nullptr, join1 = nullptr, join2 = nullptr;
+    if (lead || trail) {
         CU(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
         CU(cudaEventRecord(fork, s));
-        CU(cudaStreamWaitEvent(es, fork, 0));
     }
-    if (t_lo > 0) {
-        v2::match_table<kMinLen, true><<<(unsigned)t_lo, v2::kThreads, smem_edge, es>>>(
+    if (lead) {
+        if (es1 != s) { CU(cudaStreamWaitEvent(es1, fork, 0)); }
+        v2::match_table<kMinLen, true><<<(unsigned)t_lo, v2::kThreads, smem_edge, es1>>>(
             d_shard, (long long)back, (long long)n, (long long)ahead, max_len, max_dist, d_table, 0, g_tile_cycles);
         LAUNCHED("match_table_v2_edge");
+        if (es1 != s) {
+            CU(cudaEventCreateWithFlags(&join1, cudaEventDisableTiming));
+            CU(cudaEventRecord(join1, es1));
+        }
     }
-    if (tiles > t_hi) {
-        v2::match_table<kMinLen, true><<<(unsigned)(tiles - t_hi), v2::kThreads, smem_edge, es>>>(
+    if (trail) {
+        if (es2 != s) { CU(cudaStreamWaitEvent(es2, fork, 0)); }
+        v2::match_table<kMinLen, true><<<(unsigned)(tiles - t_hi), v2::kThreads, smem_edge, es2>>>(
             d_shard, (long long)back, (long long)n, (long long)ahead, max_len, max_dist, d_table, (int)t_hi, g_tile_cycles);
         LAUNCHED("match_table_v2_edge");
+        if (es2 != s) {
+            CU(cudaEventCreateWithFlags(&join2, cudaEventDisableTiming));
+            CU(cudaEventRecord(join2, es2));
+        }
     }
     if (t_hi > t_lo) {
         v2::match_table<kMinLen, false><<<(unsigned)(t_hi - t_lo), v2::kThreads, smem_main, s>>>(
             d_shard, (long long)back, (long long)n, (long long)ahead, max_len, max_dist, d_table, (int)t_lo, g_tile_cycles);
         LAUNCHED("match_table_v2");
     }
-    if (edges && es != s) {
-        CU(cudaEventRecord(join, es));
-        CU(cudaStreamWaitEvent(s, join, 0));
-        CU(cudaEventDestroy(fork));
-        CU(cudaEventDestroy(join));
-    }
+    if (join1 != nullptr) { CU(cudaStreamWaitEvent(s, join1, 0)); CU(cudaEventDestroy(join1)); }
+    if (join2 != nullptr) { CU(cudaStreamWaitEvent(s, join2, 0)); CU(cudaEventDestroy(join2)); }
+    if (fork != nullptr) { CU(cudaEventDestroy(fork)); }
     v2::finish_marked<<<148 * 8, v2::kThreads, 0, s>>>(d_shard, (long long)back, (long long)n, (long long)ahead,
                                                      (uint32_t)kMinLen, max_len, max_dist, d_table, d_counters,
                                                      g_tile_cycles ? g_tile_cycles + (1 << 20) : nullptr);
@@ -764,12 +772,16 @@ static std::vector<Slot> g_parked;
 constexpr size_t kMaxParked = 4;
 
 static int slot_take(Slot& s, int device, size_t chunk, uint32_t max_len, uint32_t max_dist, bool tokens) {
+    // round the capacity up to a power of two (>= 1 MiB) so that calls of similar size share slots
+    size_t cap = (size_t)1 << 20;
+    while (cap < chunk) { cap <<= 1; }
+    chunk = cap;
     {
         std::lock_guard<std::mutex> lk(g_park_mu);
         for (size_t k = 0; k < g_parked.size(); k++) {
             const Slot& c = g_parked[k];
             if (c.device == device && c.cap_tokens == tokens && c.cap_chunk >= chunk &&
-                c.cap_chunk <= 2 * chunk + (1u << 20) && c.cap_len >= max_len && c.cap_dist >= max_dist) {
+                c.cap_chunk <= 4 * chunk && c.cap_len >= max_len && c.cap_dist >= max_dist) {
                 s = c;
                 g_parked.erase(g_parked.begin() + (long)k);
                 s.first = 0; s.n = 0; s.busy = false;

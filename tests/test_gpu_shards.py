@@ -179,3 +179,49 @@ def test_sampled_positions_against_the_brute_force_oracle(oracle):
                                     np.arange((4 << 20) - 150, (4 << 20) + 150)]))
     for i in pos.tolist():
         assert oracle.best(d, i, 1 << 15) == (int(ln[i]), int(ds[i])), i
+
+
+def _random_input(rng, n):
+    kind = rng.integers(0, 6)
+    if kind == 0:
+        return rng.integers(0, 256, n, dtype=np.uint8)
+    if kind == 1:
+        return rng.integers(0, rng.integers(2, 6), n, dtype=np.uint8)
+    if kind == 2:                                          # byte runs of random length
+        vals = rng.integers(0, 4, n, dtype=np.uint8)
+        return np.repeat(vals, rng.integers(1, 600, n))[:n].copy()
+    if kind == 3:                                          # periodic with a few defects
+        d = np.tile(rng.integers(0, 256, int(rng.integers(1, 300)), dtype=np.uint8), n)[:n].copy()
+        d[rng.integers(0, n, max(n // 500, 1))] ^= 1
+        return d
+    if kind == 4:                                          # zero-rich records
+        d = np.zeros(n, np.uint8)
+        idx = rng.integers(0, n, n // 12 + 1)
+        d[idx] = rng.integers(1, 256, idx.size, dtype=np.uint8)
+        return d
+    base = corpus.base()
+    at = int(rng.integers(0, base.size - n))
+    return base[at:at + n].copy()
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_randomised_inputs_and_rules(seed, oracle, kernel):
+    """Seeded fuzz: random structure, random (min_len, max_len, max_dist, window), table + tokens."""
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.choice([1, 2, 3, 31, 32, 33, 257, 1000, 4064, 16256, 16257, 40000, 70000]))
+    d = _random_input(rng, n)
+    window = 1 << int(rng.integers(10, 16))
+    mn = int(rng.integers(2, 4))
+    mx = int(rng.choice([33, 64, 254, 257, 258, 300, 512]))
+    md = int(rng.choice([1, 7, 31, 32, 33, 1000, window - 1, window]))
+    md = min(md, window, 65535)
+    ln, ds = sq.match_table(d, window, mn, mx, md)
+    oln, ods = oracle.match_table(d, window, fast=True, min_len=mn, max_len=mx, max_dist=md)
+    bad = np.nonzero((ln != oln) | (ds != ods))[0]
+    assert bad.size == 0, (seed, n, window, mn, mx, md, bad[:5], ln[bad[:5]], oln[bad[:5]], ds[bad[:5]], ods[bad[:5]])
+    if n <= 20000:                                          # and oracle B against the restated reference loop
+        aln, ads = oracle.match_table(d, window, min_len=mn, max_len=mx, max_dist=md)
+        assert (aln == oln).all() and (ads == ods).all()
+    t = sq.tokens(d, window, mn, mx, md)
+    ot, end = oracle.tokens_from_table(d, oln, ods, mn)
+    assert end == n and t.size == ot.size and (t == ot).all()
