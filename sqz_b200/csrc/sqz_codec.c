@@ -220,19 +220,41 @@ static void promote(struct sqz_tree* t, int32_t x) {
 
 /* Propagate a weight change from `i` to the root, re-ordering siblings on the
  * way up and, on the way back down, promoting right children that outgrew
- * their uncle (huffman.h:130-147).  Depth is < 64 so recursion is shallow.  */
+ * their uncle (huffman.h:130-147).  The reference recurses; this is the same
+ * sequence of steps with the recursion unrolled: first every level from the
+ * leaf to the root refreshes its parent's weight and orders the two children
+ * (continuing, after a swap, with the node that took the old slot), then the
+ * levels are revisited from the root down for the promotion test, each with
+ * the (node, parent) pair it captured on the way up.                         */
 static void weight_changed(struct sqz_tree* t, int32_t i) {
     struct sqz_node* nd = t->node;
-    const int32_t p = nd[i].up;
-    if (p < 0) {
-        sum_children(t, i);
-        (void)order_siblings(t, i);
-        return;
+    int32_t node_at[2 * sqz_lit_symbols], parent_at[2 * sqz_lit_symbols];
+    int levels = 0;
+    for (;;) {
+        const int32_t p = nd[i].up;
+        if (p < 0) {                        /* the root: refresh its own weight, nothing to order */
+            sum_children(t, i);
+            break;
+        }
+        const int32_t lo = nd[p].lo, hi = nd[p].hi;
+        const uint64_t wl = lo >= 0 ? nd[lo].freq : 0, wh = hi >= 0 ? nd[hi].freq : 0;
+        nd[p].freq = wl + wh;
+        if (lo >= 0 && hi >= 0 && wl > wh) { /* heavier child goes right */
+            nd[p].lo = hi;
+            nd[p].hi = lo;
+            relabel(t, p);
+            i = (i == lo) ? hi : lo;
+        }
+        node_at[levels] = i;
+        parent_at[levels] = p;
+        levels++;
+        i = p;
     }
-    sum_children(t, p);
-    i = order_siblings(t, i);
-    weight_changed(t, p);
-    if (nd[p].up >= 0 && nd[p].hi == i) { promote(t, i); }
+    while (levels > 0) {
+        levels--;
+        const int32_t p = parent_at[levels];
+        if (nd[p].up >= 0 && nd[p].hi == node_at[levels]) { promote(t, node_at[levels]); }
+    }
 }
 
 /* First occurrence of symbol `s` (huffman.h:149-216): walk from the root,
