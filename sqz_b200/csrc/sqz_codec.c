@@ -225,31 +225,51 @@ static void promote(struct sqz_tree* t, int32_t x) {
  * leaf to the root refreshes its parent's weight and orders the two children
  * (continuing, after a swap, with the node that took the old slot), then the
  * levels are revisited from the root down for the promotion test, each with
- * the (node, parent) pair it captured on the way up.                         */
+ * the (node, parent) pair it captured on the way up.
+ *
+ * The second pass is almost always a no-op, and whether it is can be told on
+ * the way up at no cost: the test of level k reads only the final weight of
+ * its node (settled at level k), whether that node ended up as the right
+ * child (settled at level k) and the weight of the parent's sibling, which
+ * is not on the path and is loaded anyway at level k+1.  Nothing changes the
+ * tree during the second pass unless a test fires, so if no test would fire
+ * on the state left by the first pass the second pass is skipped; otherwise it
+ * runs exactly as the reference's unwinding does.                            */
 static void weight_changed(struct sqz_tree* t, int32_t i) {
     struct sqz_node* nd = t->node;
     int32_t node_at[2 * sqz_lit_symbols], parent_at[2 * sqz_lit_symbols];
     int levels = 0;
+    int may_promote = 0;
+    int below_is_right = 0;             /* level below: did its node end up as the right child? */
+    uint64_t below_weight = 0;          /* level below: final weight of its node */
     for (;;) {
         const int32_t p = nd[i].up;
-        if (p < 0) {                        /* the root: refresh its own weight, nothing to order */
+        if (p < 0) {                    /* the root: refresh its own weight, nothing to order */
             sum_children(t, i);
             break;
         }
         const int32_t lo = nd[p].lo, hi = nd[p].hi;
         const uint64_t wl = lo >= 0 ? nd[lo].freq : 0, wh = hi >= 0 ? nd[hi].freq : 0;
+        /* `i` (the parent of the level below) has a sibling here: the promotion test of the
+         * level below compares against its weight */
+        if (below_is_right && below_weight > (i == lo ? wh : wl)) { may_promote = 1; }
         nd[p].freq = wl + wh;
+        int32_t right = hi;
         if (lo >= 0 && hi >= 0 && wl > wh) { /* heavier child goes right */
             nd[p].lo = hi;
             nd[p].hi = lo;
             relabel(t, p);
             i = (i == lo) ? hi : lo;
+            right = lo;
         }
+        below_is_right = (i == right);
+        below_weight = (i == lo) ? wl : wh;
         node_at[levels] = i;
         parent_at[levels] = p;
         levels++;
         i = p;
     }
+    if (!may_promote) { return; }
     while (levels > 0) {
         levels--;
         const int32_t p = parent_at[levels];
