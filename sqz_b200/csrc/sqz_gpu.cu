@@ -536,8 +536,18 @@ static int launch_v2(const uint8_t* d_shard, size_t back, size_t n, size_t ahead
     t_lo = std::min(t_lo, tiles);
     t_hi = std::max(std::min(t_hi, tiles), t_lo);
     if ((unsigned long long)n > 0xFFFFFFFFull) { return fail(EINVAL, "shard too large for one launch"); }
-    unsigned int* d_counters = nullptr;               // segment cursor of phase 2 (stream-ordered scratch)
-    CU(cudaMallocAsync((void**)&d_counters, 16, s));
+    // segment cursor of phase 2: one of a small ring of device counters set up once per device
+    // (no stream-ordered allocation on the hot path: the pool ties streams together)
+    constexpr unsigned kRing = 256;
+    static unsigned int* rings[kMaxDevices];
+    static std::atomic<unsigned> ring_next[kMaxDevices];
+    static std::once_flag ring_once[kMaxDevices];
+    std::call_once(ring_once[dev], [dev] {
+        rings[dev] = nullptr;
+        if (cudaMalloc((void**)&rings[dev], kRing * 16) != cudaSuccess) { rings[dev] = nullptr; cudaGetLastError(); }
+    });
+    if (rings[dev] == nullptr) { return fail(ENOMEM, "cannot allocate the phase 2 cursors"); }
+    unsigned int* d_counters = rings[dev] + 4 * (ring_next[dev].fetch_add(1) % kRing);
     CU(cudaMemsetAsync(d_counters, 0, 16, s));
     const int smem_main = v2::geometry(max_len, max_dist, false).smem_bytes;
     const int smem_edge = v2::geometry(max_len, max_dist, true).smem_bytes;
@@ -582,7 +592,6 @@ static int launch_v2(const uint8_t* d_shard, size_t back, size_t n, size_t ahead
                                                      (uint32_t)kMinLen, max_len, max_dist, d_table, d_counters,
                                                      g_tile_cycles ? g_tile_cycles + (1 << 20) : nullptr);
     LAUNCHED("match_finish_marked");
-    CU(cudaFreeAsync(d_counters, s));
     return 0;
 }
 
