@@ -60,6 +60,7 @@ constexpr int kTilePos = kTileBlocks * 32;            // positions per CTA
 #define SQZ_GATED 3
 #endif
 constexpr int kGated = SQZ_GATED;         // need is tracked exactly up to min_len + kGated
+constexpr int kStageBlocks = 448;         // staging piece: 448 x 32 B + alignment slack fits in best_len
 constexpr uint8_t kHandOver = 0xFF;       // best_len mark: finish this position in phase 2
 constexpr uint32_t kOpenBit = 0x80000000u; // table word mark: position is finished by the phase 2 kernel
 
@@ -232,23 +233,54 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     // ---- stage: bytes -> bit planes (and validity), zero this tile's outputs ----
+    // The window + tile arrive in pieces of kStageBlocks*32 bytes: 16-byte cp.async copies
+    // (global -> shared, no registers) into a staging area -- the best_len bytes, unused until
+    // the scan starts -- then warp ballots transpose every 32 bytes into 8 plane words.
     {
         uint32_t* PLw = reinterpret_cast<uint32_t*>(smem_raw);
-        for (int blk = warp; blk < geo.plane_blocks; blk += kWarps) {
-            const long long pos = plane_pos0 + (long long)blk * 32 + lane;
-            const bool ok = pos >= -back && pos < n + ahead;
-            const uint32_t byte = ok ? (uint32_t)__ldg(shard + pos) : 0u;
-            uint32_t mine = 0;
+        uint8_t* stage = best_len;
+        const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+        const uintptr_t valid_lo = reinterpret_cast<uintptr_t>(shard) - (uintptr_t)back;
+        const uintptr_t valid_hi = reinterpret_cast<uintptr_t>(shard) + (uintptr_t)(n + ahead);
+        for (int b0 = 0; b0 < geo.plane_blocks; b0 += kStageBlocks) {
+            const int nb = min(kStageBlocks, geo.plane_blocks - b0);
+            const uint8_t* src0 = shard + plane_pos0 + 32LL * b0;
+            const int mis = (int)(reinterpret_cast<uintptr_t>(src0) & 15);
+            const uint8_t* base = src0 - mis;                   // 16-byte aligned
+            const int chunks = (mis + nb * 32 + 15) >> 4;
+            for (int c = threadIdx.x; c < chunks; c += kThreads) {
+                const uint8_t* g = base + 16 * c;
+                const uintptr_t ga = reinterpret_cast<uintptr_t>(g);
+                if (ga >= valid_lo && ga + 16 <= valid_hi) {
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n"
+                                 :: "r"(stage_s + 16u * (uint32_t)c), "l"(g) : "memory");
+                } else {                                        // chunk straddles the end of the data
 #pragma unroll
-            for (int b = 0; b < 8; b++) {
-                const uint32_t w = __ballot_sync(0xFFFFFFFFu, (byte >> b) & 1u);
-                if (lane == b) { mine = w; }
+                    for (int k = 0; k < 16; k++) {
+                        stage[16 * c + k] = (ga + k >= valid_lo && ga + k < valid_hi) ? __ldg(g + k) : (uint8_t)0;
+                    }
+                }
             }
-            if (lane < 8) { PLw[blk * 8 + lane] = mine; }
-            if (kEdge) {
-                const uint32_t v = __ballot_sync(0xFFFFFFFFu, ok);
-                if (lane == 0) { VL[blk] = v; }
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+            __syncthreads();
+            for (int blk = b0 + warp; blk < b0 + nb; blk += kWarps) {
+                const long long pos = plane_pos0 + (long long)blk * 32 + lane;
+                const bool ok = pos >= -back && pos < n + ahead;
+                const uint32_t byte = stage[mis + (blk - b0) * 32 + lane];   // zero where there is no data
+                uint32_t mine = 0;
+#pragma unroll
+                for (int bit = 0; bit < 8; bit++) {
+                    const uint32_t w = __ballot_sync(0xFFFFFFFFu, (byte >> bit) & 1u);
+                    if (lane == bit) { mine = w; }
+                }
+                if (lane < 8) { PLw[blk * 8 + lane] = mine; }
+                if (kEdge) {
+                    const uint32_t v = __ballot_sync(0xFFFFFFFFu, ok);
+                    if (lane == 0) { VL[blk] = v; }
+                }
             }
+            __syncthreads();                                    // the next piece overwrites the staging area
         }
         for (int k = threadIdx.x; k < kTilePos + 32; k += kThreads) { best_len[k] = 0; }
         for (int k = threadIdx.x; k < kTilePos; k += kThreads) {
