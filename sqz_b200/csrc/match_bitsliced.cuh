@@ -9,9 +9,8 @@
 //     plane b is bit b of byte i.  For a block of 32 consecutive positions and a
 //     distance d, "byte i equals byte i-d" for all 32 positions is
 //         E = AND_b ~( plane_b[i..i+31] ^ plane_b[i-d..i-d+31] )
-//     i.e. one funnel shift + one LOP3 per plane: 17 integer instructions for
-//     32 candidate-compares, where a thread-per-position kernel needs 32 loads
-//     and 32 compares.
+//     i.e. one funnel shift + one LOP3 per plane for 32 candidate-compares, where
+//     a thread-per-position kernel needs 32 loads and 32 compares.
 //   * Per-position state is bit-sliced too: the run length a candidate has to
 //     reach to beat the position's current best, need = best+1 (exact up to
 //     min_len+3, anything longer counts as min_len+3), is kept as a thermometer
@@ -25,9 +24,9 @@
 //     (7 funnel shifts per plane for 16 block-distance pairs).  Positions whose
 //     best was set inside the current group accept a nearer equal run, so the
 //     result is still "longest, nearest among equals".
-//   * Survivors of the multiplexer take a scalar path: the run is measured from
-//     the same E bits (32-bit window), compared with the position's current
-//     best and recorded as (len, dist).
+//   * Survivors of that test take a scalar path: the run is measured from the
+//     same E bits (32-bit window), compared with the position's current best and
+//     recorded as (len, dist).
 //
 // Phase 2 (few positions, separate kernel finish_marked):
 //   Positions whose run leaves the 32-bit window (matches of >= 32 bytes, the
@@ -41,8 +40,8 @@
 //
 // Work split in phase 1: a thread owns kQ consecutive blocks (32*kQ positions)
 // for the whole scan, so all per-position state is private to one thread: no
-// atomics, no inter-thread ordering.  Lane 31 of every warp recomputes the
-// first kQ blocks of the next warp as look-ahead only (its positions are closed).
+// atomics, no inter-thread ordering.  The last block of every warp is the first
+// block of the next warp, recomputed as look-ahead only (its positions are closed).
 #pragma once
 
 #include <cstdint>
@@ -66,9 +65,9 @@ constexpr uint32_t kOpenBit = 0x80000000u; // table word mark: position is finis
 
 struct Geometry {            // identical for all CTAs of a launch
     int back_blocks;         // plane blocks staged before the tile: ceil(max_dist/32) + 2*kQ
-    int ahead_blocks;        // after the tile: look-ahead lane + slack
+    int ahead_blocks;        // after the tile: look-ahead block + slack
     int plane_blocks;
-    int region_bytes;        // planes (phase 1) / raw bytes (phase 2) share this region
+    int region_bytes;        // the bit planes
     int smem_bytes;
 };
 
@@ -77,10 +76,9 @@ __host__ __device__ inline Geometry geometry(uint32_t max_len, uint32_t max_dist
     g.back_blocks = (int)((max_dist + 31) / 32) + 2 * kQ;   // a group of kQ word distances + its window
     g.ahead_blocks = kQ + 2;
     g.plane_blocks = g.back_blocks + kTileBlocks + g.ahead_blocks;
-    const int plane_bytes = g.plane_blocks * 32;                           // 8 planes x 4 B per block
-    const int raw_bytes = (int)max_dist + kTilePos + (int)max_len + 64;    // phase 2 image
-    g.region_bytes = ((plane_bytes > raw_bytes ? plane_bytes : raw_bytes) + 15) & ~15;
-    int bytes = g.region_bytes + kTilePos + 32;                            // + u8 best length per position
+    (void)max_len;
+    g.region_bytes = g.plane_blocks * 32;                                  // 8 planes x 4 B per block
+    int bytes = g.region_bytes + kTilePos + 32;                            // + one state byte per position
     if (edge) { bytes += g.plane_blocks * 4; }                             // validity plane
     g.smem_bytes = (bytes + 15) & ~15;
     return g;
@@ -92,7 +90,7 @@ __device__ __forceinline__ uint32_t fsr(uint32_t lo, uint32_t hi, int s) {
 
 // ---------------------------------------------------------------------------
 // phase 2: one warp finishes one position with the exact search on raw bytes.
-// S = 4-byte aligned byte image (shared or global), S[xi] = the position's first
+// S = 4-byte aligned byte image, S[xi] = the position's first
 // byte, x_end = one past the last readable byte; candidates S[xi-d] for d up to
 // `reach`; `room` = min(max_len, bytes left).  (best, bdist) enter with what
 // phase 1 found (all distances <= bdist are settled) and leave final.
