@@ -47,6 +47,19 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+// Bounds-checked build (-DSQZ_BOUNDS, tools/sanitize_case.py): every indexed access of the
+// kernels is range-checked and traps with a message.  compute-sanitizer is not available on
+// the GPU pool, so this is how out-of-range accesses are looked for.
+#ifdef SQZ_BOUNDS
+#include <cstdio>
+#define SQZ_CHECK(cond, what)                                                             \
+    do {                                                                                  \
+        if (!(cond)) { printf("SQZ_BOUNDS: %s (line %d)\n", what, __LINE__); __trap(); }  \
+    } while (0)
+#else
+#define SQZ_CHECK(cond, what) do { } while (0)
+#endif
+
 namespace v2 {
 
 constexpr int kWarps = 4;                 // warps per CTA
@@ -158,6 +171,7 @@ __device__ __noinline__ void finish_position(const uint8_t* __restrict__ S, int 
             uint32_t hb = 0;
             n_steps++;
             if ((w << 2) + 3 >= c_lo) {
+                SQZ_CHECK(w >= 0 && w <= w_last, "finish: candidate word outside the image");
                 const uint32_t low = W[w], hiw = word_at(W, w + 1, w_last);
                 const uint32_t t0 = (low ^ key) & mask;
                 const uint32_t t1 = (__byte_perm(low, hiw, 0x4321) ^ key) & mask;
@@ -171,6 +185,7 @@ __device__ __noinline__ void finish_position(const uint8_t* __restrict__ S, int 
                 if (hb != 0 && so >= 0) {
                     const int w2 = w - back_words;         // >= 0: the window lies inside the match
                     // words below the image start can only feed candidates that are cut off anyway
+                    SQZ_CHECK(w2 <= w_last, "finish: second window outside the image");
                     const uint32_t x0 = w2 >= 0 ? W[w2] : 0u;
                     const uint32_t x1 = w2 + 1 >= 0 ? word_at(W, w2 + 1, w_last) : 0u;
                     const uint32_t x2 = w2 + 2 >= 0 ? word_at(W, w2 + 2, w_last) : 0u;
@@ -195,6 +210,7 @@ __device__ __noinline__ void finish_position(const uint8_t* __restrict__ S, int 
                 for (uint32_t base = 0; base < room; base += 32) {
                     n_rounds++;
                     const uint32_t k = base + (uint32_t)lane;
+                    SQZ_CHECK(k >= room || (xi - (int)hit_d + (int)k >= 0 && xi + (int)k < x_end), "finish: verify outside the image");
                     const bool diff = k < room && S[xi + (int)k] != S[xi - (int)hit_d + (int)k];
                     const uint32_t bal = __ballot_sync(0xFFFFFFFFu, diff);
                     if (bal != 0) { m = base + (uint32_t)(__ffs((int)bal) - 1); break; }
@@ -298,6 +314,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
     uint32_t G[kGated][kQ], closed_m[kQ];
 #pragma unroll
     for (int q = 0; q < kQ; q++) {
+        SQZ_CHECK(blk0 + q >= 0 && blk0 + q < geo.plane_blocks, "phase 1: query plane block out of range");
         const uint4 a = PL[2 * (blk0 + q)], b = PL[2 * (blk0 + q) + 1];
         qv[q][0] = a.x; qv[q][1] = a.y; qv[q][2] = a.z; qv[q][3] = a.w;
         qv[q][4] = b.x; qv[q][5] = b.y; qv[q][6] = b.z; qv[q][7] = b.w;
@@ -336,6 +353,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
         const int jb = blk0 - m0 - (kQ - 1);
 #pragma unroll
         for (int j = 0; j < 2 * kQ; j++) {
+            SQZ_CHECK(jb + j >= 0 && jb + j < geo.plane_blocks, "phase 1: candidate plane block out of range");
             const uint4 a = PL[2 * (jb + j)], b = PL[2 * (jb + j) + 1];
             cr[j][0] = a.x; cr[j][1] = a.y; cr[j][2] = a.z; cr[j][3] = a.w;
             cr[j][4] = b.x; cr[j][5] = b.y; cr[j][6] = b.z; cr[j][7] = b.w;
@@ -404,6 +422,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                             todo &= todo - 1;
                             const uint32_t bit = 1u << p;
                             const int k = (own0 + q) * 32 + p;          // tile-relative position
+                            SQZ_CHECK(k >= 0 && k < kTilePos && tile_pos0 + k < n, "phase 1: survivor outside the tile or the shard");
                             const uint32_t state = best_len[k];         // low 5 bits: best, high 3: near-ties seen
                             const uint32_t have = state & 31u;
                             const uint32_t lo = e[q][t], hi = q + 1 < kQ ? e[q + 1][t] : en[t];
@@ -510,6 +529,7 @@ finish_marked(const uint8_t* __restrict__ shard, long long back, long long n, lo
                 bool inherited = false;
                 if ((nb & kOpenBit) == 0 && nlen >= min_len && nlen < max_len && ndist <= far &&
                     nlen + 1 <= room) {
+                    SQZ_CHECK(p - (long long)ndist >= -back && p < n + ahead, "phase 2: inheritance byte outside the data");
                     if (shard[p] == shard[p - (long long)ndist]) {
                         best = nlen + 1;
                         bdist = ndist;
@@ -522,6 +542,7 @@ finish_marked(const uint8_t* __restrict__ shard, long long back, long long n, lo
                     const int mis = (int)(reinterpret_cast<uintptr_t>(lo) & 3);
                     const long long left = n + ahead - p;
                     const int x_end = mis + (int)far + (int)min(left, (long long)max_len + 8);
+                    SQZ_CHECK(p - (long long)far >= -back && p + (long long)room <= n + ahead, "phase 2: search window outside the data");
                     finish_position(lo - mis, mis + (int)far, x_end, far, room, min_len, best, bdist, lane, dbg);
                 } else if (dbg != nullptr && lane == 0) {
                     atomicAdd(dbg + 5, 1ull);
