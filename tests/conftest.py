@@ -10,6 +10,16 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+def _ensure_built():
+    """The product library is built in-tree; make sure it exists before anything loads it."""
+    from sqz_b200 import build
+    if build.stale():
+        build.build()
+
+
+_ensure_built()
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
