@@ -72,6 +72,10 @@ constexpr int kTilePos = kTileBlocks * 32;            // positions per CTA
 #define SQZ_GATED 3
 #endif
 constexpr int kGated = SQZ_GATED;         // need is tracked exactly up to min_len + kGated
+#ifndef SQZ_TIE_MASK
+#define SQZ_TIE_MASK 0
+#endif
+constexpr uint32_t kTieMask = SQZ_TIE_MASK;   // a rejected survivor is counted when (d & kTieMask) == 0; the 7th hands the position over
 constexpr int kStageBlocks = 448;         // staging piece: 448 x 32 B + alignment slack fits in best_len
 constexpr uint8_t kHandOver = 0xFF;       // best_len mark: finish this position in phase 2
 constexpr uint32_t kOpenBit = 0x80000000u; // table word mark: position is finished by the phase 2 kernel
@@ -345,6 +349,8 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
     uint32_t fresh[kQ];
 #pragma unroll
     for (int q = 0; q < kQ; q++) { fresh[q] = 0; }
+    // debugging aid (tools/tile_cycles.py): what the scalar path sees
+    unsigned int c_surv = 0, c_better = 0, c_tie_fresh = 0, c_reject = 0, c_hand = 0, c_iter_slow = 0;
 
     for (int m0 = 1; m0 <= m_end; m0 += kQ) {
         // raw candidate words j = 0..2*kQ-1 <-> plane block blk0 - m0 - (kQ-1) + j
@@ -410,6 +416,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
             }
             if (none != 0xFFFFFFFFu) {
                 // ---- scalar path: exact decision for the few surviving positions ----
+                c_iter_slow++;
 #pragma unroll
                 for (int t = 0; t < kQ; t++) {
                     const uint32_t d = (uint32_t)(32 * (m0 + t) - sh);
@@ -422,6 +429,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                             todo &= todo - 1;
                             const uint32_t bit = 1u << p;
                             const int k = (own0 + q) * 32 + p;          // tile-relative position
+                            c_surv++;
                             SQZ_CHECK(k >= 0 && k < kTilePos && tile_pos0 + k < n, "phase 1: survivor outside the tile or the shard");
                             const uint32_t state = best_len[k];         // low 5 bits: best, high 3: near-ties seen
                             const uint32_t have = state & 31u;
@@ -434,12 +442,14 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                                 best_len[k] = kHandOver;
                                 *slot = (fresh[q] & bit) ? kOpenBit : (*slot | kOpenBit);
                                 closed_m[q] |= bit;
+                                c_hand++;
                                 continue;
                             }
                             const uint32_t run = (uint32_t)(__ffs((int)win) - 1);
                             bool better = run > have;
-                            if (run == have && (fresh[q] & bit)) { better = d < (*slot & 0xFFFFu); }
+                            if (run == have && (fresh[q] & bit)) { better = d < (*slot & 0xFFFFu); c_tie_fresh++; }
                             if (better) {
+                                c_better++;
                                 best_len[k] = (uint8_t)run;
                                 *slot = (run << 16) | d;
                                 fresh[q] |= bit;
@@ -447,7 +457,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                                 for (int g = 0; g < kGated; g++) {
                                     if (run > (uint32_t)(kMinLen + g)) { G[g][q] |= bit; }
                                 }
-                            } else if ((d & 15u) == 0) {
+                            } else if ((c_reject++, (d & kTieMask) == 0)) {
                                 // a candidate that only ties or falls short: count a sample of them; a
                                 // position that keeps attracting them is cheaper to finish in phase 2
                                 if (state >= 0xC0u) {
@@ -472,7 +482,11 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
             fresh[q] = 0;
         }
     }
-    if (tile_cycles != nullptr) {          // debugging aid: per-tile duration
+    if (tile_cycles != nullptr) {          // debugging aid: per-tile duration and scalar-path counts
+        unsigned long long* dbg2 = tile_cycles + (1 << 20) + 8;
+        atomicAdd(dbg2 + 0, (unsigned long long)c_surv); atomicAdd(dbg2 + 1, (unsigned long long)c_better);
+        atomicAdd(dbg2 + 2, (unsigned long long)c_tie_fresh); atomicAdd(dbg2 + 3, (unsigned long long)c_reject);
+        atomicAdd(dbg2 + 4, (unsigned long long)c_hand); atomicAdd(dbg2 + 5, (unsigned long long)c_iter_slow);
         __syncthreads();
         if (threadIdx.x == 0) { tile_cycles[tile] = (unsigned long long)(clock64() - t_begin); }
     }
@@ -527,21 +541,29 @@ finish_marked(const uint8_t* __restrict__ shard, long long back, long long n, lo
                 if (p + 1 < n) { nb = (p + 1 == known_pos) ? known_word : table[p + 1]; }
                 const uint32_t nlen = (nb >> 16) & 0x7FFFu, ndist = nb & 0xFFFFu;
                 bool inherited = false;
-                if ((nb & kOpenBit) == 0 && nlen >= min_len && nlen < max_len && ndist <= far &&
-                    nlen + 1 <= room) {
+                const bool usable = (nb & kOpenBit) == 0 && nlen >= min_len && ndist >= 1 && ndist <= far;
+                // local byte image for a search: starts at the farthest candidate, rounded down to a word
+                const uint8_t* lo = shard + p - (long long)far;
+                const int mis = (int)(reinterpret_cast<uintptr_t>(lo) & 3);
+                const long long left = n + ahead - p;
+                const int x_end = mis + (int)far + (int)min(left, (long long)max_len + 8);
+                if (usable && nlen + 1 <= room && nlen < max_len) {
                     SQZ_CHECK(p - (long long)ndist >= -back && p < n + ahead, "phase 2: inheritance byte outside the data");
                     if (shard[p] == shard[p - (long long)ndist]) {
                         best = nlen + 1;
                         bdist = ndist;
                         inherited = true;
                     }
+                } else if (usable && nlen == max_len && room == max_len && ndist == 1) {
+                    // inside a run of one byte value: the position above holds max_len at distance 1;
+                    // if byte p continues the run, so does this one, and nothing is nearer than 1
+                    if (shard[p] == shard[p - 1]) {
+                        best = max_len;
+                        bdist = 1;
+                        inherited = true;
+                    }
                 }
                 if (!inherited) {
-                    // local byte image: starts at the farthest candidate, rounded down to a word
-                    const uint8_t* lo = shard + p - (long long)far;
-                    const int mis = (int)(reinterpret_cast<uintptr_t>(lo) & 3);
-                    const long long left = n + ahead - p;
-                    const int x_end = mis + (int)far + (int)min(left, (long long)max_len + 8);
                     SQZ_CHECK(p - (long long)far >= -back && p + (long long)room <= n + ahead, "phase 2: search window outside the data");
                     finish_position(lo - mis, mis + (int)far, x_end, far, room, min_len, best, bdist, lane, dbg);
                 } else if (dbg != nullptr && lane == 0) {
