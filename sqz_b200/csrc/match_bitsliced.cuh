@@ -79,6 +79,8 @@ constexpr uint32_t kTieMask = SQZ_TIE_MASK;   // a rejected survivor is counted 
 constexpr int kStageBlocks = 448;         // staging piece: 448 x 32 B + alignment slack fits in best_len
 constexpr uint8_t kHandOver = 0xFF;       // best_len mark: finish this position in phase 2
 constexpr uint32_t kOpenBit = 0x80000000u; // table word mark: position is finished by the phase 2 kernel
+constexpr int kResumeShift = 26;          // bits 26..30 of an open word: distance/1024 below which all is settled
+constexpr uint32_t kStateMask = 0x03FFFFFFu; // (len << 16) | dist of an open word
 
 struct Geometry {            // identical for all CTAs of a launch
     int back_blocks;         // plane blocks staged before the tile: ceil(max_dist/32) + 2*kQ
@@ -110,7 +112,7 @@ __device__ __forceinline__ uint32_t fsr(uint32_t lo, uint32_t hi, int s) {
 // S = 4-byte aligned byte image, S[xi] = the position's first
 // byte, x_end = one past the last readable byte; candidates S[xi-d] for d up to
 // `reach`; `room` = min(max_len, bytes left).  (best, bdist) enter with what
-// phase 1 found (all distances <= bdist are settled) and leave final.
+// phase 1 found (all distances < max(bdist+1, d_from) are settled) and leave final.
 //
 // 32 lanes x 4 candidates per step: every lane takes one aligned word and tests
 // the four byte offsets in it against the 4 bytes a candidate has to match to
@@ -146,13 +148,13 @@ __device__ __forceinline__ int pick_second_window(const uint32_t* __restrict__ W
 }
 
 __device__ __noinline__ void finish_position(const uint8_t* __restrict__ S, int xi, int x_end,
-                                             uint32_t reach, uint32_t room, uint32_t min_len,
+                                             uint32_t d_from, uint32_t reach, uint32_t room, uint32_t min_len,
                                              uint32_t& best, uint32_t& bdist, int lane,
                                              unsigned long long* dbg = nullptr) {
     const uint32_t* W = reinterpret_cast<const uint32_t*>(S);
     const int w_last = (x_end - 1) >> 2;
     unsigned int n_steps = 0, n_verify = 0, n_rounds = 0, n_improve = 0;
-    uint32_t d0 = bdist + 1;
+    uint32_t d0 = max(bdist + 1, d_from);              // everything nearer is settled
     while (d0 <= reach && best < room) {
         const uint32_t need = max(best + 1, min_len);
         if (need > room) { break; }
@@ -357,6 +359,9 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
         uint32_t cr[2 * kQ][8];
         uint32_t vr[2 * kQ];
         const int jb = blk0 - m0 - (kQ - 1);
+        // a position handed over in this group (and not fresh) has every distance below the
+        // group's first one settled: phase 2 resumes there (in units of 1024, rounded down)
+        const uint32_t resume_tag = (uint32_t)min(31, (32 * (m0 - 1) + 1) >> 10) << kResumeShift;
 #pragma unroll
         for (int j = 0; j < 2 * kQ; j++) {
             SQZ_CHECK(jb + j >= 0 && jb + j < geo.plane_blocks, "phase 1: candidate plane block out of range");
@@ -440,7 +445,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                                 // at least 32 equal bytes: longer than the window, phase 2 finishes it.
                                 // A fresh best may still have a nearer equal: let phase 2 start over.
                                 best_len[k] = kHandOver;
-                                *slot = (fresh[q] & bit) ? kOpenBit : (*slot | kOpenBit);
+                                *slot = (fresh[q] & bit) ? kOpenBit : (*slot | kOpenBit | resume_tag);
                                 closed_m[q] |= bit;
                                 c_hand++;
                                 continue;
@@ -462,7 +467,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                                 // position that keeps attracting them is cheaper to finish in phase 2
                                 if (state >= 0xC0u) {
                                     best_len[k] = kHandOver;
-                                    *slot = (fresh[q] & bit) ? kOpenBit : (*slot | kOpenBit);
+                                    *slot = (fresh[q] & bit) ? kOpenBit : (*slot | kOpenBit | resume_tag);
                                     closed_m[q] |= bit;
                                 } else {
                                     best_len[k] = (uint8_t)(state + 32u);
@@ -532,7 +537,9 @@ finish_marked(const uint8_t* __restrict__ shard, long long back, long long n, lo
                 const int src = 31 - __clz((int)marks);             // highest position first
                 marks &= ~(1u << src);
                 const long long p = top - 32 + src;
-                const uint32_t word = __shfl_sync(0xFFFFFFFFu, mine, src) & ~kOpenBit;
+                const uint32_t raw = __shfl_sync(0xFFFFFFFFu, mine, src);
+                const uint32_t word = raw & kStateMask;
+                const uint32_t resume = ((raw >> kResumeShift) & 31u) << 10;   // phase 1 settled every nearer distance
                 uint32_t best = word >> 16, bdist = word & 0xFFFFu;
                 const uint32_t room = (uint32_t)min((long long)max_len, n + ahead - p);
                 const uint32_t far = (uint32_t)min((long long)max_dist, p + back);
@@ -565,7 +572,7 @@ finish_marked(const uint8_t* __restrict__ shard, long long back, long long n, lo
                 }
                 if (!inherited) {
                     SQZ_CHECK(p - (long long)far >= -back && p + (long long)room <= n + ahead, "phase 2: search window outside the data");
-                    finish_position(lo - mis, mis + (int)far, x_end, far, room, min_len, best, bdist, lane, dbg);
+                    finish_position(lo - mis, mis + (int)far, x_end, resume, far, room, min_len, best, bdist, lane, dbg);
                 } else if (dbg != nullptr && lane == 0) {
                     atomicAdd(dbg + 5, 1ull);
                 }
