@@ -76,6 +76,10 @@ constexpr int kGated = SQZ_GATED;         // need is tracked exactly up to min_l
 #define SQZ_TIE_MASK 0
 #endif
 constexpr uint32_t kTieMask = SQZ_TIE_MASK;   // a rejected survivor is counted when (d & kTieMask) == 0; the 7th hands the position over
+#ifndef SQZ_TIE_LIMIT
+#define SQZ_TIE_LIMIT 6
+#endif
+constexpr uint32_t kTieLimit = SQZ_TIE_LIMIT; // rejected survivors a position may collect before the next one hands it over (<= 6)
 constexpr int kStageBlocks = 448;         // staging piece: 448 x 32 B + alignment slack fits in best_len
 constexpr uint8_t kHandOver = 0xFF;       // best_len mark: finish this position in phase 2
 constexpr uint32_t kOpenBit = 0x80000000u; // table word mark: position is finished by the phase 2 kernel
@@ -176,7 +180,9 @@ __device__ __noinline__ void finish_position(const uint8_t* __restrict__ S, int 
             const int w = wtop - lane;                     // lane 0 holds the nearest word
             uint32_t hb = 0;
             n_steps++;
-            if ((w << 2) + 3 >= c_lo) {
+            // interior steps: all 128 candidates of the warp lie strictly inside (c_lo, c_hi]
+            const bool interior = (wtop << 2) + 3 <= c_hi && ((wtop - 31) << 2) >= c_lo;
+            if (interior || (w << 2) + 3 >= c_lo) {
                 SQZ_CHECK(w >= 0 && w <= w_last, "finish: candidate word outside the image");
                 const uint32_t low = W[w], hiw = word_at(W, w + 1, w_last);
                 const uint32_t t0 = (low ^ key) & mask;
@@ -184,10 +190,12 @@ __device__ __noinline__ void finish_position(const uint8_t* __restrict__ S, int 
                 const uint32_t t2 = (__byte_perm(low, hiw, 0x5432) ^ key) & mask;
                 const uint32_t t3 = (__byte_perm(low, hiw, 0x6543) ^ key) & mask;
                 hb = (t0 == 0 ? 1u : 0u) | (t1 == 0 ? 2u : 0u) | (t2 == 0 ? 4u : 0u) | (t3 == 0 ? 8u : 0u);
-                const int kmax = min(3, c_hi - (w << 2));  // only the very first word is cut at the top
-                const int kmin = max(0, c_lo - (w << 2));
-                hb &= (2u << kmax) - 1u;
-                hb &= ~((1u << kmin) - 1u);
+                if (!interior) {
+                    const int kmax = min(3, c_hi - (w << 2));  // only the very first word is cut at the top
+                    const int kmin = max(0, c_lo - (w << 2));
+                    hb &= (2u << kmax) - 1u;
+                    hb &= ~((1u << kmin) - 1u);
+                }
                 if (hb != 0 && so >= 0) {
                     const int w2 = w - back_words;         // >= 0: the window lies inside the match
                     // words below the image start can only feed candidates that are cut off anyway
@@ -465,7 +473,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                             } else if ((c_reject++, (d & kTieMask) == 0)) {
                                 // a candidate that only ties or falls short: count a sample of them; a
                                 // position that keeps attracting them is cheaper to finish in phase 2
-                                if (state >= 0xC0u) {
+                                if (state >= (kTieLimit << 5)) {
                                     best_len[k] = kHandOver;
                                     *slot = (fresh[q] & bit) ? kOpenBit : (*slot | kOpenBit | resume_tag);
                                     closed_m[q] |= bit;
