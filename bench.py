@@ -44,6 +44,7 @@ MIN_LEN, MAX_LEN, MAX_DIST = 3, 257, WINDOW - 1      # reference G1 rules, squee
 SMEM_BYTES_PER_CLK_PER_SM = 128
 SMS = 148
 METRIC = "match_search_input_MBps"
+TRAFFIC_1GIB = 1215603712 + 4293076480   # bytes, ncu, dominant kernel, one launch on a 1 GiB shard
 KERNEL_ALU_INSTR = 354       # LOP3 + SHF per iteration of the hot loop (ncu source page, round 1 final kernel)
 KERNEL_CC_PER_STEP = 16256   # 127 owned blocks x 32 positions x 4 distances per warp and iteration
 
@@ -393,7 +394,8 @@ def ours(args) -> None:
         "roofline": {
             "bound": "smem", "kernel": "match_table",
             "achieved": achieved, "peak": smem_peak, "unit": "GB/s",
-            "frac": achieved / smem_peak if achieved else None, "traffic": None,
+            "frac": achieved / smem_peak if achieved else None,
+            "traffic": TRAFFIC_1GIB if n == (1 << 30) else None,
             "note": "algorithmic shared-memory bytes = 4 B per candidate-compare (SURVEY 8d), %d CC per launch; "
                     "peak = 128 B/clk/SM x 148 SMs x %.0f MHz (SM clock sampled under this load); "
                     "north_star fixes the smem compare bound, HBM is shown in 'hbm'" % (cc, f_mhz),
@@ -407,8 +409,9 @@ def ours(args) -> None:
                 "note": "achieved counts the whole sqz_gpu_match_table_device call: bit-sliced kernel, edge tiles "
                         "and the finish kernel",
             },
-            "traffic_note": "ncu --set full on a 16 MiB shard (profiles/r01_match_table_ncu_full.txt): 2.0 B of DRAM "
-                            "traffic per input byte while the table still sits in L2; algorithmic 5 B per input byte",
+            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of v2::match_table<3,false> on a 1 GiB shard "
+                            "(profiles/r01_dram_traffic_bench_size.csv: 1.22 GB read + 4.29 GB written; algorithmic "
+                            "1.07 + 4.29 GB); the finish kernel adds 4.96 GB read + 0.82 GB written (it scans the table)",
         },
         "hbm": {"achieved": hbm_bytes / t_match / 1e9 if t_match > 0 else None, "peak": hbm_peak, "unit": "GB/s",
                 "frac": hbm_bytes / t_match / 1e9 / hbm_peak if t_match > 0 else None,
