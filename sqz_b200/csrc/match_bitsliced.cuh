@@ -578,6 +578,17 @@ finish_marked(const uint8_t* __restrict__ shard, long long back, long long n, lo
                         inherited = true;
                     }
                 }
+                if (!inherited && dbg != nullptr && lane == 0) {
+                    // why not: 16 neighbour open, 17 neighbour without a match, 18 neighbour at max_len (d != 1 or byte differs),
+                    // 19 byte differs, 20 no neighbour in this shard, 21 other
+                    int why = 21;
+                    if (p + 1 >= n) { why = 20; }
+                    else if (nb & kOpenBit) { why = 16; }
+                    else if (nlen < min_len) { why = 17; }
+                    else if (nlen >= max_len) { why = 18; }
+                    else if (usable && nlen + 1 <= room) { why = 19; }
+                    atomicAdd(dbg + why, 1ull);
+                }
                 if (!inherited) {
                     SQZ_CHECK(p - (long long)far >= -back && p + (long long)room <= n + ahead, "phase 2: search window outside the data");
                     finish_position(lo - mis, mis + (int)far, x_end, resume, far, room, min_len, best, bdist, lane, dbg);

@@ -11,7 +11,7 @@ pad = torch.zeros(size + 1024, dtype=torch.uint8, device="cuda"); pad[:size] = d
 table = torch.empty(size, dtype=torch.int32, device="cuda")
 TP = 4 * (32 * 4 - 1) * 32      # v2::kTilePos
 tiles = (size + TP - 1) // TP
-cyc = torch.zeros((1 << 20) + 16, dtype=torch.int64, device="cuda")
+cyc = torch.zeros((1 << 20) + 64, dtype=torch.int64, device="cuda")
 L.sqz_gpu_debug_tile_cycles(cyc.data_ptr())
 for it in range(2):
     torch.cuda.synchronize()
@@ -21,6 +21,7 @@ for it in range(2):
     e1.record(); torch.cuda.synchronize()
     print("rc", rc, "ms", e0.elapsed_time(e1))
 call = cyc.cpu().numpy(); c = call[:tiles]; dbg = call[1 << 20:] // 2
+print('search reasons: neighbour open %d, neighbour has no match %d, neighbour at max_len %d, byte differs %d, shard end %d, other %d' % tuple(int(x) for x in dbg[16:22]))
 print('finish: searched %d (%.3f%%), inherited %d (%.3f%%), word-steps/search %.1f, verifies/search %.1f, improvements/search %.2f' % (dbg[0], 100.0*dbg[0]/size, dbg[5], 100.0*dbg[5]/size, dbg[1]/max(dbg[0],1), dbg[2]/max(dbg[0],1), dbg[3]/max(dbg[0],1)))
 print("tiles", tiles, "sum Gcyc", c.sum() / 1e9, "median", np.median(c), "p90", np.percentile(c, 90), "max", c.max())
 order = np.argsort(-c)[:12]
