@@ -57,38 +57,48 @@ struct sqz_bitstream {
     int    (*input)(struct sqz_bitstream* bs);
 };
 
-struct sqz_node {       /* one adaptive-Huffman node, huffman.h:13-20 */
-    uint64_t freq;
-    uint64_t path;      /* code, emitted LSB first */
-    int32_t  bits;      /* code length; 0 = root or unseen leaf */
-    int32_t  up;        /* parent, -1 = none */
-    int32_t  lo;        /* left child  (bit 0) */
-    int32_t  hi;        /* right child (bit 1) */
-};
-
-struct sqz_tree {       /* huffman.h:22-34 */
-    struct sqz_node* node;
-    int32_t n;          /* leaves; nodes = 2n-1, root = 2n-2 */
+/* One adaptive-Huffman tree (huffman.h:13-34) as a structure of arrays with
+ * 16-bit links.  Node k: leaves 0..n-1 (index == symbol), root 2n-2, internal
+ * nodes handed out downward from 2n-3.  freq[] has ten extra entries:
+ * freq[2n-1] = 0 and freq[2n] = 2^64-1, the comparators "always" and "never"
+ * of the plans, and eight spare slots that pad a plan (sqz_codec.c).  The
+ * root's own weight is only kept up to date by the exact walk.              */
+struct sqz_tree {
+    uint64_t* freq;     /* weights */
+    uint64_t* path;     /* code, emitted LSB first (huffman.h:16) */
+    uint64_t* code;     /* leaves only: the same code in emission order */
+    int16_t*  up;       /* parent, -1 = none */
+    int16_t*  lo;       /* left child  (bit 0) */
+    int16_t*  hi;       /* right child (bit 1) */
+    uint32_t* plan;     /* per leaf 16 x (node | comparator << 16), leaf to root */
+    uint8_t*  steps;    /* per leaf: plan length; 0 = no plan yet, 255 = deeper than a plan */
+    uint8_t*  bits;     /* code length; 0 = root or unseen leaf */
+    int32_t n;          /* leaves; nodes = 2n-1 */
     int32_t next;       /* internal nodes are handed out downward from here */
     int32_t depth;      /* high-water mark, reset by a root-level relabel */
     int32_t complete;   /* frozen: no more frequency updates */
 };
 
+#define SQZ_TREE_STORE(N) struct {                                          \
+    uint32_t plan[N][16];                                                     \
+    uint64_t freq[2 * (N) + 9]; uint64_t path[2 * (N) - 1]; uint64_t code[N]; \
+    int16_t up[2 * (N) - 1]; int16_t lo[2 * (N) - 1]; int16_t hi[2 * (N) - 1]; \
+    uint8_t steps[N]; uint8_t bits[2 * (N) - 1]; }
+
 struct sqz {
     int32_t error;      /* sticky errno: E2BIG, EINVAL, ENODEV, ENOMEM, EIO */
     int32_t device;     /* CUDA device for the match search; -1 (default) = the current one */
     struct sqz_bitstream* bs;
-    struct sqz_tree lit;
-    struct sqz_tree pos;
-    struct sqz_node lit_nodes[sqz_lit_symbols * 2 - 1];
-    struct sqz_node pos_nodes[sqz_pos_symbols * 2 - 1];
-    uint8_t len_index[sqz_max_len + 2]; /* len -> length bucket, squeeze.h:151-161 */
-    uint8_t pos_index[1u << 15];        /* dist -> distance bucket, squeeze.h:162-171 */
     /* statistics of the last sqz_compress (zero until then) */
     uint64_t tokens;
     uint64_t matches;
     double   search_seconds;            /* GPU search + parse + copies */
     double   entropy_seconds;           /* host adaptive-Huffman stage */
+    struct sqz_tree lit;
+    struct sqz_tree pos;
+    uint8_t len_index[sqz_max_len + 2]; /* len -> length bucket, squeeze.h:151-161 */
+    SQZ_TREE_STORE(sqz_lit_symbols) lit_store;
+    SQZ_TREE_STORE(sqz_pos_symbols) pos_store;
 };
 
 /* 64 raw bits of `bytes` then 8 raw bits of `win_bits`, each LSB first.
@@ -110,6 +120,15 @@ void sqz_compress(struct sqz* s, struct sqz_bitstream* bs,
  * squeeze.h:377-396 would.                                                  */
 void sqz_encode_tokens(struct sqz* s, struct sqz_bitstream* bs,
                        const uint32_t* tokens, uint64_t count);
+
+/* The same for symbol words -- tokens with the bucket arithmetic of
+ * squeeze.h:290-315 already done, which is what the GPU parse emits in
+ * `symbols` mode (include/sqz_gpu.h has the layout).  Words are trusted.     */
+void sqz_encode_symbols(struct sqz* s, struct sqz_bitstream* bs,
+                        const uint32_t* words, uint64_t count);
+/* token -> symbol word on the host (0xFFFFFFFF for a token the decoder would
+ * reject); the reference for what the GPU emits.                             */
+void sqz_symbols_of_tokens(const uint32_t* tokens, uint64_t count, uint32_t* words);
 
 void sqz_decompress(struct sqz* s, struct sqz_bitstream* bs,
                     uint8_t* data, uint64_t bytes);

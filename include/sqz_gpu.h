@@ -21,6 +21,18 @@
  * match = (len << 16) | dist.  A match-table word uses the same packing, with
  * 0 meaning "no match of at least min_len here".
  *
+ * Symbol word (what the host coder of sqz.h consumes directly, sqz_encode_symbols): the same
+ * token with the bucket arithmetic of squeeze_encode_len / squeeze_encode_pos
+ * (squeeze.h:290-315, tables squeeze.h:29-79,151-172) already done on the GPU:
+ *   bits  0..8   symbol of the literal/length tree: byte value, or 257 + length bucket
+ *   bits  9..13  the length's extra bits      (len - len_base[bucket])
+ *   bits 14..18  symbol of the distance tree  (distance bucket)
+ *   bits 19..31  the distance's extra bits    (dist - pos_base[bucket])
+ * Extra bits are stored in emission order, i.e. bit-reversed within their field
+ * width, because the bitstream takes values least significant bit first
+ * (bitstream.h:49-63).  Symbol words exist only within the bitstream's own
+ * limits: min_len >= 3, max_len <= 258, max_dist <= 32767.
+ *
  * Errors: 0, EINVAL (bad rule parameters), E2BIG (output capacity), ENOMEM,
  * ENODEV (no CUDA device / driver: there is NO CPU fallback), EIO (CUDA error;
  * sqz_gpu_last_error() has the text).
@@ -35,7 +47,7 @@
 extern "C" {
 #endif
 
-#define SQZ_GPU_ABI_VERSION 1
+#define SQZ_GPU_ABI_VERSION 2
 
 enum {
     sqz_gpu_max_len_limit  = 512,     /* parse hand-off tables are sized for this */
@@ -67,10 +79,12 @@ int sqz_gpu_tokens(const uint8_t* data, size_t bytes,
  * parse order, from double-buffered pinned memory while the device already
  * works on the next chunk.  *tokens stays valid until the next call.        */
 typedef struct sqz_gpu_stream sqz_gpu_stream;
+#define SQZ_GPU_STREAM_SYMBOLS 1u   /* deliver symbol words instead of plain tokens */
 int  sqz_gpu_stream_open(sqz_gpu_stream** st, int device,
                          const uint8_t* data, size_t bytes,
                          uint32_t window, uint32_t min_len, uint32_t max_len,
-                         uint32_t max_dist, size_t chunk_bytes /* 0 = default */);
+                         uint32_t max_dist, size_t chunk_bytes /* 0 = default */,
+                         uint32_t flags /* SQZ_GPU_STREAM_* */);
 int  sqz_gpu_stream_next(sqz_gpu_stream* st, const uint32_t** tokens, size_t* count);
 void sqz_gpu_stream_close(sqz_gpu_stream* st);
 
@@ -103,6 +117,15 @@ int sqz_gpu_parse_device(const uint8_t* d_shard, const uint32_t* d_table, size_t
                          uint32_t* d_tokens, size_t tokens_cap,
                          void* d_work, uint64_t* d_result /* 2 x u64, device */,
                          void* stream);
+
+/* The same parse, emitting symbol words (see above) instead of plain tokens:
+ * replaces squeeze.h:377-394 together with the table lookups and subtractions
+ * of squeeze.h:290-315.                                                      */
+int sqz_gpu_parse_symbols_device(const uint8_t* d_shard, const uint32_t* d_table, size_t n,
+                                 uint32_t entry, uint32_t min_len, uint32_t max_len,
+                                 uint32_t* d_words, size_t words_cap,
+                                 void* d_work, uint64_t* d_result /* 2 x u64, device */,
+                                 void* stream);
 
 /* Seam hand-off without waiting for the previous shard: exit_map[e] is the
  * overshoot this shard produces when entered at offset e, for every

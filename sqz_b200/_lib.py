@@ -31,25 +31,31 @@ Bitstream._fields_ = [
 ]
 
 
-class Node(C.Structure):
-    _fields_ = [("freq", C.c_uint64), ("path", C.c_uint64), ("bits", C.c_int32),
-                ("up", C.c_int32), ("lo", C.c_int32), ("hi", C.c_int32)]
-
-
 class Tree(C.Structure):
-    _fields_ = [("node", C.POINTER(Node)), ("n", C.c_int32), ("next", C.c_int32),
-                ("depth", C.c_int32), ("complete", C.c_int32)]
+    _fields_ = [("freq", u64p), ("path", u64p), ("code", u64p),
+                ("up", C.POINTER(C.c_int16)), ("lo", C.POINTER(C.c_int16)), ("hi", C.POINTER(C.c_int16)),
+                ("plan", u32p), ("steps", u8p), ("bits", u8p),
+                ("n", C.c_int32), ("next", C.c_int32), ("depth", C.c_int32), ("complete", C.c_int32)]
+
+
+def _store(n: int):
+    class Store(C.Structure):
+        _fields_ = [("plan", C.c_uint32 * 16 * n),
+                    ("freq", C.c_uint64 * (2 * n + 9)), ("path", C.c_uint64 * (2 * n - 1)), ("code", C.c_uint64 * n),
+                    ("up", C.c_int16 * (2 * n - 1)), ("lo", C.c_int16 * (2 * n - 1)), ("hi", C.c_int16 * (2 * n - 1)),
+                    ("steps", C.c_uint8 * n), ("bits", C.c_uint8 * (2 * n - 1))]
+    return Store
 
 
 class State(C.Structure):
     """struct sqz (include/sqz.h)."""
     _fields_ = [
         ("error", C.c_int32), ("device", C.c_int32), ("bs", C.POINTER(Bitstream)),
-        ("lit", Tree), ("pos", Tree),
-        ("lit_nodes", Node * 1023), ("pos_nodes", Node * 63),
-        ("len_index", C.c_uint8 * 259), ("pos_index", C.c_uint8 * 32768),
         ("tokens", C.c_uint64), ("matches", C.c_uint64),
         ("search_seconds", C.c_double), ("entropy_seconds", C.c_double),
+        ("lit", Tree), ("pos", Tree),
+        ("len_index", C.c_uint8 * 259),
+        ("lit_store", _store(512)), ("pos_store", _store(32)),
     ]
 
 
@@ -62,6 +68,8 @@ SYMBOLS = {
     "sqz_init": (None, [C.POINTER(State)]),
     "sqz_compress": (None, [C.POINTER(State), C.POINTER(Bitstream), u8p, C.c_uint64, C.c_uint32]),
     "sqz_encode_tokens": (None, [C.POINTER(State), C.POINTER(Bitstream), u32p, C.c_uint64]),
+    "sqz_encode_symbols": (None, [C.POINTER(State), C.POINTER(Bitstream), u32p, C.c_uint64]),
+    "sqz_symbols_of_tokens": (None, [u32p, C.c_uint64, u32p]),
     "sqz_decompress": (None, [C.POINTER(State), C.POINTER(Bitstream), u8p, C.c_uint64]),
     "sqz_compress_buffer": (C.c_int, [u8p, C.c_uint64, C.c_uint8, u8p, C.c_uint64, u64p]),
     "sqz_decompress_buffer": (C.c_int, [u8p, C.c_uint64, u8p, C.c_uint64, u64p]),
@@ -70,7 +78,7 @@ SYMBOLS = {
     "sqz_gpu_tokens": (C.c_int, [u8p, size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u32p, size_t,
                                  C.POINTER(size_t)]),
     "sqz_gpu_stream_open": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, u8p, size_t, C.c_uint32, C.c_uint32,
-                                      C.c_uint32, C.c_uint32, size_t]),
+                                      C.c_uint32, C.c_uint32, size_t, C.c_uint32]),
     "sqz_gpu_stream_next": (C.c_int, [C.c_void_p, C.POINTER(u32p), C.POINTER(size_t)]),
     "sqz_gpu_stream_close": (None, [C.c_void_p]),
     "sqz_gpu_match_table_device": (C.c_int, [C.c_void_p, size_t, size_t, size_t, C.c_uint32, C.c_uint32,
@@ -79,6 +87,8 @@ SYMBOLS = {
     "sqz_gpu_parse_workspace": (size_t, [size_t]),
     "sqz_gpu_parse_device": (C.c_int, [C.c_void_p, C.c_void_p, size_t, C.c_uint32, C.c_uint32, C.c_uint32,
                                        C.c_void_p, size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sqz_gpu_parse_symbols_device": (C.c_int, [C.c_void_p, C.c_void_p, size_t, C.c_uint32, C.c_uint32, C.c_uint32,
+                                               C.c_void_p, size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sqz_gpu_parse_exit_map_device": (C.c_int, [C.c_void_p, size_t, C.c_uint32, C.c_uint32, C.c_void_p,
                                                 C.c_void_p, C.c_void_p]),
     "sqz_gpu_abi_version": (C.c_int, []),

@@ -125,10 +125,9 @@ def compress(data, win_bits: int = 15, file_mode: bool = False, stats: dict | No
     return out[: bs.bytes].tobytes()
 
 
-def encode_tokens(toks, nbytes: int, win_bits: int = 15, file_mode: bool = False) -> bytes:
-    """Host entropy stage alone (squeeze.h:278-315 + huffman.h + bitstream.h) on a token list."""
-    L = _lib.load()
-    t = np.ascontiguousarray(toks, dtype=np.uint32)
+def _encode(entry: str, arr, nbytes: int, win_bits: int, file_mode: bool, lib=None) -> bytes:
+    L = lib or _lib.load()
+    t = np.ascontiguousarray(arr, dtype=np.uint32)
     out = np.empty(_capacity(nbytes) + 64, dtype=np.uint8)
     bs = Bitstream()
     sink = {"at": 0}
@@ -147,9 +146,27 @@ def encode_tokens(toks, nbytes: int, win_bits: int = 15, file_mode: bool = False
     _check(bs.error, "sqz_write_header")
     s = State()
     L.sqz_init(C.byref(s))
-    L.sqz_encode_tokens(C.byref(s), C.byref(bs), t.ctypes.data_as(u32p), t.size)
-    _check(s.error, "sqz_encode_tokens")
+    getattr(L, entry)(C.byref(s), C.byref(bs), t.ctypes.data_as(u32p), t.size)
+    _check(s.error, entry)
     return out[: bs.bytes].tobytes()
+
+
+def encode_tokens(toks, nbytes: int, win_bits: int = 15, file_mode: bool = False, lib=None) -> bytes:
+    """Host entropy stage alone (squeeze.h:278-315 + huffman.h + bitstream.h) on a token list."""
+    return _encode("sqz_encode_tokens", toks, nbytes, win_bits, file_mode, lib)
+
+
+def encode_symbols(words, nbytes: int, win_bits: int = 15, file_mode: bool = False, lib=None) -> bytes:
+    """The same on symbol words (include/sqz_gpu.h), the form the GPU parse emits for the coder."""
+    return _encode("sqz_encode_symbols", words, nbytes, win_bits, file_mode, lib)
+
+
+def symbols_of_tokens(toks) -> np.ndarray:
+    """Host statement of token -> symbol word (squeeze.h:290-315 bucket arithmetic)."""
+    t = np.ascontiguousarray(toks, dtype=np.uint32)
+    w = np.empty_like(t)
+    _lib.load().sqz_symbols_of_tokens(t.ctypes.data_as(u32p), t.size, w.ctypes.data_as(u32p))
+    return w
 
 
 def read_header(comp) -> tuple[int, int]:

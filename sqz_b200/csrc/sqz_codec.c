@@ -65,24 +65,29 @@ static void word_out(struct sqz_bitstream* bs) {
     bs->b64 = 0;
 }
 
-/* append the low `count` bits of `value`, least significant first */
-static inline void put_bits(struct sqz_bitstream* bs, uint64_t value, int count) {
+/* append `count` bits that are already in emission order (first bit = MSB of the field) */
+static inline void put_code(struct sqz_bitstream* bs, uint64_t seq, int count) {
     if (bs->error != 0 || count <= 0) { return; }
-    /* in emission order the value is bit-reversed: its bit 0 goes out first */
-    uint64_t seq = reverse64(value) >> (64 - count);
     int room = 64 - bs->bits;
     if (count < room) {
         bs->b64 = (bs->b64 << count) | seq;
         bs->bits += count;
         return;
     }
-    int rest = count - room;                                  /* bits left over */
+    int rest = count - room;
     bs->b64 = (room == 64 ? 0 : bs->b64 << room) | (seq >> rest);
     word_out(bs);
     if (rest > 0 && bs->error == 0) {
         bs->b64 = seq & (((uint64_t)1 << rest) - 1);
         bs->bits = rest;
     }
+}
+
+/* append the low `count` bits of `value`, least significant first */
+static inline void put_bits(struct sqz_bitstream* bs, uint64_t value, int count) {
+    if (bs->error != 0 || count <= 0) { return; }
+    /* in emission order the value is bit-reversed: its bit 0 goes out first */
+    put_code(bs, reverse64(value) >> (64 - count), count);
 }
 
 static inline void pad_to_word(struct sqz_bitstream* bs) {     /* bitstream.h:112-114 */
@@ -133,60 +138,109 @@ static inline uint64_t get_bits(struct sqz_bitstream* bs, int count) {
  *  adaptive Huffman tree  (reference huffman.h:36-269)    *
  *  Leaves are 0..n-1 (index == symbol); the root is 2n-2; further internal  *
  *  nodes are allocated downward from 2n-3.                                  *
+ *                                                                           *
+ *  Stored as a structure of arrays (16-bit links) so that the per-symbol    *
+ *  walk stays in L1.  Two kinds of walk exist:                              *
+ *   - the exact one (weight_changed), the reference's algorithm step by     *
+ *     step, which may reorder the tree;                                     *
+ *   - the quick one (quick_count), which only adds 1 to every weight on the *
+ *     path and is taken when no reordering can happen.  Whether one can is  *
+ *     known per node: a walk through node i does something other than add 1 *
+ *     only if i, after its increment, outweighs one fixed other node --     *
+ *     its right sibling when i is a left child (the two would trade places, *
+ *     huffman.h:64-86), its parent's sibling when i is a right child (i     *
+ *     would be promoted, huffman.h:98-128).  That comparator is a function  *
+ *     of the tree's shape, which changes about once per 2700 symbols on the *
+ *     bench corpus.  Every leaf therefore keeps a plan: the (node,          *
+ *     comparator) pairs from itself to the root, one cache line, so the     *
+ *     quick walk is a loop over independent loads instead of a pointer      *
+ *     chase.  A plan is dropped when the shape above or beside its leaf     *
+ *     changes (relabel, forget_plans) and rebuilt on the leaf's next use.   *
  * ======================================================================== */
 
-static void tree_init(struct sqz_tree* t, struct sqz_node* nodes, int32_t leaves) {
-    t->node = nodes;
-    t->n = leaves;
-    t->next = 2 * leaves - 2;
-    t->depth = 0;
-    t->complete = 0;
-    for (int32_t k = 0; k < 2 * leaves - 1; k++) {
-        nodes[k].freq = 0; nodes[k].path = 0; nodes[k].bits = 0;
-        nodes[k].up = -1;  nodes[k].lo = -1;  nodes[k].hi = -1;
-    }
-}
+enum { none = -1 };
 
 static inline int32_t tree_root(const struct sqz_tree* t) { return 2 * t->n - 2; }
+static inline uint32_t always_node(const struct sqz_tree* t) { return 2 * (uint32_t)t->n - 1; } /* weight 0 */
+static inline uint32_t never_node(const struct sqz_tree* t) { return 2 * (uint32_t)t->n; }       /* weight 2^64-1 */
+static inline uint32_t spare_node(const struct sqz_tree* t, int k) { return 2 * (uint32_t)t->n + 1 + ((uint32_t)k & 7); }
+
+#define SQZ_BIND_TREE(t, store, leaves) do {                                      \
+    (t)->freq = (store).freq; (t)->path = (store).path; (t)->code = (store).code; \
+    (t)->up = (store).up; (t)->lo = (store).lo; (t)->hi = (store).hi;             \
+    (t)->plan = &(store).plan[0][0]; (t)->steps = (store).steps;                  \
+    (t)->bits = (store).bits; (t)->n = (leaves); } while (0)
+
+static void tree_init(struct sqz_tree* t) {
+    const int32_t nodes = 2 * t->n - 1;
+    t->next = 2 * t->n - 2;
+    t->depth = 0;
+    t->complete = 0;
+    for (int32_t k = 0; k < nodes; k++) {
+        t->freq[k] = 0; t->path[k] = 0; t->bits[k] = 0;
+        t->up[k] = none; t->lo[k] = none; t->hi[k] = none;
+    }
+    for (int32_t k = 0; k < t->n; k++) { t->code[k] = 0; t->steps[k] = 0; }
+    t->freq[always_node(t)] = 0;
+    t->freq[never_node(t)] = UINT64_MAX;
+    for (int k = 0; k < 8; k++) { t->freq[spare_node(t, k)] = 0; }
+}
 
 /* Re-derive code length and code of everything below `top` from top's own.
  * A relabel that starts at the root restarts the depth high-water mark
  * (huffman.h:41-62).  Iterative: the order of visits does not matter.       */
 static void relabel(struct sqz_tree* t, int32_t top) {
-    struct sqz_node* nd = t->node;
-    int32_t stack[2 * sqz_lit_symbols];
+    int16_t stack[2 * sqz_lit_symbols];
     int sp = 0;
     int32_t depth = (top == tree_root(t)) ? 0 : t->depth;
-    stack[sp++] = top;
+    stack[sp++] = (int16_t)top;
     while (sp > 0) {
         const int32_t i = stack[--sp];
-        const int32_t bits = nd[i].bits;
-        const uint64_t path = nd[i].path;
+        const int32_t bits = t->bits[i];
+        const uint64_t path = t->path[i];
         if (bits > depth) { depth = bits; }
-        const int32_t lo = nd[i].lo, hi = nd[i].hi;
-        if (lo >= 0) { nd[lo].bits = bits + 1; nd[lo].path = path; stack[sp++] = lo; }
-        if (hi >= 0) { nd[hi].bits = bits + 1; nd[hi].path = path | ((uint64_t)1 << bits); stack[sp++] = hi; }
+        const int32_t lo = t->lo[i], hi = t->hi[i];
+        if (lo >= 0) { t->bits[lo] = (uint8_t)(bits + 1); t->path[lo] = path; stack[sp++] = (int16_t)lo; }
+        if (hi >= 0) { t->bits[hi] = (uint8_t)(bits + 1); t->path[hi] = path | ((uint64_t)1 << bits); stack[sp++] = (int16_t)hi; }
+        if (i < t->n) {
+            if (bits > 0) { t->code[i] = reverse64(path) >> (64 - bits); }
+            t->steps[i] = 0;            /* the shape above this leaf changed: its plan is void */
+        }
     }
     t->depth = depth;
 }
 
+/* drop the plans of every leaf below `top` */
+static void forget_plans(struct sqz_tree* t, int32_t top) {
+    int16_t stack[2 * sqz_lit_symbols];
+    int sp = 0;
+    stack[sp++] = (int16_t)top;
+    while (sp > 0) {
+        const int32_t i = stack[--sp];
+        if (i < t->n) { t->steps[i] = 0; continue; }
+        if (t->lo[i] >= 0) { stack[sp++] = t->lo[i]; }
+        if (t->hi[i] >= 0) { stack[sp++] = t->hi[i]; }
+    }
+}
+
+static inline uint64_t weight_or_zero(const struct sqz_tree* t, int32_t i) {
+    return i >= 0 ? t->freq[i] : 0;
+}
+
 static inline void sum_children(struct sqz_tree* t, int32_t i) {
-    const struct sqz_node* nd = t->node;
-    t->node[i].freq = (nd[i].lo >= 0 ? nd[nd[i].lo].freq : 0) +
-                      (nd[i].hi >= 0 ? nd[nd[i].hi].freq : 0);
+    t->freq[i] = weight_or_zero(t, t->lo[i]) + weight_or_zero(t, t->hi[i]);
 }
 
 /* Keep the lighter child on the left.  When the children trade places the
  * caller continues with the node that now sits where `i` used to be, i.e.
  * i's sibling (huffman.h:64-86).                                            */
 static int32_t order_siblings(struct sqz_tree* t, int32_t i) {
-    struct sqz_node* nd = t->node;
     if (i == tree_root(t)) { return i; }
-    const int32_t p = nd[i].up;
-    const int32_t lo = nd[p].lo, hi = nd[p].hi;
-    if (lo >= 0 && hi >= 0 && nd[lo].freq > nd[hi].freq) {
-        nd[p].lo = hi;
-        nd[p].hi = lo;
+    const int32_t p = t->up[i];
+    const int32_t lo = t->lo[p], hi = t->hi[p];
+    if (lo >= 0 && hi >= 0 && t->freq[lo] > t->freq[hi]) {
+        t->lo[p] = (int16_t)hi;
+        t->hi[p] = (int16_t)lo;
         relabel(t, p);
         return i == lo ? hi : lo;
     }
@@ -198,16 +252,15 @@ static void weight_changed(struct sqz_tree* t, int32_t i);
 /* `x` is the right child of p; if it outweighs p's sibling u the two trade
  * places: x moves up next to p, u moves down under p (huffman.h:98-128).    */
 static void promote(struct sqz_tree* t, int32_t x) {
-    struct sqz_node* nd = t->node;
-    const int32_t p = nd[x].up;
-    const int32_t g = nd[p].up;
-    const int p_left = nd[g].lo == p;
-    const int32_t u = p_left ? nd[g].hi : nd[g].lo;
-    if (nd[x].freq > nd[u].freq) {
-        nd[x].up = g;
-        if (p_left) { nd[g].hi = x; } else { nd[g].lo = x; }
-        nd[p].hi = u;
-        nd[u].up = p;
+    const int32_t p = t->up[x];
+    const int32_t g = t->up[p];
+    const int p_left = t->lo[g] == p;
+    const int32_t u = p_left ? t->hi[g] : t->lo[g];
+    if (u >= 0 && t->freq[x] > t->freq[u]) {
+        t->up[x] = (int16_t)g;
+        if (p_left) { t->hi[g] = (int16_t)x; } else { t->lo[g] = (int16_t)x; }
+        t->hi[p] = (int16_t)u;
+        t->up[u] = (int16_t)p;
         sum_children(t, p);
         sum_children(t, g);
         (void)order_siblings(t, x);
@@ -218,80 +271,162 @@ static void promote(struct sqz_tree* t, int32_t x) {
     }
 }
 
-/* Propagate a weight change from `i` to the root, re-ordering siblings on the
- * way up and, on the way back down, promoting right children that outgrew
- * their uncle (huffman.h:130-147).  The reference recurses; this is the same
- * sequence of steps with the recursion unrolled: first every level from the
- * leaf to the root refreshes its parent's weight and orders the two children
- * (continuing, after a swap, with the node that took the old slot), then the
- * levels are revisited from the root down for the promotion test, each with
- * the (node, parent) pair it captured on the way up.
- *
- * The second pass is almost always a no-op, and whether it is can be told on
- * the way up at no cost: the test of level k reads only the final weight of
- * its node (settled at level k), whether that node ended up as the right
- * child (settled at level k) and the weight of the parent's sibling, which
- * is not on the path and is loaded anyway at level k+1.  Nothing changes the
- * tree during the second pass unless a test fires, so if no test would fire
- * on the state left by the first pass the second pass is skipped; otherwise it
- * runs exactly as the reference's unwinding does.                            */
+/* The exact walk.  Propagate a weight change from `i` to the root, re-ordering
+ * siblings on the way up and, on the way back down, promoting right children
+ * that outgrew their uncle (huffman.h:130-147).  The reference recurses; this
+ * is the same sequence of steps with the recursion unrolled: first every level
+ * from the leaf to the root refreshes its parent's weight and orders the two
+ * children (continuing, after a swap, with the node that took the old slot),
+ * then the levels are revisited from the root down for the promotion test,
+ * each with the (node, parent) pair it captured on the way up.              */
 static void weight_changed(struct sqz_tree* t, int32_t i) {
-    struct sqz_node* nd = t->node;
-    int32_t node_at[2 * sqz_lit_symbols], parent_at[2 * sqz_lit_symbols];
+    int16_t node_at[2 * sqz_lit_symbols], parent_at[2 * sqz_lit_symbols];
     int levels = 0;
-    int may_promote = 0;
-    int below_is_right = 0;             /* level below: did its node end up as the right child? */
-    uint64_t below_weight = 0;          /* level below: final weight of its node */
     for (;;) {
-        const int32_t p = nd[i].up;
+        const int32_t p = t->up[i];
         if (p < 0) {                    /* the root: refresh its own weight, nothing to order */
             sum_children(t, i);
             break;
         }
-        const int32_t lo = nd[p].lo, hi = nd[p].hi;
-        const uint64_t wl = lo >= 0 ? nd[lo].freq : 0, wh = hi >= 0 ? nd[hi].freq : 0;
-        /* `i` (the parent of the level below) has a sibling here: the promotion test of the
-         * level below compares against its weight */
-        if (below_is_right && below_weight > (i == lo ? wh : wl)) { may_promote = 1; }
-        nd[p].freq = wl + wh;
-        int32_t right = hi;
+        const int32_t lo = t->lo[p], hi = t->hi[p];
+        const uint64_t wl = weight_or_zero(t, lo), wh = weight_or_zero(t, hi);
+        t->freq[p] = wl + wh;
         if (lo >= 0 && hi >= 0 && wl > wh) { /* heavier child goes right */
-            nd[p].lo = hi;
-            nd[p].hi = lo;
+            t->lo[p] = (int16_t)hi;
+            t->hi[p] = (int16_t)lo;
             relabel(t, p);
             i = (i == lo) ? hi : lo;
-            right = lo;
         }
-        below_is_right = (i == right);
-        below_weight = (i == lo) ? wl : wh;
-        node_at[levels] = i;
-        parent_at[levels] = p;
+        node_at[levels] = (int16_t)i;
+        parent_at[levels] = (int16_t)p;
         levels++;
         i = p;
     }
-    if (!may_promote) { return; }
     while (levels > 0) {
         levels--;
         const int32_t p = parent_at[levels];
-        if (nd[p].up >= 0 && nd[p].hi == node_at[levels]) { promote(t, node_at[levels]); }
+        if (t->up[p] >= 0 && t->hi[p] == node_at[levels]) { promote(t, node_at[levels]); }
     }
+}
+
+/* The node whose weight `i` may not exceed without the tree being reordered.
+ * A parent that is not in the state the quick walk relies on (children out of
+ * order, a weight that is not the sum of its children) yields the weight-0
+ * comparator, which sends every walk through `i` to the exact path.          */
+static uint32_t comparator(const struct sqz_tree* t, int32_t i) {
+    const int32_t p = t->up[i];
+    if (p < 0) { return never_node(t); }
+    const int32_t lo = t->lo[p], hi = t->hi[p];
+    /* (the root's own weight is exempt: nothing compares against it, quick walks leave it alone
+     * and every exact walk recomputes it from its children before anything reads it) */
+    if ((t->up[p] >= 0 && t->freq[p] != weight_or_zero(t, lo) + weight_or_zero(t, hi)) ||
+        (lo >= 0 && hi >= 0 && t->freq[lo] > t->freq[hi])) {
+        return always_node(t);
+    }
+    if (i == lo) { return hi >= 0 ? (uint32_t)hi : never_node(t); }
+    const int32_t g = t->up[p];
+    if (g < 0) { return never_node(t); }
+    const int32_t u = t->lo[g] == p ? t->hi[g] : t->lo[g];
+    return u >= 0 ? (uint32_t)u : always_node(t);
+}
+
+enum { plan_levels = 16, plan_too_deep = 0xFF,
+       lit_plan = 10, pos_plan = 6 };  /* covers 98 % / 97 % of the symbols of the bench corpus */
+
+/* plan of leaf `s`: (node | comparator << 16) from the leaf up to the root's
+ * child, padded with spare nodes nobody reads to the tree's usual plan length
+ * (so that the common walk is straight-line code), or to 16 when deeper       */
+static int plan_for(const struct sqz_tree* t, int32_t s, uint32_t* plan) {
+    const int usual = t->n == sqz_lit_symbols ? lit_plan : pos_plan;
+    int k = 0;
+    for (int32_t i = s; t->up[i] >= 0; i = t->up[i]) {
+        if (k == plan_levels) { return plan_too_deep; }
+        plan[k++] = (uint32_t)i | comparator(t, i) << 16;
+    }
+    const int padded = k <= usual ? usual : plan_levels;
+    for (int pad = 0; k < padded; pad++) { plan[k++] = spare_node(t, pad) | never_node(t) << 16; }
+    return padded;
+}
+
+static void make_plan(struct sqz_tree* t, int32_t s) {
+    t->steps[s] = (uint8_t)plan_for(t, s, t->plan + (size_t)s * plan_levels);
+}
+
+#ifdef SQZ_SELFCHECK
+/* Test builds only (tests/test_codec.py): after every symbol, every plan that
+ * is held valid must equal a freshly made one, and the state the quick walk
+ * relies on must hold everywhere: weights are the sums of their children,
+ * the lighter child is on the left.                                          */
+#include <stdio.h>
+#include <stdlib.h>
+static void selfcheck(const struct sqz_tree* t) {
+    const int32_t root = tree_root(t);
+    for (int32_t s = 0; s < t->n; s++) {
+        if (t->up[s] < 0 || t->steps[s] == 0) { continue; }
+        uint32_t fresh[plan_levels];
+        const int steps = plan_for(t, s, fresh);
+        if (steps != t->steps[s] ||
+            (steps != plan_too_deep && memcmp(fresh, t->plan + (size_t)s * plan_levels, 4 * (size_t)steps) != 0)) {
+            fprintf(stderr, "sqz selfcheck: stale plan of leaf %d\n", s);
+            abort();
+        }
+    }
+    for (int32_t p = t->next; p < root; p++) {
+        const int32_t lo = t->lo[p], hi = t->hi[p];
+        if (t->freq[p] != weight_or_zero(t, lo) + weight_or_zero(t, hi) || lo < 0 || hi < 0 ||
+            t->freq[lo] > t->freq[hi]) {
+            fprintf(stderr, "sqz selfcheck: node %d is not in the state the quick walk relies on\n", p);
+            abort();
+        }
+    }
+}
+#define SQZ_CHECK(t) selfcheck(t)
+#else
+#define SQZ_CHECK(t) ((void)0)
+#endif
+
+/* The quick walk: add 1 to every weight from leaf `s` to the root's child,
+ * provided no node on the way comes to outweigh its comparator.  Returns 0
+ * with all weights as they were when one would: the exact walk has to decide
+ * then.  `usual` is the tree's usual plan length (a constant at every call).  */
+#define SQZ_PLAN_STEP(e_) do { const uint32_t en_ = (e_);                        \
+        const uint64_t w_ = freq[en_ & 0xFFFF] + 1;                              \
+        fires |= (uint64_t)(w_ > freq[en_ >> 16]);                               \
+        freq[en_ & 0xFFFF] = w_; } while (0)
+
+static inline __attribute__((always_inline))
+int quick_count(struct sqz_tree* t, int32_t s, const int usual) {
+    uint64_t* const freq = t->freq;
+    if (t->steps[s] == 0) { make_plan(t, s); }
+    const int steps = t->steps[s];
+    const uint32_t* const plan = t->plan + (size_t)s * plan_levels;
+    uint64_t fires = 0;
+    if (steps == usual) {
+        for (int k = 0; k < usual; k++) { SQZ_PLAN_STEP(plan[k]); }     /* unrolled: usual is constant */
+    } else if (steps == plan_levels) {
+        for (int k = 0; k < plan_levels; k++) { SQZ_PLAN_STEP(plan[k]); }
+    } else {
+        return 0;                                                       /* deeper than a plan */
+    }
+    if (fires == 0) { return 1; }
+    for (int k = 0; k < steps; k++) { freq[plan[k] & 0xFFFF]--; }
+    return 0;
 }
 
 /* First occurrence of symbol `s` (huffman.h:149-216): walk from the root,
  * always to the left, to the first free child slot (right slot preferred) or
  * to a leaf, which is then split by a fresh internal node.                  */
 static int tree_insert(struct sqz_tree* t, int32_t s) {
-    struct sqz_node* nd = t->node;
     int ok = 1;
     int32_t at = tree_root(t);
-    nd[s].freq = 1;
+    t->freq[s] = 1;
     while (at >= t->n) {
-        if (nd[at].hi < 0)      { nd[at].hi = s; nd[s].up = at; break; }
-        else if (nd[at].lo < 0) { nd[at].lo = s; nd[s].up = at; break; }
-        else                    { at = nd[at].lo; }
+        if (t->hi[at] < 0)      { t->hi[at] = (int16_t)s; t->up[s] = (int16_t)at; break; }
+        else if (t->lo[at] < 0) { t->lo[at] = (int16_t)s; t->up[s] = (int16_t)at; break; }
+        else                    { at = t->lo[at]; }
     }
     if (at >= t->n) {
-        nd[at].freq++;
+        t->freq[at]++;
         s = order_siblings(t, s);
     } else if (t->next == t->n) {
         ok = 0;
@@ -299,38 +434,47 @@ static int tree_insert(struct sqz_tree* t, int32_t s) {
     } else {
         const int32_t leaf = at;
         const int32_t x = --t->next;
-        nd[x].freq = nd[leaf].freq;
-        nd[x].path = nd[leaf].path;
-        nd[x].bits = nd[leaf].bits;
-        nd[x].up   = nd[leaf].up;
-        nd[x].lo   = leaf;
-        nd[x].hi   = s;
-        if (nd[x].up >= 0) {
-            if (nd[nd[x].up].lo == leaf) { nd[nd[x].up].lo = x; } else { nd[nd[x].up].hi = x; }
+        t->freq[x] = t->freq[leaf];
+        t->path[x] = t->path[leaf];
+        t->bits[x] = t->bits[leaf];
+        t->up[x]   = t->up[leaf];
+        t->lo[x]   = (int16_t)leaf;
+        t->hi[x]   = (int16_t)s;
+        if (t->up[x] >= 0) {
+            const int32_t above = t->up[x];
+            if (t->lo[above] == leaf) { t->lo[above] = (int16_t)x; } else { t->hi[above] = (int16_t)x; }
         }
-        nd[leaf].up = x;
-        nd[leaf].bits = nd[x].bits + 1;          /* left edge: same code, one longer */
-        nd[s].up = x;
-        nd[s].bits = nd[x].bits + 1;
-        nd[s].path = nd[x].path | ((uint64_t)1 << nd[x].bits);
+        t->up[leaf] = (int16_t)x;
+        t->bits[leaf] = (uint8_t)(t->bits[x] + 1);   /* left edge: same code, one longer */
+        t->up[s] = (int16_t)x;
+        t->bits[s] = (uint8_t)(t->bits[x] + 1);
+        t->path[s] = t->path[x] | ((uint64_t)1 << t->bits[x]);
         sum_children(t, x);
         at = x;
+        /* x took the leaf's place: it is now the comparator of the leaf's old neighbours */
+        forget_plans(t, t->up[x] >= 0 ? t->up[x] : x);
     }
     weight_changed(t, s);
     relabel(t, at);
     return ok;
 }
 
-static void tree_count(struct sqz_tree* t, int32_t s) {        /* huffman.h:218-235 */
-    struct sqz_node* nd = t->node;
-    if (nd[s].up < 0) {
+static inline __attribute__((always_inline))
+void tree_count_as(struct sqz_tree* t, int32_t s, const int usual) {   /* huffman.h:218-235 */
+    if (t->up[s] < 0) {
         (void)tree_insert(t, s);
-    } else if (!t->complete && t->depth < 63 && nd[s].freq < UINT64_MAX - 1) {
-        nd[s].freq++;
+    } else if (!t->complete && t->depth < 63 && t->freq[s] < UINT64_MAX - 1) {
+        if (quick_count(t, s, usual)) { return; }
+        t->freq[s]++;
         weight_changed(t, s);
     } else {
         t->complete = 1;
     }
+}
+
+static void tree_count(struct sqz_tree* t, int32_t s) {
+    if (t->n == sqz_lit_symbols) { tree_count_as(t, s, lit_plan); } else { tree_count_as(t, s, pos_plan); }
+    SQZ_CHECK(t);
 }
 
 /* ======================================================================== *
@@ -346,18 +490,24 @@ static void bucket_tables(struct sqz* s) {
         while (b + 1 < 28 && len_base[b + 1] <= len) { b++; }
         s->len_index[len] = (uint8_t)b;
     }
-    int b = 0;
-    for (uint32_t d = 0; d < (1u << 15); d++) {
-        while (b + 1 < 30 && pos_base[b + 1] <= d) { b++; }
-        s->pos_index[d] = (uint8_t)b;
-    }
+}
+
+/* dist -> distance bucket (squeeze.h:162-171 builds a 32 KiB table for this;
+ * the buckets are deflate's: two per power of two above 4)                  */
+static inline uint32_t pos_bucket(uint32_t dist) {
+    if (dist <= 4) { return dist - 1; }
+    const uint32_t m = dist - 1;
+    const uint32_t k = 31u - (uint32_t)__builtin_clz(m);
+    return 2 * k + ((m >> (k - 1)) & 1);
 }
 
 void sqz_init(struct sqz* s) {
     memset(s, 0, sizeof(*s));
     s->device = -1;                       /* the caller's current CUDA device */
-    tree_init(&s->lit, s->lit_nodes, sqz_lit_symbols);
-    tree_init(&s->pos, s->pos_nodes, sqz_pos_symbols);
+    SQZ_BIND_TREE(&s->lit, s->lit_store, sqz_lit_symbols);
+    SQZ_BIND_TREE(&s->pos, s->pos_store, sqz_pos_symbols);
+    tree_init(&s->lit);
+    tree_init(&s->pos);
 }
 
 static void coder_begin(struct sqz* s, struct sqz_bitstream* bs) {
@@ -375,12 +525,12 @@ static inline void s_put(struct sqz* s, uint64_t v, int count) {
 
 /* current code of `sym`, then bump its weight (squeeze.h:239-246) */
 static inline void emit_symbol(struct sqz* s, struct sqz_tree* t, int32_t sym) {
-    s_put(s, t->node[sym].path, t->node[sym].bits);
+    if (s->error == 0) { put_code(s->bs, t->code[sym], t->bits[sym]); s->error = s->bs->error; }
     tree_count(t, sym);
 }
 
 static inline void code_lit(struct sqz* s, uint32_t sym) {     /* squeeze.h:278-288 */
-    if (s->lit.node[sym].bits == 0) {
+    if (s->lit.bits[sym] == 0) {
         emit_symbol(s, &s->lit, sqz_lit_nyt);
         s_put(s, sym, 9);
         if (!tree_insert(&s->lit, (int32_t)sym)) { s->error = E2BIG; }
@@ -389,42 +539,129 @@ static inline void code_lit(struct sqz* s, uint32_t sym) {     /* squeeze.h:278-
     }
 }
 
-static inline void code_len(struct sqz* s, uint32_t len) {     /* squeeze.h:290-298 */
-    const uint32_t b = s->len_index[len];
-    code_lit(s, len_symbol0 + b);
-    if (len_extra[b] > 0) { s_put(s, len - len_base[b], len_extra[b]); }
+/* ---- symbol words ---------------------------------------------------------
+ * What the coder consumes is one 32-bit word per token with the bucket
+ * arithmetic of squeeze.h:290-315 already done (sqz_gpu.h: the GPU emits these
+ * words directly, `symbols` mode of the stream; for a caller's plain tokens
+ * symbols_of_token() below makes them):
+ *   bits  0..8   symbol of the literal/length tree: byte, or 257 + length bucket
+ *   bits  9..13  the length's extra bits, in emission order
+ *   bits 14..18  symbol of the distance tree (distance bucket)
+ *   bits 19..31  the distance's extra bits, in emission order
+ * "In emission order" = bit-reversed within its field width, since values go
+ * out least significant bit first (bitstream.h:49-63).                       */
+
+static inline uint32_t reverse_field(uint32_t v, uint32_t width) {   /* width <= 16 */
+    static const uint8_t rev4[16] = { 0, 8, 4, 12, 2, 10, 6, 14, 1, 9, 5, 13, 3, 11, 7, 15 };
+    const uint32_t r = (uint32_t)rev4[v & 15] << 12 | (uint32_t)rev4[(v >> 4) & 15] << 8 |
+                       (uint32_t)rev4[(v >> 8) & 15] << 4 | (uint32_t)rev4[(v >> 12) & 15];
+    return r >> (16 - width);
 }
 
-static inline void code_dist(struct sqz* s, uint32_t dist) {   /* squeeze.h:300-315 */
-    const uint32_t b = s->pos_index[dist];
-    if (s->pos.node[b].bits == 0) {
-        emit_symbol(s, &s->pos, sqz_pos_nyt);
-        s_put(s, b, 5);
-        if (!tree_insert(&s->pos, (int32_t)b)) { s->error = E2BIG; }
-    } else {
-        emit_symbol(s, &s->pos, (int32_t)b);
-    }
-    if (pos_extra[b] > 0) { s_put(s, dist - pos_base[b], pos_extra[b]); }
+static inline int token_is_valid(uint32_t t) {          /* the decoder's limits: squeeze.h:529-545 */
+    const uint32_t len = t >> 16, dist = t & 0xFFFF;
+    return len == 0 ? t <= 0xFF : (len >= sqz_min_len && len <= sqz_max_len && dist >= 1 && dist <= 0x7FFF);
 }
 
-static void code_tokens(struct sqz* s, const uint32_t* tokens, uint64_t count) {
-    for (uint64_t k = 0; k < count && s->error == 0; k++) {
-        const uint32_t t = tokens[k];
-        const uint32_t len = t >> 16;
-        if (len == 0) {
-            code_lit(s, t & 0xFF);
+static inline uint32_t symbols_of_token(const struct sqz* s, uint32_t t) {
+    const uint32_t len = t >> 16;
+    if (len == 0) { return t; }
+    const uint32_t dist = t & 0xFFFF;
+    const uint32_t lb = s->len_index[len], pb = pos_bucket(dist);
+    return (len_symbol0 + lb) | reverse_field(len - len_base[lb], len_extra[lb]) << 9 |
+           pb << 14 | reverse_field(dist - pos_base[pb], pos_extra[pb]) << 19;
+}
+
+/* The coder proper.  The bit register lives in locals for the whole run and a
+ * full word goes straight to memory when the sink is a buffer with room;
+ * everything unusual (first occurrence of a symbol, callback sinks, a full
+ * buffer) goes through the general functions above with the register synced. */
+static void code_symbols(struct sqz* s, const uint32_t* words, uint64_t count) {
+    struct sqz_bitstream* const bs = s->bs;
+    struct sqz_tree* const lit = &s->lit;
+    struct sqz_tree* const pos = &s->pos;
+    uint64_t acc = bs->b64;
+    uint32_t fill = (uint32_t)bs->bits;
+    uint64_t matches = 0;
+    if (s->error != 0) { return; }
+
+#define SQZ_SYNC_OUT()  do { bs->b64 = acc; bs->bits = (int32_t)fill; } while (0)
+#define SQZ_SYNC_IN()   do { acc = bs->b64; fill = (uint32_t)bs->bits; } while (0)
+#define SQZ_APPEND(seq_, count_) do {                                            \
+        const uint64_t q_ = (seq_); const uint32_t c_ = (count_);                \
+        const uint32_t f_ = fill + c_;                                           \
+        if (f_ < 64) { acc = (acc << c_) | q_; fill = f_; }                      \
+        else {                                                                   \
+            const uint32_t rest_ = f_ - 64;                                      \
+            const uint64_t word_ = (fill == 0 ? 0 : acc << (64 - fill)) | (q_ >> rest_); \
+            if (bs->data != NULL && bs->capacity - bs->bytes >= 8 && bs->capacity >= bs->bytes) { \
+                const uint64_t be_ = __builtin_bswap64(word_);                   \
+                memcpy(bs->data + bs->bytes, &be_, 8);                           \
+                bs->bytes += 8;                                                  \
+            } else {                                                             \
+                bs->b64 = word_; bs->bits = 64;                                  \
+                word_out(bs);                                                    \
+                if (bs->error != 0) { s->error = bs->error; goto done; }         \
+            }                                                                    \
+            acc = rest_ == 0 ? 0 : (q_ & (((uint64_t)1 << rest_) - 1));          \
+            fill = rest_;                                                        \
+        } } while (0)
+
+    for (uint64_t k = 0; k < count; k++) {
+        const uint32_t w = words[k];
+        const uint32_t sym = w & 0x1FF;
+        if (lit->bits[sym] == 0) {                   /* first occurrence: escape + raw symbol */
+            SQZ_SYNC_OUT();
+            code_lit(s, sym);
+            SQZ_SYNC_IN();
+            if (s->error != 0) { goto done; }
         } else {
-            const uint32_t dist = t & 0xFFFF;
-            if (len < sqz_min_len || len > sqz_max_len || dist == 0 || dist > 0x7FFF) {
-                s->error = EINVAL;      /* the decoder would reject it: squeeze.h:529-545 */
-                break;
+            SQZ_APPEND(lit->code[sym], lit->bits[sym]);
+            tree_count_as(lit, (int32_t)sym, lit_plan);
+            SQZ_CHECK(lit);
+        }
+        if (sym >= len_symbol0) {                    /* length first, then distance: squeeze.h:379-380 */
+            const uint32_t pb = (w >> 14) & 31;
+            SQZ_APPEND((w >> 9) & 31, len_extra[sym - len_symbol0]);
+            if (pos->bits[pb] == 0) {
+                SQZ_SYNC_OUT();
+                emit_symbol(s, pos, sqz_pos_nyt);
+                s_put(s, pb, 5);
+                if (!tree_insert(pos, (int32_t)pb)) { s->error = E2BIG; }
+                SQZ_SYNC_IN();
+                if (s->error != 0) { goto done; }
+            } else {
+                SQZ_APPEND(pos->code[pb], pos->bits[pb]);
+                tree_count_as(pos, (int32_t)pb, pos_plan);
+                SQZ_CHECK(pos);
             }
-            code_len(s, len);           /* length first, then distance: squeeze.h:379-380 */
-            code_dist(s, dist);
-            s->matches++;
+            SQZ_APPEND(w >> 19, pos_extra[pb]);
+            matches++;
         }
     }
+done:
+    SQZ_SYNC_OUT();
+    s->matches += matches;
     s->tokens += count;
+#undef SQZ_APPEND
+#undef SQZ_SYNC_IN
+#undef SQZ_SYNC_OUT
+}
+
+/* plain tokens (literal byte or (len << 16) | dist): checked, turned into symbol
+ * words a block at a time, coded                                             */
+static void code_tokens(struct sqz* s, const uint32_t* tokens, uint64_t count) {
+    uint32_t words[1024];
+    for (uint64_t at = 0; at < count && s->error == 0; at += 1024) {
+        const uint64_t n = count - at < 1024 ? count - at : 1024;
+        uint64_t good = 0;
+        while (good < n && token_is_valid(tokens[at + good])) {
+            words[good] = symbols_of_token(s, tokens[at + good]);
+            good++;
+        }
+        code_symbols(s, words, good);
+        if (good < n && s->error == 0) { s->error = EINVAL; }
+    }
 }
 
 void sqz_write_header(struct sqz_bitstream* bs, uint64_t bytes, uint8_t win_bits) {
@@ -454,6 +691,23 @@ void sqz_encode_tokens(struct sqz* s, struct sqz_bitstream* bs,
     s->entropy_seconds += now_seconds() - t0;
 }
 
+void sqz_symbols_of_tokens(const uint32_t* tokens, uint64_t count, uint32_t* words) {
+    struct sqz s;                       /* only the length table is used */
+    bucket_tables(&s);
+    for (uint64_t k = 0; k < count; k++) {
+        words[k] = token_is_valid(tokens[k]) ? symbols_of_token(&s, tokens[k]) : 0xFFFFFFFFu;
+    }
+}
+
+void sqz_encode_symbols(struct sqz* s, struct sqz_bitstream* bs,
+                        const uint32_t* words, uint64_t count) {
+    coder_begin(s, bs);
+    double t0 = now_seconds();
+    code_symbols(s, words, count);
+    if (s->error == 0) { pad_to_word(bs); s->error = bs->error; }
+    s->entropy_seconds += now_seconds() - t0;
+}
+
 void sqz_compress(struct sqz* s, struct sqz_bitstream* bs,
                   const uint8_t* data, uint64_t bytes, uint32_t window) {
     if (window < (1u << sqz_min_win_bits) || window > (1u << sqz_max_win_bits) ||
@@ -463,24 +717,24 @@ void sqz_compress(struct sqz* s, struct sqz_bitstream* bs,
     }
     coder_begin(s, bs);
     if (s->error != 0) { return; }
-    /* The GPU produces the greedy token stream chunk by chunk; while the host
-     * entropy-codes chunk k the device already searches chunk k+1.           */
+    /* The GPU produces the greedy token stream chunk by chunk, as symbol words;
+     * while the host entropy-codes chunk k the device already searches chunk k+1. */
     sqz_gpu_stream* st = NULL;
     double t_search = 0, t_code = 0, t0 = now_seconds();
     int r = sqz_gpu_stream_open(&st, s->device, data, (size_t)bytes, window,
-                                sqz_min_len, sqz_max_len, window - 1, 0);
+                                sqz_min_len, sqz_max_len, window - 1, 0, SQZ_GPU_STREAM_SYMBOLS);
     t_search += now_seconds() - t0;
     if (r != 0) { s->error = r; return; }
     for (;;) {
-        const uint32_t* tokens = NULL;
+        const uint32_t* words = NULL;
         size_t count = 0;
         t0 = now_seconds();
-        r = sqz_gpu_stream_next(st, &tokens, &count);
+        r = sqz_gpu_stream_next(st, &words, &count);
         t_search += now_seconds() - t0;
         if (r != 0) { s->error = r; break; }
         if (count == 0) { break; }
         t0 = now_seconds();
-        code_tokens(s, tokens, count);
+        code_symbols(s, words, count);
         t_code += now_seconds() - t0;
         if (s->error != 0) { break; }
     }
@@ -495,14 +749,13 @@ void sqz_compress(struct sqz* s, struct sqz_bitstream* bs,
  * ======================================================================== */
 
 static int32_t read_symbol(struct sqz* s, struct sqz_tree* t) { /* squeeze.h:429-442 */
-    const struct sqz_node* nd = t->node;
     int32_t i = tree_root(t);
     for (;;) {
         int bit = get_bit(s->bs);
         if (s->bs->error != 0) { s->error = s->bs->error; return -1; }
-        i = bit ? nd[i].hi : nd[i].lo;
+        i = bit ? t->hi[i] : t->lo[i];
         if (i < 0) { s->error = EINVAL; return -1; }
-        if (nd[i].lo < 0 && nd[i].hi < 0) { break; }
+        if (i < t->n) { break; }                    /* leaves are the nodes below n */
     }
     tree_count(t, i);
     return i;
@@ -524,7 +777,7 @@ void sqz_decompress(struct sqz* s, struct sqz_bitstream* bs,
         if (sym == sqz_lit_nyt) {
             sym = (int32_t)s_get(s, 9);
             if (s->error != 0) { break; }
-            if (s->lit.node[sym].up >= 0) { s->error = EINVAL; break; }  /* already known */
+            if (s->lit.up[sym] >= 0) { s->error = EINVAL; break; }  /* already known */
             if (!tree_insert(&s->lit, sym)) { s->error = E2BIG; break; }
         }
         if (sym <= 0xFF) {
@@ -542,7 +795,7 @@ void sqz_decompress(struct sqz* s, struct sqz_bitstream* bs,
         if (pb == sqz_pos_nyt) {
             pb = (int32_t)s_get(s, 5);
             if (s->error != 0) { break; }
-            if (pb >= 30 || s->pos.node[pb].up >= 0) { s->error = EINVAL; break; }
+            if (pb >= 30 || s->pos.up[pb] >= 0) { s->error = EINVAL; break; }
             if (!tree_insert(&s->pos, pb)) { s->error = E2BIG; break; }
         }
         if (pb >= 30) { s->error = EINVAL; break; }

@@ -394,6 +394,33 @@ scan_counts(const uint32_t* __restrict__ count, size_t blocks,
     if (threadIdx.x == 0) { result[0] = carry_s; }
 }
 
+// Symbol word of a match token (include/sqz_gpu.h): the bucket arithmetic of the reference's
+// squeeze_encode_len / squeeze_encode_pos (squeeze.h:290-315, tables squeeze.h:29-79) done here,
+// extra bits already in emission order (bit-reversed within their field).
+//   lengths   3..10 -> buckets 0..7, no extra bits; above that four buckets per power of two of
+//             len-3, with 258 kept in bucket 27 (squeeze.h:151-161)
+//   distances 1..4 -> buckets 0..3; above that two buckets per power of two of dist-1
+__device__ __forceinline__ uint32_t symbols_of_match(uint32_t len, uint32_t dist) {
+    const uint32_t m = len - 3;
+    uint32_t lb = m, lxb = 0;
+    if (m >= 8) {
+        const uint32_t k = 31u - (uint32_t)__clz((int)m);
+        lxb = k - 2;
+        lb = 4 * (k - 1) + ((m >> lxb) & 3);
+    }
+    const uint32_t lx = lxb ? __brev(m & ((1u << lxb) - 1)) >> (32 - lxb) : 0;
+    const uint32_t q = dist - 1;
+    uint32_t pb = q, pxb = 0;
+    if (q >= 4) {
+        const uint32_t k = 31u - (uint32_t)__clz((int)q);
+        pxb = k - 1;
+        pb = 2 * k + ((q >> pxb) & 1);
+    }
+    const uint32_t px = pxb ? __brev(q & ((1u << pxb) - 1)) >> (32 - pxb) : 0;
+    return (257 + lb) | lx << 9 | pb << 14 | px << 19;
+}
+
+template <bool kSymbols>
 __global__ void parse_emit(const uint8_t* __restrict__ shard,
                            const uint32_t* __restrict__ table, size_t n, size_t blocks,
                            uint32_t min_len, const uint32_t* __restrict__ block_entry,
@@ -409,7 +436,7 @@ __global__ void parse_emit(const uint8_t* __restrict__ shard,
         const uint32_t w = table[p];
         const uint32_t len = w >> 16;
         uint32_t t, step;
-        if (len >= min_len) { t = w; step = len; }
+        if (len >= min_len) { t = kSymbols ? symbols_of_match(len, w & 0xFFFF) : w; step = len; }
         else                { t = shard[p]; step = 1; }
         if (k < cap) { tokens[k] = t; }
         k++;
@@ -652,7 +679,7 @@ static int parse_maps(const uint32_t* d_table, size_t n, uint32_t min_len, uint3
 static int parse_launch(const uint8_t* d_shard, const uint32_t* d_table, size_t n,
                         const uint32_t* d_entry, uint32_t entry, uint32_t min_len,
                         uint32_t max_len, uint32_t* d_tokens, size_t cap, void* d_work,
-                        uint64_t* d_result, cudaStream_t s) {
+                        uint64_t* d_result, cudaStream_t s, bool symbols = false) {
     if (n == 0) {
         // nothing to parse: count 0, overshoot = entry
         CU(cudaMemsetAsync(d_result, 0, 16, s));
@@ -676,8 +703,13 @@ static int parse_launch(const uint8_t* d_shard, const uint32_t* d_table, size_t 
     LAUNCHED("parse_count");
     parse::scan_counts<<<1, 1024, 0, s>>>(w.count, w.blocks, w.offset, d_result);
     LAUNCHED("scan_counts");
-    parse::parse_emit<<<wb, 64, 0, s>>>(d_shard, d_table, n, w.blocks, min_len, w.block_entry,
-                                        w.offset, d_tokens, cap);
+    if (symbols) {
+        parse::parse_emit<true><<<wb, 64, 0, s>>>(d_shard, d_table, n, w.blocks, min_len,
+                                                  w.block_entry, w.offset, d_tokens, cap);
+    } else {
+        parse::parse_emit<false><<<wb, 64, 0, s>>>(d_shard, d_table, n, w.blocks, min_len,
+                                                   w.block_entry, w.offset, d_tokens, cap);
+    }
     LAUNCHED("parse_emit");
     return 0;
 }
@@ -690,6 +722,25 @@ extern "C" int sqz_gpu_parse_device(const uint8_t* d_shard, const uint32_t* d_ta
     if (entry >= max_len) { return fail(EINVAL, "entry must be < max_len"); }
     return parse_launch(d_shard, d_table, n, nullptr, entry, min_len, max_len, d_tokens,
                         tokens_cap, d_work, d_result, (cudaStream_t)stream);
+}
+
+// symbol words only exist for the bitstream's own limits (squeeze.h:13-15, 529-545)
+static int check_symbol_rules(uint32_t min_len, uint32_t max_len, uint32_t max_dist) {
+    if (min_len < 3 || max_len > 258 || max_dist > 0x7FFF) {
+        return fail(EINVAL, "symbol words need min_len >= 3, max_len <= 258, max_dist <= 32767");
+    }
+    return 0;
+}
+
+extern "C" int sqz_gpu_parse_symbols_device(const uint8_t* d_shard, const uint32_t* d_table, size_t n,
+                                            uint32_t entry, uint32_t min_len, uint32_t max_len,
+                                            uint32_t* d_words, size_t words_cap, void* d_work,
+                                            uint64_t* d_result, void* stream) {
+    if (int r = check_rules(min_len, max_len, 1)) { return r; }
+    if (int r = check_symbol_rules(min_len, max_len, 1)) { return r; }
+    if (entry >= max_len) { return fail(EINVAL, "entry must be < max_len"); }
+    return parse_launch(d_shard, d_table, n, nullptr, entry, min_len, max_len, d_words,
+                        words_cap, d_work, d_result, (cudaStream_t)stream, true);
 }
 
 extern "C" int sqz_gpu_parse_exit_map_device(const uint32_t* d_table, size_t n,
@@ -739,6 +790,7 @@ struct sqz_gpu_stream {
     size_t delivered = 0;             // input bytes whose tokens were returned
     int next_slot = 0, read_slot = 0;
     bool want_tokens = true;
+    bool symbols = false;             // emit symbol words instead of plain tokens
     Slot slot[2];
     const uint64_t* prev_result = nullptr;   // device: previous chunk's result (entry hand-off)
     cudaEvent_t prev_parsed = nullptr;
@@ -862,7 +914,7 @@ static int stream_launch_next(sqz_gpu_stream* st, uint16_t* len_out, uint16_t* d
             d_entry = reinterpret_cast<const uint32_t*>(st->prev_result + 1);  // low half of overshoot
         }
         if (int r = parse_launch(d_shard, s.d_table, n, d_entry, 0, st->min_len, st->max_len,
-                                 s.d_tokens, n, s.d_work, s.d_result, s.stream)) { return r; }
+                                 s.d_tokens, n, s.d_work, s.d_result, s.stream, st->symbols)) { return r; }
         CU(cudaMemcpyAsync(s.h_result, s.d_result, 16, cudaMemcpyDeviceToHost, s.stream));
         if (st->prev_parsed == nullptr) {
             CU(cudaEventCreateWithFlags(&st->prev_parsed, cudaEventDisableTiming));
@@ -919,10 +971,16 @@ static int stream_open(sqz_gpu_stream** out, int device, const uint8_t* data, si
 
 extern "C" int sqz_gpu_stream_open(sqz_gpu_stream** st, int device, const uint8_t* data,
                                    size_t bytes, uint32_t window, uint32_t min_len,
-                                   uint32_t max_len, uint32_t max_dist, size_t chunk_bytes) {
+                                   uint32_t max_len, uint32_t max_dist, size_t chunk_bytes,
+                                   uint32_t flags) {
     if (st == nullptr) { return fail(EINVAL, "null stream handle"); }
+    if ((flags & ~(uint32_t)SQZ_GPU_STREAM_SYMBOLS) != 0) { return fail(EINVAL, "unknown stream flags"); }
+    if (flags & SQZ_GPU_STREAM_SYMBOLS) {
+        if (int r = check_symbol_rules(min_len, max_len, max_dist)) { return r; }
+    }
     if (int r = stream_open(st, device, data, bytes, window, min_len, max_len, max_dist,
                             chunk_bytes, true)) { return r; }
+    (*st)->symbols = (flags & SQZ_GPU_STREAM_SYMBOLS) != 0;
     if (bytes > 0) {
         if (int r = stream_launch_next(*st, nullptr, nullptr)) {
             sqz_gpu_stream_close(*st);
@@ -974,7 +1032,7 @@ extern "C" int sqz_gpu_tokens(const uint8_t* data, size_t bytes, uint32_t window
     sqz_gpu_stream* st = nullptr;
     // one-shot call: nothing consumes the chunks on the way, so use the larger streaming chunk
     if (int r = sqz_gpu_stream_open(&st, -1, data, bytes, window, min_len, max_len, max_dist,
-                                    default_chunk(bytes, false))) {
+                                    default_chunk(bytes, false), 0)) {
         return r;
     }
     size_t total = 0;

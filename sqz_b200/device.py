@@ -44,15 +44,17 @@ def exit_map(table: torch.Tensor, n: int, min_len: int = G1_MIN_LEN, max_len: in
 
 
 def parse(buf: torch.Tensor, first: int, table: torch.Tensor, n: int, entry: int = 0, min_len: int = G1_MIN_LEN,
-          max_len: int = G1_MAX_LEN):
-    """Greedy parse of one shard (squeeze.h:337,377-394): (tokens int32[count], overshoot)."""
+          max_len: int = G1_MAX_LEN, symbols: bool = False):
+    """Greedy parse of one shard (squeeze.h:337,377-394): (tokens int32[count], overshoot).
+    symbols=True: symbol words (include/sqz_gpu.h) instead of plain tokens."""
     L = _lib.load()
     dev = buf.device
     work = torch.empty(L.sqz_gpu_parse_workspace(n), dtype=torch.uint8, device=dev)
     tokens = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
     result = torch.zeros(2, dtype=torch.int64, device=dev)
-    rc = L.sqz_gpu_parse_device(buf.data_ptr() + first, table.data_ptr(), n, entry, min_len, max_len,
-                                tokens.data_ptr(), n, work.data_ptr(), result.data_ptr(), _stream())
-    _check(rc, "sqz_gpu_parse_device")
+    fn = L.sqz_gpu_parse_symbols_device if symbols else L.sqz_gpu_parse_device
+    rc = fn(buf.data_ptr() + first, table.data_ptr(), n, entry, min_len, max_len,
+            tokens.data_ptr(), n, work.data_ptr(), result.data_ptr(), _stream())
+    _check(rc, "sqz_gpu_parse_symbols_device" if symbols else "sqz_gpu_parse_device")
     count, overshoot = (int(x) for x in result.cpu())
     return tokens[:count], overshoot

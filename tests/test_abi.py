@@ -45,16 +45,16 @@ def test_struct_layout_matches_the_header(tmp_path):
     """ctypes mirrors of struct sqz / sqz_bitstream have the C sizes."""
     src = tmp_path / "s.c"
     src.write_text('#include <stdio.h>\n#include "sqz.h"\nint main(void){printf("%zu %zu %zu\\n", sizeof(struct sqz), '
-                   'sizeof(struct sqz_bitstream), sizeof(struct sqz_node));return 0;}\n')
+                   'sizeof(struct sqz_bitstream), sizeof(struct sqz_tree));return 0;}\n')
     exe = tmp_path / "s"
     subprocess.check_call(["gcc", "-std=c99", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     a, b, c = map(int, subprocess.check_output([str(exe)]).split())
-    assert (a, b, c) == (C.sizeof(_lib.State), C.sizeof(_lib.Bitstream), C.sizeof(_lib.Node))
+    assert (a, b, c) == (C.sizeof(_lib.State), C.sizeof(_lib.Bitstream), C.sizeof(_lib.Tree))
 
 
 def test_version_and_device_probe():
     L = _lib.load()
-    assert L.sqz_gpu_abi_version() == 1
+    assert L.sqz_gpu_abi_version() == 2
     assert L.sqz_gpu_device_count() >= 0
     assert L.sqz_gpu_parse_workspace(1 << 20) > 0
     assert L.sqz_gpu_select_kernel(7) != 0 and L.sqz_gpu_select_kernel(0) == 0

@@ -2,12 +2,13 @@
 made with the unmodified reference, round trips, header bytes, error behaviour."""
 import ctypes as C
 import errno
+import os
 
 import numpy as np
 import pytest
 
 import sqz_b200 as sq
-from conftest import fnv
+from conftest import ROOT, fnv
 from sqz_b200 import _lib
 
 ALL = ["zeros4096", "pat1234x1024", "hello", "abc40", "lorem3", "empty", "one", "two", "aaa", "aaaa",
@@ -47,6 +48,94 @@ def test_cross_decoding_with_the_reference(name, inputs, reference, oracle):
     ours = sq.encode_tokens(oracle_tokens(oracle, d, 15), d.size, 15)
     assert ours == theirs
     assert reference.decompress(ours) == d.tobytes()
+
+
+@pytest.mark.parametrize("name", ["hello", "abc40", "zeros4096", "laozi.txt", "arm64.elf", "mandrill.bmp"])
+def test_symbol_words_code_to_the_same_bytes(name, inputs, golden, oracle):
+    """sqz_encode_symbols (the form the GPU parse hands over) == sqz_encode_tokens."""
+    d = inputs[name]
+    t = oracle_tokens(oracle, d, 15)
+    w = sq.symbols_of_tokens(t)
+    comp = sq.encode_symbols(w, d.size, 15)
+    assert fnv(oracle, np.frombuffer(comp, np.uint8)) == golden[name]["win"]["15"]["fnv_mem"]
+    assert sq.encode_symbols(w, d.size, 15, file_mode=True) == sq.encode_tokens(t, d.size, 15, file_mode=True)
+
+
+def test_symbol_word_layout():
+    """bits 0..8 lit/len symbol, 9..13 length extra, 14..18 distance bucket, 19..31 distance extra;
+    extra bits are stored in emission order (bit-reversed within the field): squeeze.h:29-79,290-315."""
+    len_base = [3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227]
+    len_xb = [0] * 8 + [1] * 4 + [2] * 4 + [3] * 4 + [4] * 4 + [5] * 4
+    pos_base = [1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049,
+                3073, 4097, 6145, 8193, 12289, 16385, 24577]
+    pos_xb = [0, 0, 0, 0] + [k // 2 for k in range(2, 28)]
+    rev = lambda v, n: int(format(v, "0%db" % n)[::-1], 2) if n else 0
+    lens = np.arange(3, 258, dtype=np.uint32)
+    dists = np.r_[np.arange(1, 600), np.arange(4090, 4100), np.arange(24570, 24580), 32766, 32767].astype(np.uint32)
+    toks = np.r_[np.arange(256, dtype=np.uint32), (lens[:, None] << 16 | dists[None, :]).ravel()]
+    words = sq.symbols_of_tokens(toks)
+    assert (words[:256] == np.arange(256)).all()
+    for t, w in zip(toks[256::37].tolist(), words[256::37].tolist()):
+        ln, ds = t >> 16, t & 0xFFFF
+        lb = max(k for k in range(28) if len_base[k] <= ln)
+        pb = max(k for k in range(30) if pos_base[k] <= ds)
+        assert w & 0x1FF == 257 + lb
+        assert (w >> 9) & 31 == rev(ln - len_base[lb], len_xb[lb])
+        assert (w >> 14) & 31 == pb
+        assert w >> 19 == rev(ds - pos_base[pb], pos_xb[pb])
+    bad = np.array([(258 << 16) | 1, (3 << 16) | 0x8000, (2 << 16) | 5, (3 << 16) | 0, 256], np.uint32)
+    assert (sq.symbols_of_tokens(bad) == 0xFFFFFFFF).all()
+
+
+@pytest.fixture(scope="module")
+def selfcheck_lib(tmp_path_factory):
+    """The codec alone, built with -DSQZ_SELFCHECK: after every coded symbol it verifies that every
+    leaf's cached plan equals a fresh one and that the tree is in the state the quick walk assumes."""
+    import subprocess
+    d = tmp_path_factory.mktemp("selfcheck")
+    stub = d / "stub.c"
+    stub.write_text('#include "sqz_gpu.h"\n#include <errno.h>\n'
+                    'int sqz_gpu_stream_open(sqz_gpu_stream** s, int dev, const uint8_t* p, size_t n, uint32_t w, '
+                    'uint32_t a, uint32_t b, uint32_t c, size_t k, uint32_t m) { (void)s; (void)dev; (void)p; (void)n; (void)w; (void)a; '
+                    '(void)b; (void)c; (void)k; (void)m; return ENODEV; }\n'
+                    'int sqz_gpu_stream_next(sqz_gpu_stream* s, const uint32_t** t, size_t* c) { (void)s; (void)t; (void)c; return ENODEV; }\n'
+                    'void sqz_gpu_stream_close(sqz_gpu_stream* s) { (void)s; }\n')
+    so = d / "libsqzcheck.so"
+    subprocess.check_call(["gcc", "-std=gnu11", "-O2", "-fPIC", "-shared", "-DSQZ_SELFCHECK",
+                           "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "sqz_b200", "csrc", "sqz_codec.c"),
+                           str(stub), "-o", str(so)])
+    L = C.CDLL(str(so))
+    for name in ("sqz_write_header", "sqz_init", "sqz_encode_tokens", "sqz_encode_symbols", "sqz_decompress_buffer"):
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = _lib.SYMBOLS[name]
+    return L
+
+
+def _skewed(n, seed):
+    """Symbols with geometric probabilities: a deep, lopsided tree (plans longer than the usual length,
+    leaves deeper than a plan holds) and, through the periodic shuffles, many reorderings."""
+    rng = np.random.default_rng(seed)
+    out = np.minimum(rng.geometric(0.35, n) - 1, 40).astype(np.uint32)
+    for k in range(0, n, 4000):
+        out[k:k + 4000] = (out[k:k + 4000] + (k // 4000) * 7) % 41
+    lens = rng.integers(3, 258, n).astype(np.uint32)
+    dist = np.minimum(2 ** rng.integers(0, 15, n) + rng.integers(0, 50, n), 32767).astype(np.uint32)
+    is_match = rng.random(n) < 0.2
+    return np.where(is_match, lens << 16 | dist, out).astype(np.uint32)
+
+
+@pytest.mark.parametrize("case", ["hello", "laozi.txt", "confucius.txt", "x64.elf", "mandrill.bmp", "skewed", "uniform"])
+def test_quick_walk_plans_stay_valid(case, selfcheck_lib, inputs, oracle, reference):
+    if case == "skewed":
+        t, nbytes = _skewed(60000, 5), 1 << 30
+    elif case == "uniform":
+        t, nbytes = np.random.default_rng(3).integers(0, 256, 150000).astype(np.uint32), 150000
+    else:
+        d = inputs[case][:120000]
+        t, nbytes = oracle_tokens(oracle, d, 15), d.size
+    ours = sq.encode_tokens(t, nbytes, 15, lib=selfcheck_lib)          # aborts the process on a stale plan
+    assert ours == sq.encode_tokens(t, nbytes, 15)
+    assert ours == reference.encode_tokens(t, nbytes, 15)
 
 
 def test_header_bytes():

@@ -93,25 +93,64 @@ def test_seam_hand_off_between_shards(world, oracle):
     maps = [device.exit_map(t, s.n).cpu().numpy().view(np.uint16) for t, s in zip(tables, plan)]
     entries = shard.chain_entries(maps)
     assert entries[-1] == 0
-    parts = []
+    parts, words = [], []
     for s, t, e in zip(plan, tables, entries):
         tok, over = device.parse(dev, s.first, t, s.n, e)
         assert over == entries[s.rank + 1]
         parts.append(tok.cpu().numpy().view(np.uint32))
+        sym, over = device.parse(dev, s.first, t, s.n, e, symbols=True)
+        assert over == entries[s.rank + 1]
+        words.append(sym.cpu().numpy().view(np.uint32))
     cat = np.concatenate(parts)
     assert cat.size == whole.size and (cat == whole).all()
+    # symbol words from the GPU == the host statement of squeeze.h:290-315 on the same tokens
+    assert (np.concatenate(words) == sq.symbols_of_tokens(whole)).all()
 
 
+def test_symbol_words_cover_every_bucket():
+    """Every length 3..257 and distances over every bucket edge, through the GPU emit kernel."""
+    from sqz_b200 import device
+    rng = np.random.default_rng(11)
+    pieces = []
+    for ln in list(range(3, 40)) + [41, 42, 43, 50, 51, 58, 59, 66, 67, 82, 83, 98, 99, 114, 115, 130, 131, 162,
+                                    163, 194, 195, 226, 227, 256, 257]:
+        for gap in (0, 1, 2, 3, 4, 5, 7, 12, 23, 40, 100, 500, 3000, 9000, 30000):
+            unit = rng.integers(0, 256, ln, dtype=np.uint8)
+            pieces += [unit, rng.integers(0, 256, gap + 1, dtype=np.uint8), unit, rng.integers(0, 256, 3, dtype=np.uint8)]
+    data = np.concatenate(pieces)[: 6 << 20]
+    whole = oracle_tokens_fast(data)
+    dev = torch.cat([torch.from_numpy(data).cuda(), torch.zeros(64, dtype=torch.uint8, device="cuda")])
+    t = device.match_table(dev, 0, data.size, 0, 0)
+    sym, over = device.parse(dev, 0, t, data.size, 0, symbols=True)
+    assert over == 0
+    got = sym.cpu().numpy().view(np.uint32)
+    want = sq.symbols_of_tokens(whole)
+    assert got.size == want.size and (got == want).all()
+    lens = set((whole[whole > 0xFFFF] >> 16).tolist())
+    assert {3, 10, 11, 18, 19, 34, 35, 66, 67, 130, 131, 226, 227, 257} <= lens
+
+
+def oracle_tokens_fast(data):
+    from oracle import Oracle
+    o = Oracle.get()
+    return o.tokens_from_table(data, *o.match_table(data, 1 << 15, fast=True))[0]
+
+
+@pytest.mark.parametrize("flags", [0, 1], ids=["tokens", "symbols"])
 @pytest.mark.parametrize("chunk", [4096, 50001, 65536, 1 << 20])
-def test_streaming_pipeline_chunk_sizes(chunk, inputs, oracle):
-    """sqz_gpu_stream_*: any chunking of the input gives the same token stream."""
+def test_streaming_pipeline_chunk_sizes(chunk, flags, inputs, oracle):
+    """sqz_gpu_stream_*: any chunking of the input gives the same token stream; in symbols mode
+    (SQZ_GPU_STREAM_SYMBOLS) the words equal the host statement of squeeze.h:290-315."""
     import ctypes as C
     from sqz_b200 import _lib
     L = _lib.load()
     d = np.concatenate([inputs["confucius.txt"], inputs["x64.elf"][:200000], inputs["mandrill.bmp"][:50000]])
     want = oracle.tokens_from_table(d, *oracle.match_table(d, 1 << 15, fast=True))[0]
     st = C.c_void_p()
-    rc = L.sqz_gpu_stream_open(C.byref(st), 0, d.ctypes.data_as(_lib.u8p), d.size, 1 << 15, 3, 257, 32767, chunk)
+    if flags:
+        want = sq.symbols_of_tokens(want)
+    rc = L.sqz_gpu_stream_open(C.byref(st), 0, d.ctypes.data_as(_lib.u8p), d.size, 1 << 15, 3, 257, 32767, chunk,
+                               flags)
     assert rc == 0, L.sqz_gpu_last_error()
     got = []
     while True:
