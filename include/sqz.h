@@ -73,6 +73,8 @@ struct sqz_tree {
     uint32_t* plan;     /* per leaf 16 x (node | comparator << 16), leaf to root */
     uint8_t*  steps;    /* per leaf: plan length; 0 = no plan yet, 255 = deeper than a plan */
     uint8_t*  bits;     /* code length; 0 = root or unseen leaf */
+    uint16_t* lut;      /* decoder only: node reached by the next lut_bits bits of the stream */
+    int32_t lut_bits;
     int32_t n;          /* leaves; nodes = 2n-1 */
     int32_t next;       /* internal nodes are handed out downward from here */
     int32_t depth;      /* high-water mark, reset by a root-level relabel */
@@ -99,6 +101,8 @@ struct sqz {
     uint8_t len_index[sqz_max_len + 2]; /* len -> length bucket, squeeze.h:151-161 */
     SQZ_TREE_STORE(sqz_lit_symbols) lit_store;
     SQZ_TREE_STORE(sqz_pos_symbols) pos_store;
+    uint16_t lit_lut[1 << 10];          /* decoder look-ahead tables (sqz_codec.c: lit_lut_bits, pos_lut_bits) */
+    uint16_t pos_lut[1 << 6];
 };
 
 /* 64 raw bits of `bytes` then 8 raw bits of `win_bits`, each LSB first.

@@ -34,7 +34,7 @@ Bitstream._fields_ = [
 class Tree(C.Structure):
     _fields_ = [("freq", u64p), ("path", u64p), ("code", u64p),
                 ("up", C.POINTER(C.c_int16)), ("lo", C.POINTER(C.c_int16)), ("hi", C.POINTER(C.c_int16)),
-                ("plan", u32p), ("steps", u8p), ("bits", u8p),
+                ("plan", u32p), ("steps", u8p), ("bits", u8p), ("lut", u16p), ("lut_bits", C.c_int32),
                 ("n", C.c_int32), ("next", C.c_int32), ("depth", C.c_int32), ("complete", C.c_int32)]
 
 
@@ -56,6 +56,7 @@ class State(C.Structure):
         ("lit", Tree), ("pos", Tree),
         ("len_index", C.c_uint8 * 259),
         ("lit_store", _store(512)), ("pos_store", _store(32)),
+        ("lit_lut", C.c_uint16 * 1024), ("pos_lut", C.c_uint16 * 64),
     ]
 
 

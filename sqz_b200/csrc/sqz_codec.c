@@ -158,7 +158,8 @@ static inline uint64_t get_bits(struct sqz_bitstream* bs, int count) {
  *     changes (relabel, forget_plans) and rebuilt on the leaf's next use.   *
  * ======================================================================== */
 
-enum { none = -1 };
+enum { none = -1, no_node = 0xFFFF,
+       lit_lut_bits = 10, pos_lut_bits = 6 };   /* sizes of sqz.h's lit_lut / pos_lut */
 
 static inline int32_t tree_root(const struct sqz_tree* t) { return 2 * t->n - 2; }
 static inline uint32_t always_node(const struct sqz_tree* t) { return 2 * (uint32_t)t->n - 1; } /* weight 0 */
@@ -169,7 +170,8 @@ static inline uint32_t spare_node(const struct sqz_tree* t, int k) { return 2 * 
     (t)->freq = (store).freq; (t)->path = (store).path; (t)->code = (store).code; \
     (t)->up = (store).up; (t)->lo = (store).lo; (t)->hi = (store).hi;             \
     (t)->plan = &(store).plan[0][0]; (t)->steps = (store).steps;                  \
-    (t)->bits = (store).bits; (t)->n = (leaves); } while (0)
+    (t)->bits = (store).bits; (t)->n = (leaves); (t)->lut = NULL;                 \
+    (t)->lut_bits = (leaves) == sqz_lit_symbols ? lit_lut_bits : pos_lut_bits; } while (0)
 
 static void tree_init(struct sqz_tree* t) {
     const int32_t nodes = 2 * t->n - 1;
@@ -205,6 +207,12 @@ static void relabel(struct sqz_tree* t, int32_t top) {
         if (i < t->n) {
             if (bits > 0) { t->code[i] = reverse64(path) >> (64 - bits); }
             t->steps[i] = 0;            /* the shape above this leaf changed: its plan is void */
+        }
+        /* decoder only: every lut_bits-bit look-ahead that starts with this node's code leads here */
+        if (t->lut != NULL && bits > 0 && bits <= t->lut_bits && (i < t->n || bits == t->lut_bits)) {
+            const int32_t spread = t->lut_bits - bits;
+            const uint64_t first = (reverse64(path) >> (64 - bits)) << spread;
+            for (uint64_t k = 0; k < ((uint64_t)1 << spread); k++) { t->lut[first + k] = (uint16_t)i; }
         }
     }
     t->depth = depth;
@@ -368,6 +376,14 @@ static void selfcheck(const struct sqz_tree* t) {
         if (steps != t->steps[s] ||
             (steps != plan_too_deep && memcmp(fresh, t->plan + (size_t)s * plan_levels, 4 * (size_t)steps) != 0)) {
             fprintf(stderr, "sqz selfcheck: stale plan of leaf %d\n", s);
+            abort();
+        }
+    }
+    for (uint32_t look = 0; t->lut != NULL && look < (1u << t->lut_bits); look++) {
+        int32_t i = root;
+        for (int b = t->lut_bits - 1; b >= 0 && i >= t->n; b--) { i = (look >> b) & 1 ? t->hi[i] : t->lo[i]; }
+        if (t->lut[look] != (i >= 0 ? (uint16_t)i : (uint16_t)no_node)) {
+            fprintf(stderr, "sqz selfcheck: stale decode table entry %u\n", look);
             abort();
         }
     }
@@ -748,37 +764,90 @@ void sqz_compress(struct sqz* s, struct sqz_bitstream* bs,
  *  decompressor  (reference squeeze.h:411-551); never touches the GPU       *
  * ======================================================================== */
 
-static int32_t read_symbol(struct sqz* s, struct sqz_tree* t) { /* squeeze.h:429-442 */
-    int32_t i = tree_root(t);
-    for (;;) {
-        int bit = get_bit(s->bs);
-        if (s->bs->error != 0) { s->error = s->bs->error; return -1; }
-        i = bit ? t->hi[i] : t->lo[i];
-        if (i < 0) { s->error = EINVAL; return -1; }
-        if (i < t->n) { break; }                    /* leaves are the nodes below n */
+/* The decoder reads through a window of its own: `acc` holds the next `have`
+ * bits of the stream left-aligned, topped up from `pend`, the unread rest of
+ * the last 64-bit word taken from the bitstream.  A word is taken when fewer
+ * than 32 bits are at hand, i.e. up to 31 bits before the reference would
+ * take it (bitstream.h:65-95); running dry there is only an error once bits
+ * that are not there are consumed.                                           */
+struct window {
+    struct sqz_bitstream* bs;
+    uint64_t acc, pend;
+    int32_t have, pend_bits;
+    int32_t dry;                        /* errno met while reading ahead */
+};
+
+static inline void window_fill(struct window* w) {
+    if (w->have >= 32) { return; }
+    if (w->pend_bits == 0 && w->dry == 0) {
+        word_in(w->bs);
+        if (w->bs->error != 0) { w->dry = w->bs->error; w->bs->error = 0; }
+        else { w->pend = w->bs->b64; w->pend_bits = 64; }
+        w->bs->bits = 0;
     }
-    tree_count(t, i);
-    return i;
+    if (w->pend_bits > 0) {
+        const int32_t room = 64 - w->have;
+        const int32_t take = room < w->pend_bits ? room : w->pend_bits;
+        w->acc |= w->pend >> w->have;
+        w->pend = take == 64 ? 0 : w->pend << take;
+        w->pend_bits -= take;
+        w->have += take;
+    }
 }
 
-static inline uint64_t s_get(struct sqz* s, int count) {
-    uint64_t v = 0;
-    if (s->error == 0) { v = get_bits(s->bs, count); s->error = s->bs->error; }
-    return v;
+/* drop `count` bits; 0 when they were not all there */
+static inline int window_skip(struct sqz* s, struct window* w, int32_t count) {
+    if (count > w->have) { s->error = w->dry != 0 ? w->dry : E2BIG; return 0; }
+    w->acc <<= count;
+    w->have -= count;
+    return 1;
+}
+
+/* `count` <= 16 raw bits, first bit = least significant (bitstream.h:97-110) */
+static inline uint32_t window_bits(struct sqz* s, struct window* w, int32_t count) {
+    window_fill(w);
+    const uint32_t top = (uint32_t)(w->acc >> 48);          /* the next 16 bits */
+    const uint32_t v = reverse_field(top, 16) & ((1u << count) - 1);
+    return window_skip(s, w, count) ? v : 0;
+}
+
+static inline int32_t window_symbol(struct sqz* s, struct window* w, struct sqz_tree* t,
+                                    const int lut_bits, const int usual) {  /* squeeze.h:429-442 */
+    window_fill(w);
+    int32_t i = t->lut[w->acc >> (64 - lut_bits)];   /* one lookup walks lut_bits levels */
+    if (i == no_node) { s->error = EINVAL; return -1; }
+    if (!window_skip(s, w, i < t->n ? t->bits[i] : lut_bits)) { return -1; }
+    while (i >= t->n) {                              /* a longer code: leaves are the nodes below n */
+        window_fill(w);
+        const int bit = (int)(w->acc >> 63);
+        if (!window_skip(s, w, 1)) { return -1; }
+        i = bit ? t->hi[i] : t->lo[i];
+        if (i < 0) { s->error = EINVAL; return -1; }
+    }
+    tree_count_as(t, i, usual);
+    SQZ_CHECK(t);
+    return i;
 }
 
 void sqz_decompress(struct sqz* s, struct sqz_bitstream* bs,
                     uint8_t* data, uint64_t bytes) {
+    s->lit.lut = s->lit_lut;
+    s->pos.lut = s->pos_lut;
+    memset(s->lit_lut, 0xFF, sizeof(s->lit_lut));
+    memset(s->pos_lut, 0xFF, sizeof(s->pos_lut));
     coder_begin(s, bs);
+    if (bs->error != 0) { s->error = bs->error; }
+    struct window w = { bs, bs->bits > 0 ? bs->b64 : 0, 0, bs->bits, 0, 0 };
     uint64_t i = 0;
     while (i < bytes && s->error == 0) {
-        int32_t sym = read_symbol(s, &s->lit);
+        int32_t sym = window_symbol(s, &w, &s->lit, lit_lut_bits, lit_plan);
         if (s->error != 0) { break; }
         if (sym == sqz_lit_nyt) {
-            sym = (int32_t)s_get(s, 9);
+            sym = (int32_t)window_bits(s, &w, 9);
             if (s->error != 0) { break; }
             if (s->lit.up[sym] >= 0) { s->error = EINVAL; break; }  /* already known */
             if (!tree_insert(&s->lit, sym)) { s->error = E2BIG; break; }
+            SQZ_CHECK(&s->lit);
         }
         if (sym <= 0xFF) {
             data[i++] = (uint8_t)sym;
@@ -787,30 +856,38 @@ void sqz_decompress(struct sqz* s, struct sqz_bitstream* bs,
         const int32_t b = sym - len_symbol0;
         if (b < 0 || b >= 28) { s->error = EINVAL; break; }
         uint32_t len = len_base[b];
-        if (len_extra[b] > 0) { len += (uint32_t)s_get(s, len_extra[b]); }
+        if (len_extra[b] > 0) { len += window_bits(s, &w, len_extra[b]); }
         if (s->error != 0) { break; }
         if (len < sqz_min_len || len > sqz_max_len) { s->error = EINVAL; break; }
-        int32_t pb = read_symbol(s, &s->pos);
+        int32_t pb = window_symbol(s, &w, &s->pos, pos_lut_bits, pos_plan);
         if (s->error != 0) { break; }
         if (pb == sqz_pos_nyt) {
-            pb = (int32_t)s_get(s, 5);
+            pb = (int32_t)window_bits(s, &w, 5);
             if (s->error != 0) { break; }
             if (pb >= 30 || s->pos.up[pb] >= 0) { s->error = EINVAL; break; }
             if (!tree_insert(&s->pos, pb)) { s->error = E2BIG; break; }
+            SQZ_CHECK(&s->pos);
         }
         if (pb >= 30) { s->error = EINVAL; break; }
         uint32_t dist = pos_base[pb];
-        if (pos_extra[pb] > 0) { dist += (uint32_t)s_get(s, pos_extra[pb]); }
+        if (pos_extra[pb] > 0) { dist += window_bits(s, &w, pos_extra[pb]); }
         if (s->error != 0) { break; }
         if (dist == 0 || dist > 0x7FFF || dist > i || len > bytes - i) {
             s->error = EINVAL;
             break;
         }
-        /* the source may overlap the destination: copy forward byte by byte */
-        const uint8_t* from = data + i - dist;
-        for (uint32_t k = 0; k < len; k++) { data[i + k] = from[k]; }
+        /* squeeze.h:533-539 copies byte by byte because the source may overlap the
+         * destination; the result is the same as these three cases */
+        uint8_t* to = data + i;
+        const uint8_t* from = to - dist;
+        if (dist >= len)    { memcpy(to, from, len); }
+        else if (dist == 1) { memset(to, from[0], len); }
+        else                { for (uint32_t k = 0; k < len; k++) { to[k] = from[k]; } }
         i += len;
     }
+    bs->b64 = w.acc;                    /* what is left of the window (any bits in `pend` are dropped) */
+    bs->bits = w.have;
+    if (s->error != 0 && bs->error == 0) { bs->error = s->error; }
 }
 
 /* ---- whole-buffer conveniences ----------------------------------------- */

@@ -786,6 +786,7 @@ struct sqz_gpu_stream {
     size_t bytes = 0;
     uint32_t min_len = 0, max_len = 0, max_dist = 0;
     size_t chunk = 0;
+    size_t ramp = 0;                  // size of the next chunk while it is still below `chunk`
     size_t launched = 0;              // input bytes handed to the device so far
     size_t delivered = 0;             // input bytes whose tokens were returned
     int next_slot = 0, read_slot = 0;
@@ -897,7 +898,11 @@ static int ensure_device(int& device) {
 static int stream_launch_next(sqz_gpu_stream* st, uint16_t* len_out, uint16_t* dist_out) {
     Slot& s = st->slot[st->next_slot];
     const size_t first = st->launched;
-    const size_t n = std::min(st->chunk, st->bytes - first);
+    size_t n = std::min(st->chunk, st->bytes - first);
+    if (st->ramp != 0) {               // short chunks first: the consumer starts after milliseconds
+        n = std::min(n, st->ramp);
+        st->ramp = st->ramp * 2 >= st->chunk ? 0 : st->ramp * 2;
+    }
     const size_t back = std::min<size_t>(first, st->max_dist);
     const size_t ahead = std::min<size_t>(st->bytes - (first + n), st->max_len);
     s.first = first;
@@ -958,7 +963,9 @@ static int stream_open(sqz_gpu_stream** out, int device, const uint8_t* data, si
     st->min_len = min_len; st->max_len = max_len; st->max_dist = max_dist;
     st->chunk = chunk ? chunk : default_chunk(bytes, tokens);
     st->want_tokens = tokens;
-    const int slots = bytes > st->chunk ? 2 : 1;
+    // token streams with the default chunking start with short chunks: 2, 4, 8, 16 MiB, then 32 MiB
+    if (tokens && chunk == 0 && st->chunk > ((size_t)2 << 20)) { st->ramp = (size_t)2 << 20; }
+    const int slots = bytes > (st->ramp ? st->ramp : st->chunk) ? 2 : 1;
     for (int k = 0; k < slots && bytes > 0; k++) {
         if (int r = slot_take(st->slot[k], device, st->chunk, max_len, max_dist, tokens)) {
             sqz_gpu_stream_close(st);

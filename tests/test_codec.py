@@ -121,13 +121,15 @@ def _skewed(n, seed):
     lens = rng.integers(3, 258, n).astype(np.uint32)
     dist = np.minimum(2 ** rng.integers(0, 15, n) + rng.integers(0, 50, n), 32767).astype(np.uint32)
     is_match = rng.random(n) < 0.2
+    is_match[:33000] = False                 # every distance below points at bytes that exist
     return np.where(is_match, lens << 16 | dist, out).astype(np.uint32)
 
 
 @pytest.mark.parametrize("case", ["hello", "laozi.txt", "confucius.txt", "x64.elf", "mandrill.bmp", "skewed", "uniform"])
 def test_quick_walk_plans_stay_valid(case, selfcheck_lib, inputs, oracle, reference):
     if case == "skewed":
-        t, nbytes = _skewed(60000, 5), 1 << 30
+        t = _skewed(60000, 5)
+        nbytes = int(np.where(t >> 16 != 0, t >> 16, 1).sum())
     elif case == "uniform":
         t, nbytes = np.random.default_rng(3).integers(0, 256, 150000).astype(np.uint32), 150000
     else:
@@ -136,6 +138,14 @@ def test_quick_walk_plans_stay_valid(case, selfcheck_lib, inputs, oracle, refere
     ours = sq.encode_tokens(t, nbytes, 15, lib=selfcheck_lib)          # aborts the process on a stale plan
     assert ours == sq.encode_tokens(t, nbytes, 15)
     assert ours == reference.encode_tokens(t, nbytes, 15)
+    # the decoder keeps the same plans and, besides, a look-ahead table per tree (checked the same way)
+    c = np.frombuffer(ours, np.uint8)
+    out = np.zeros(nbytes, np.uint8)
+    got = C.c_uint64()
+    rc = selfcheck_lib.sqz_decompress_buffer(c.ctypes.data_as(_lib.u8p), c.size, out.ctypes.data_as(_lib.u8p), out.size,
+                                             C.byref(got))
+    assert rc == 0 and got.value == nbytes
+    assert out.tobytes() == sq.decompress(ours) == reference.decompress(ours)
 
 
 def test_header_bytes():
