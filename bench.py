@@ -355,11 +355,18 @@ def ours(args) -> None:
         t0 = time.perf_counter()
         blob = sq.compress(sample, 15, stats=st)
         dt = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        back_again = sq.decompress(blob)
+        dt_dec = time.perf_counter() - t0
         comp = {"value": sample.size / 1e6 / dt, "unit": "MB/s", "sample_bytes": int(sample.size),
                 "compressed_bytes": len(blob), "seconds": dt, "search_wait_seconds": st["search_seconds"],
                 "entropy_seconds": st["entropy_seconds"], "tokens": st["tokens"],
+                "entropy_ns_per_token": st["entropy_seconds"] * 1e9 / max(st["tokens"], 1),
+                "decompress": {"value": sample.size / 1e6 / dt_dec, "unit": "MB/s", "seconds": dt_dec,
+                               "round_trip_identical": back_again == sample.tobytes()},
                 "note": "sqz_compress(host in, host bitstream out): the serial adaptive-Huffman stage on one "
-                        "host core bounds it (SURVEY 7 H4); the search runs ahead on the GPU"}
+                        "host core bounds it (SURVEY 7 H4); the search runs ahead on the GPU and hands over "
+                        "symbol words (SURVEY 8f N3); sqz_decompress is host only"}
     except Exception as e:
         comp = {"value": None, "error": repr(e)}
 
@@ -434,7 +441,7 @@ def main():
     ap.add_argument("--size", type=int, default=1 << 30, help="bytes per GPU")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-sample", type=int, default=512 << 10)
-    ap.add_argument("--compress-sample", type=int, default=64 << 20)
+    ap.add_argument("--compress-sample", type=int, default=256 << 20)
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

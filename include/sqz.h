@@ -60,7 +60,7 @@ struct sqz_bitstream {
 /* One adaptive-Huffman tree (huffman.h:13-34) as a structure of arrays with
  * 16-bit links.  Node k: leaves 0..n-1 (index == symbol), root 2n-2, internal
  * nodes handed out downward from 2n-3.  freq[] has ten extra entries:
- * freq[2n-1] = 0 and freq[2n] = 2^64-1, the comparators "always" and "never"
+ * freq[2n-1] = 0 and freq[2n] = 2^63-1, the comparators "always" and "never"
  * of the plans, and eight spare slots that pad a plan (sqz_codec.c).  The
  * root's own weight is only kept up to date by the exact walk.              */
 struct sqz_tree {
@@ -70,7 +70,7 @@ struct sqz_tree {
     int16_t*  up;       /* parent, -1 = none */
     int16_t*  lo;       /* left child  (bit 0) */
     int16_t*  hi;       /* right child (bit 1) */
-    uint32_t* plan;     /* per leaf 16 x (node | comparator << 16), leaf to root */
+    uint16_t* plan;     /* per leaf 16 nodes (leaf to root) + their 16 comparators: one cache line */
     uint8_t*  steps;    /* per leaf: plan length; 0 = no plan yet, 255 = deeper than a plan */
     uint8_t*  bits;     /* code length; 0 = root or unseen leaf */
     uint16_t* lut;      /* decoder only: node reached by the next lut_bits bits of the stream */
@@ -82,7 +82,7 @@ struct sqz_tree {
 };
 
 #define SQZ_TREE_STORE(N) struct {                                          \
-    uint32_t plan[N][16];                                                     \
+    uint16_t plan[N][32];                                                     \
     uint64_t freq[2 * (N) + 9]; uint64_t path[2 * (N) - 1]; uint64_t code[N]; \
     int16_t up[2 * (N) - 1]; int16_t lo[2 * (N) - 1]; int16_t hi[2 * (N) - 1]; \
     uint8_t steps[N]; uint8_t bits[2 * (N) - 1]; }

@@ -34,13 +34,13 @@ Bitstream._fields_ = [
 class Tree(C.Structure):
     _fields_ = [("freq", u64p), ("path", u64p), ("code", u64p),
                 ("up", C.POINTER(C.c_int16)), ("lo", C.POINTER(C.c_int16)), ("hi", C.POINTER(C.c_int16)),
-                ("plan", u32p), ("steps", u8p), ("bits", u8p), ("lut", u16p), ("lut_bits", C.c_int32),
+                ("plan", u16p), ("steps", u8p), ("bits", u8p), ("lut", u16p), ("lut_bits", C.c_int32),
                 ("n", C.c_int32), ("next", C.c_int32), ("depth", C.c_int32), ("complete", C.c_int32)]
 
 
 def _store(n: int):
     class Store(C.Structure):
-        _fields_ = [("plan", C.c_uint32 * 16 * n),
+        _fields_ = [("plan", C.c_uint16 * 32 * n),
                     ("freq", C.c_uint64 * (2 * n + 9)), ("path", C.c_uint64 * (2 * n - 1)), ("code", C.c_uint64 * n),
                     ("up", C.c_int16 * (2 * n - 1)), ("lo", C.c_int16 * (2 * n - 1)), ("hi", C.c_int16 * (2 * n - 1)),
                     ("steps", C.c_uint8 * n), ("bits", C.c_uint8 * (2 * n - 1))]

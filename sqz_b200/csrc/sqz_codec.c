@@ -163,7 +163,7 @@ enum { none = -1, no_node = 0xFFFF,
 
 static inline int32_t tree_root(const struct sqz_tree* t) { return 2 * t->n - 2; }
 static inline uint32_t always_node(const struct sqz_tree* t) { return 2 * (uint32_t)t->n - 1; } /* weight 0 */
-static inline uint32_t never_node(const struct sqz_tree* t) { return 2 * (uint32_t)t->n; }       /* weight 2^64-1 */
+static inline uint32_t never_node(const struct sqz_tree* t) { return 2 * (uint32_t)t->n; }       /* weight 2^63-1 */
 static inline uint32_t spare_node(const struct sqz_tree* t, int k) { return 2 * (uint32_t)t->n + 1 + ((uint32_t)k & 7); }
 
 #define SQZ_BIND_TREE(t, store, leaves) do {                                      \
@@ -184,7 +184,7 @@ static void tree_init(struct sqz_tree* t) {
     }
     for (int32_t k = 0; k < t->n; k++) { t->code[k] = 0; t->steps[k] = 0; }
     t->freq[always_node(t)] = 0;
-    t->freq[never_node(t)] = UINT64_MAX;
+    t->freq[never_node(t)] = (uint64_t)INT64_MAX;
     for (int k = 0; k < 8; k++) { t->freq[spare_node(t, k)] = 0; }
 }
 
@@ -339,25 +339,32 @@ static uint32_t comparator(const struct sqz_tree* t, int32_t i) {
 }
 
 enum { plan_levels = 16, plan_too_deep = 0xFF,
-       lit_plan = 10, pos_plan = 6 };  /* covers 98 % / 97 % of the symbols of the bench corpus */
+       lit_plan = 9, pos_plan = 6 };   /* covers 98 % / 97 % of the symbols of the bench corpus */
 
-/* plan of leaf `s`: (node | comparator << 16) from the leaf up to the root's
- * child, padded with spare nodes nobody reads to the tree's usual plan length
- * (so that the common walk is straight-line code), or to 16 when deeper       */
-static int plan_for(const struct sqz_tree* t, int32_t s, uint32_t* plan) {
+/* plan of leaf `s`: one cache line, plan[0..15] the nodes from the leaf up to
+ * the root's child, plan[16..31] their comparators, padded with spare nodes
+ * nobody reads to the tree's usual plan length (so that the common walk is
+ * straight-line code), or to 16 when deeper.  The walk compares weights as
+ * signed numbers; a path that already carries 2^61 gets no plan.             */
+static int plan_for(const struct sqz_tree* t, int32_t s, uint16_t* plan) {
     const int usual = t->n == sqz_lit_symbols ? lit_plan : pos_plan;
     int k = 0;
     for (int32_t i = s; t->up[i] >= 0; i = t->up[i]) {
-        if (k == plan_levels) { return plan_too_deep; }
-        plan[k++] = (uint32_t)i | comparator(t, i) << 16;
+        if (k == plan_levels || t->freq[i] >> 61 != 0) { return plan_too_deep; }
+        plan[k] = (uint16_t)i;
+        plan[plan_levels + k] = (uint16_t)comparator(t, i);
+        k++;
     }
     const int padded = k <= usual ? usual : plan_levels;
-    for (int pad = 0; k < padded; pad++) { plan[k++] = spare_node(t, pad) | never_node(t) << 16; }
+    for (int pad = 0; k < padded; pad++, k++) {
+        plan[k] = (uint16_t)spare_node(t, pad);
+        plan[plan_levels + k] = (uint16_t)never_node(t);
+    }
     return padded;
 }
 
 static void make_plan(struct sqz_tree* t, int32_t s) {
-    t->steps[s] = (uint8_t)plan_for(t, s, t->plan + (size_t)s * plan_levels);
+    t->steps[s] = (uint8_t)plan_for(t, s, t->plan + (size_t)s * 2 * plan_levels);
 }
 
 #ifdef SQZ_SELFCHECK
@@ -371,10 +378,12 @@ static void selfcheck(const struct sqz_tree* t) {
     const int32_t root = tree_root(t);
     for (int32_t s = 0; s < t->n; s++) {
         if (t->up[s] < 0 || t->steps[s] == 0) { continue; }
-        uint32_t fresh[plan_levels];
+        uint16_t fresh[2 * plan_levels];
+        const uint16_t* held = t->plan + (size_t)s * 2 * plan_levels;
         const int steps = plan_for(t, s, fresh);
         if (steps != t->steps[s] ||
-            (steps != plan_too_deep && memcmp(fresh, t->plan + (size_t)s * plan_levels, 4 * (size_t)steps) != 0)) {
+            (steps != plan_too_deep && (memcmp(fresh, held, 2 * (size_t)steps) != 0 ||
+                                        memcmp(fresh + plan_levels, held + plan_levels, 2 * (size_t)steps) != 0))) {
             fprintf(stderr, "sqz selfcheck: stale plan of leaf %d\n", s);
             abort();
         }
@@ -405,27 +414,27 @@ static void selfcheck(const struct sqz_tree* t) {
  * provided no node on the way comes to outweigh its comparator.  Returns 0
  * with all weights as they were when one would: the exact walk has to decide
  * then.  `usual` is the tree's usual plan length (a constant at every call).  */
-#define SQZ_PLAN_STEP(e_) do { const uint32_t en_ = (e_);                        \
-        const uint64_t w_ = freq[en_ & 0xFFFF] + 1;                              \
-        fires |= (uint64_t)(w_ > freq[en_ >> 16]);                               \
-        freq[en_ & 0xFFFF] = w_; } while (0)
+#define SQZ_PLAN_STEP(k_) do {                                                   \
+        const int64_t w_ = (int64_t)freq[plan[k_]] + 1;                          \
+        fires |= (int64_t)freq[plan[plan_levels + (k_)]] - w_;   /* negative: outweighs */ \
+        freq[plan[k_]] = (uint64_t)w_; } while (0)
 
 static inline __attribute__((always_inline))
 int quick_count(struct sqz_tree* t, int32_t s, const int usual) {
     uint64_t* const freq = t->freq;
     if (t->steps[s] == 0) { make_plan(t, s); }
     const int steps = t->steps[s];
-    const uint32_t* const plan = t->plan + (size_t)s * plan_levels;
-    uint64_t fires = 0;
+    const uint16_t* const plan = t->plan + (size_t)s * 2 * plan_levels;
+    int64_t fires = 0;
     if (steps == usual) {
-        for (int k = 0; k < usual; k++) { SQZ_PLAN_STEP(plan[k]); }     /* unrolled: usual is constant */
+        for (int k = 0; k < usual; k++) { SQZ_PLAN_STEP(k); }           /* unrolled: usual is constant */
     } else if (steps == plan_levels) {
-        for (int k = 0; k < plan_levels; k++) { SQZ_PLAN_STEP(plan[k]); }
+        for (int k = 0; k < plan_levels; k++) { SQZ_PLAN_STEP(k); }
     } else {
         return 0;                                                       /* deeper than a plan */
     }
-    if (fires == 0) { return 1; }
-    for (int k = 0; k < steps; k++) { freq[plan[k] & 0xFFFF]--; }
+    if (fires >= 0) { return 1; }
+    for (int k = 0; k < steps; k++) { freq[plan[k]]--; }
     return 0;
 }
 
