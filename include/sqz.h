@@ -137,6 +137,19 @@ void sqz_symbols_of_tokens(const uint32_t* tokens, uint64_t count, uint32_t* wor
 void sqz_decompress(struct sqz* s, struct sqz_bitstream* bs,
                     uint8_t* data, uint64_t bytes);
 
+/* The serial half of sqz_decompress alone: read the tokens of a stream that
+ * expands to `bytes` bytes (literal byte, or (len << 16) | dist) without
+ * executing them.  *count receives the number of tokens even when it exceeds
+ * `cap` (then s->error = E2BIG).  Same checks as sqz_decompress.              */
+void sqz_decode_tokens(struct sqz* s, struct sqz_bitstream* bs, uint64_t bytes,
+                       uint32_t* tokens, uint64_t cap, uint64_t* count);
+
+/* sqz_decompress with the copy phase on the GPU: tokens are
+ * read on the host, then sqz_gpu_expand_tokens executes them.  bytes < 4 GiB.
+ * Host memory for the tokens is allocated inside (4 bytes per token).         */
+void sqz_decompress_gpu(struct sqz* s, struct sqz_bitstream* bs,
+                        uint8_t* data, uint64_t bytes);
+
 /* Convenience: whole buffers, memory mode, header included.  Return errno. */
 int sqz_compress_buffer(const uint8_t* data, uint64_t bytes, uint8_t win_bits,
                         uint8_t* out, uint64_t capacity, uint64_t* written);

@@ -134,6 +134,24 @@ int sqz_gpu_parse_exit_map_device(const uint32_t* d_table, size_t n,
                                   uint32_t min_len, uint32_t max_len,
                                   void* d_work, uint16_t* d_exit_map, void* stream);
 
+/* ---- decoder side: the LZ copy phase (replaces squeeze.h:533-539) --------- *
+ * The reference's decoder executes every token as it reads it: a literal is
+ * stored, a match copies len bytes from dist back, one byte at a time because
+ * the ranges may overlap.  With the tokens at hand (sqz_decode_tokens in sqz.h
+ * reads them from the bitstream on the host, which is the serial part) the
+ * copies are a parallel problem: a scan of the token lengths places every
+ * token, every output byte starts with a hop of `dist` to its source, and
+ * pointer doubling shortens all chains to one hop onto a literal.  Plain
+ * tokens (not symbol words); bytes < 4 GiB per call.  EINVAL when the tokens
+ * do not describe exactly `bytes` bytes or a match reaches before the start. */
+int sqz_gpu_expand_tokens(const uint32_t* tokens, size_t n_tokens, uint8_t* out, size_t bytes);
+/* device pointers; d_work holds sqz_gpu_expand_workspace(n_tokens, bytes) bytes.
+ * Returns after the kernels are queued on `stream`, except that it waits for
+ * the (few) rounds of pointer doubling to learn when the chains are done.     */
+size_t sqz_gpu_expand_workspace(size_t n_tokens, size_t bytes);
+int sqz_gpu_expand_tokens_device(const uint32_t* d_tokens, size_t n_tokens, uint8_t* d_out,
+                                 size_t bytes, void* d_work, void* stream);
+
 /* ---- utilities ----------------------------------------------------------- */
 int         sqz_gpu_abi_version(void);
 int         sqz_gpu_device_count(void);          /* 0 when no driver / device */

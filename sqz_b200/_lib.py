@@ -71,6 +71,8 @@ SYMBOLS = {
     "sqz_encode_tokens": (None, [C.POINTER(State), C.POINTER(Bitstream), u32p, C.c_uint64]),
     "sqz_encode_symbols": (None, [C.POINTER(State), C.POINTER(Bitstream), u32p, C.c_uint64]),
     "sqz_symbols_of_tokens": (None, [u32p, C.c_uint64, u32p]),
+    "sqz_decode_tokens": (None, [C.POINTER(State), C.POINTER(Bitstream), C.c_uint64, u32p, C.c_uint64, u64p]),
+    "sqz_decompress_gpu": (None, [C.POINTER(State), C.POINTER(Bitstream), u8p, C.c_uint64]),
     "sqz_decompress": (None, [C.POINTER(State), C.POINTER(Bitstream), u8p, C.c_uint64]),
     "sqz_compress_buffer": (C.c_int, [u8p, C.c_uint64, C.c_uint8, u8p, C.c_uint64, u64p]),
     "sqz_decompress_buffer": (C.c_int, [u8p, C.c_uint64, u8p, C.c_uint64, u64p]),
@@ -92,6 +94,9 @@ SYMBOLS = {
                                                C.c_void_p, size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sqz_gpu_parse_exit_map_device": (C.c_int, [C.c_void_p, size_t, C.c_uint32, C.c_uint32, C.c_void_p,
                                                 C.c_void_p, C.c_void_p]),
+    "sqz_gpu_expand_tokens": (C.c_int, [u32p, size_t, u8p, size_t]),
+    "sqz_gpu_expand_workspace": (size_t, [size_t, size_t]),
+    "sqz_gpu_expand_tokens_device": (C.c_int, [C.c_void_p, size_t, C.c_void_p, size_t, C.c_void_p, C.c_void_p]),
     "sqz_gpu_abi_version": (C.c_int, []),
     "sqz_gpu_device_count": (C.c_int, []),
     "sqz_gpu_last_error": (C.c_char_p, []),

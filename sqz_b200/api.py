@@ -182,6 +182,58 @@ def read_header(comp) -> tuple[int, int]:
     return int(n.value), int(wb.value)
 
 
+def decode_tokens(comp) -> np.ndarray:
+    """The serial half of the decoder: the token stream of a compressed buffer, not executed."""
+    L = _lib.load()
+    c = _u8(comp)
+    n, _ = read_header(c)
+    bs = Bitstream()
+    bs.data = c.ctypes.data_as(u8p)
+    bs.capacity = c.size
+    bs.bytes = c.size
+    hdr_n, hdr_w = C.c_uint64(), C.c_uint8()
+    L.sqz_read_header(C.byref(bs), C.byref(hdr_n), C.byref(hdr_w))
+    toks = np.empty(max(n, 1), dtype=np.uint32)
+    cnt = C.c_uint64()
+    s = State()
+    L.sqz_init(C.byref(s))
+    L.sqz_decode_tokens(C.byref(s), C.byref(bs), n, toks.ctypes.data_as(u32p), toks.size, C.byref(cnt))
+    _check(s.error, "sqz_decode_tokens")
+    return toks[: cnt.value].copy()
+
+
+def expand_tokens(toks, nbytes: int) -> bytes:
+    """The copy phase of the decoder on the GPU (squeeze.h:533-539 for all tokens at once)."""
+    L = _lib.load()
+    t = np.ascontiguousarray(toks, dtype=np.uint32)
+    out = np.empty(max(nbytes, 1), dtype=np.uint8)
+    rc = L.sqz_gpu_expand_tokens(t.ctypes.data_as(u32p), t.size, out.ctypes.data_as(u8p), nbytes)
+    _check(rc, "sqz_gpu_expand_tokens")
+    return out[:nbytes].tobytes()
+
+
+def decompress_gpu(comp, stats: dict | None = None) -> bytes:
+    """squeeze.read_header + squeeze.decompress with the copy phase on the GPU (sqz_decompress_gpu)."""
+    L = _lib.load()
+    c = _u8(comp)
+    bs = Bitstream()
+    bs.data = c.ctypes.data_as(u8p)
+    bs.capacity = c.size
+    bs.bytes = c.size
+    n, wb = C.c_uint64(), C.c_uint8()
+    L.sqz_read_header(C.byref(bs), C.byref(n), C.byref(wb))
+    _check(bs.error, "sqz_read_header")
+    out = np.empty(max(n.value, 1), dtype=np.uint8)
+    s = State()
+    L.sqz_init(C.byref(s))
+    L.sqz_decompress_gpu(C.byref(s), C.byref(bs), out.ctypes.data_as(u8p), n.value)
+    _check(s.error, "sqz_decompress_gpu")
+    if stats is not None:
+        stats.update(tokens=int(s.tokens), entropy_seconds=float(s.entropy_seconds),
+                     expand_seconds=float(s.search_seconds))
+    return out[: n.value].tobytes()
+
+
 def decompress(comp) -> bytes:
     """squeeze.read_header + squeeze.decompress (host only, never touches the GPU)."""
     L = _lib.load()

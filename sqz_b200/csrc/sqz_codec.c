@@ -427,8 +427,10 @@ int quick_count(struct sqz_tree* t, int32_t s, const int usual) {
     const uint16_t* const plan = t->plan + (size_t)s * 2 * plan_levels;
     int64_t fires = 0;
     if (steps == usual) {
-        for (int k = 0; k < usual; k++) { SQZ_PLAN_STEP(k); }           /* unrolled: usual is constant */
+#pragma GCC unroll 16
+        for (int k = 0; k < usual; k++) { SQZ_PLAN_STEP(k); }           /* usual is a constant here */
     } else if (steps == plan_levels) {
+#pragma GCC unroll 16
         for (int k = 0; k < plan_levels; k++) { SQZ_PLAN_STEP(k); }
     } else {
         return 0;                                                       /* deeper than a plan */
@@ -838,8 +840,10 @@ static inline int32_t window_symbol(struct sqz* s, struct window* w, struct sqz_
     return i;
 }
 
-void sqz_decompress(struct sqz* s, struct sqz_bitstream* bs,
-                    uint8_t* data, uint64_t bytes) {
+/* data != NULL: execute the tokens (squeeze.h:502-551); tokens != NULL: hand them out */
+static void decode_stream(struct sqz* s, struct sqz_bitstream* bs, uint8_t* data, uint64_t bytes,
+                          uint32_t* tokens, uint64_t cap, uint64_t* count) {
+    uint64_t n_tokens = 0;
     s->lit.lut = s->lit_lut;
     s->pos.lut = s->pos_lut;
     memset(s->lit_lut, 0xFF, sizeof(s->lit_lut));
@@ -859,7 +863,10 @@ void sqz_decompress(struct sqz* s, struct sqz_bitstream* bs,
             SQZ_CHECK(&s->lit);
         }
         if (sym <= 0xFF) {
-            data[i++] = (uint8_t)sym;
+            if (data != NULL) { data[i] = (uint8_t)sym; }
+            if (n_tokens < cap) { tokens[n_tokens] = (uint32_t)sym; }
+            n_tokens++;
+            i++;
             continue;
         }
         const int32_t b = sym - len_symbol0;
@@ -887,23 +894,58 @@ void sqz_decompress(struct sqz* s, struct sqz_bitstream* bs,
         }
         /* squeeze.h:533-539 copies byte by byte because the source may overlap the
          * destination; the result is the same as these three cases */
-        uint8_t* to = data + i;
-        const uint8_t* from = to - dist;
-        if (dist >= len)    { memcpy(to, from, len); }
-        else if (dist == 1) { memset(to, from[0], len); }
-        else                { for (uint32_t k = 0; k < len; k++) { to[k] = from[k]; } }
+        if (data != NULL) {
+            uint8_t* to = data + i;
+            const uint8_t* from = to - dist;
+            if (dist >= len)    { memcpy(to, from, len); }
+            else if (dist == 1) { memset(to, from[0], len); }
+            else                { for (uint32_t k = 0; k < len; k++) { to[k] = from[k]; } }
+        }
+        if (n_tokens < cap) { tokens[n_tokens] = len << 16 | dist; }
+        n_tokens++;
         i += len;
     }
+    if (count != NULL) { *count = n_tokens; }
+    if (tokens != NULL && n_tokens > cap && s->error == 0) { s->error = E2BIG; }
     bs->b64 = w.acc;                    /* what is left of the window (any bits in `pend` are dropped) */
     bs->bits = w.have;
     if (s->error != 0 && bs->error == 0) { bs->error = s->error; }
 }
 
+void sqz_decompress(struct sqz* s, struct sqz_bitstream* bs,
+                    uint8_t* data, uint64_t bytes) {
+    decode_stream(s, bs, data, bytes, NULL, 0, NULL);
+}
+
+void sqz_decode_tokens(struct sqz* s, struct sqz_bitstream* bs, uint64_t bytes,
+                       uint32_t* tokens, uint64_t cap, uint64_t* count) {
+    decode_stream(s, bs, NULL, bytes, tokens, tokens != NULL ? cap : 0, count);
+}
+
 /* ---- whole-buffer conveniences ----------------------------------------- */
+
+#include <stdlib.h>
+
+void sqz_decompress_gpu(struct sqz* s, struct sqz_bitstream* bs,
+                        uint8_t* data, uint64_t bytes) {
+    if (bytes >= ((uint64_t)1 << 32)) { s->error = EINVAL; return; }
+    uint32_t* tokens = (uint32_t*)malloc((size_t)(bytes > 0 ? bytes : 1) * 4);   /* at most one token per byte */
+    if (tokens == NULL) { s->error = ENOMEM; return; }
+    uint64_t count = 0;
+    double t0 = now_seconds();
+    sqz_decode_tokens(s, bs, bytes, tokens, bytes, &count);
+    s->entropy_seconds = now_seconds() - t0;
+    if (s->error == 0) {
+        t0 = now_seconds();
+        s->error = sqz_gpu_expand_tokens(tokens, (size_t)count, data, (size_t)bytes);
+        s->search_seconds = now_seconds() - t0;
+    }
+    s->tokens = count;
+    free(tokens);
+}
 
 static struct sqz* state_new(void);
 static void state_free(struct sqz* s);
-#include <stdlib.h>
 static struct sqz* state_new(void) { return (struct sqz*)malloc(sizeof(struct sqz)); }
 static void state_free(struct sqz* s) { free(s); }
 

@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include "match_bitsliced.cuh"
+#include "lz_expand.cuh"
 
 #include <atomic>
 #include <cerrno>
@@ -1087,6 +1088,86 @@ extern "C" int sqz_gpu_match_table(const uint8_t* data, size_t bytes, uint32_t w
         }
     }
     sqz_gpu_stream_close(st);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------
+// decoder side: the LZ copy phase on the GPU (lz_expand.cuh)
+// ---------------------------------------------------------------------------
+static size_t expand_blocks(size_t n_tokens) { return (n_tokens + expand::kScanBlock - 1) / expand::kScanBlock; }
+
+extern "C" size_t sqz_gpu_expand_workspace(size_t n_tokens, size_t bytes) {
+    // block offsets + {total, bad, changed} + one 32-bit hop per output byte
+    return parse::align_up(expand_blocks(n_tokens) * 8 + 8) + 256 + parse::align_up(bytes * 4 + 4);
+}
+
+extern "C" int sqz_gpu_expand_tokens_device(const uint32_t* d_tokens, size_t n_tokens, uint8_t* d_out,
+                                            size_t bytes, void* d_work, void* stream) {
+    if (bytes >= ((size_t)1 << 32)) { return fail(EINVAL, "one expand call handles less than 4 GiB"); }
+    if (n_tokens > bytes) { return fail(EINVAL, "more tokens than bytes"); }
+    if (bytes == 0) { return 0; }
+    if (n_tokens == 0) { return fail(EINVAL, "tokens describe fewer bytes than announced"); }
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t blocks = expand_blocks(n_tokens);
+    if (blocks > 0x7FFFFFFFull) { return fail(EINVAL, "too many tokens for one launch"); }
+    uint8_t* w = static_cast<uint8_t*>(d_work);
+    uint64_t* block_off = reinterpret_cast<uint64_t*>(w);
+    uint8_t* flags = w + parse::align_up(blocks * 8 + 8);
+    uint64_t* d_total = reinterpret_cast<uint64_t*>(flags);
+    int* d_bad = reinterpret_cast<int*>(flags + 8);
+    int* d_changed = reinterpret_cast<int*>(flags + 16);
+    uint32_t* hop = reinterpret_cast<uint32_t*>(flags + 256);
+    CU(cudaMemsetAsync(flags, 0, 256, s));
+    expand::block_lengths<<<(unsigned)blocks, 256, 0, s>>>(d_tokens, n_tokens, block_off);
+    LAUNCHED("expand_block_lengths");
+    expand::scan_blocks<<<1, 1024, 0, s>>>(block_off, blocks, d_total);
+    LAUNCHED("expand_scan_blocks");
+    struct { uint64_t total; int bad; int pad; int changed; } h = { 0, 0, 0, 0 };
+    CU(cudaMemcpyAsync(&h, flags, 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (h.total != bytes) { return fail(EINVAL, "tokens do not describe the announced number of bytes"); }
+    expand::place_tokens<<<(unsigned)blocks, 256, 0, s>>>(d_tokens, n_tokens, block_off, d_out, hop,
+                                                        (uint64_t)bytes, d_bad);
+    LAUNCHED("expand_place_tokens");
+    const unsigned grid = 148 * 8;
+    for (int round = 0; round < 40; round++) {       // a chain halves its hop count every round
+        CU(cudaMemsetAsync(d_changed, 0, 4, s));
+        expand::double_hops<<<grid, 256, 0, s>>>(hop, (uint64_t)bytes, d_changed);
+        LAUNCHED("expand_double_hops");
+        CU(cudaMemcpyAsync(&h, flags, 24, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        if (h.bad != 0) { return fail(EINVAL, "a match reaches before the start of the output"); }
+        if (h.changed == 0) { break; }
+    }
+    expand::fetch_bytes<<<grid, 256, 0, s>>>(hop, d_out, (uint64_t)bytes);
+    LAUNCHED("expand_fetch_bytes");
+    return 0;
+}
+
+extern "C" int sqz_gpu_expand_tokens(const uint32_t* tokens, size_t n_tokens, uint8_t* out, size_t bytes) {
+    if (bytes == 0) { return n_tokens == 0 ? 0 : fail(EINVAL, "tokens for an empty output"); }
+    if (tokens == nullptr || out == nullptr) { return fail(EINVAL, "null argument"); }
+    int device = -1;
+    if (int r = ensure_device(device)) { return r; }
+    uint32_t* d_tokens = nullptr;
+    uint8_t* d_out = nullptr;
+    void* d_work = nullptr;
+    cudaStream_t s = nullptr;
+    int rc = 0;
+    cudaError_t ce = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) { ce = cudaMalloc(&d_tokens, n_tokens * 4 + 4); }
+    if (ce == cudaSuccess) { ce = cudaMalloc(&d_out, bytes); }
+    if (ce == cudaSuccess) { ce = cudaMalloc(&d_work, sqz_gpu_expand_workspace(n_tokens, bytes)); }
+    if (ce == cudaSuccess) { ce = cudaMemcpyAsync(d_tokens, tokens, n_tokens * 4, cudaMemcpyHostToDevice, s); }
+    if (ce != cudaSuccess) { rc = fail(cuda_code(ce), "expand: allocation or upload", ce); }
+    if (rc == 0) { rc = sqz_gpu_expand_tokens_device(d_tokens, n_tokens, d_out, bytes, d_work, s); }
+    if (rc == 0) {
+        ce = cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, s);
+        if (ce == cudaSuccess) { ce = cudaStreamSynchronize(s); }
+        if (ce != cudaSuccess) { rc = fail(cuda_code(ce), "expand: download", ce); }
+    }
+    cudaFree(d_tokens); cudaFree(d_out); cudaFree(d_work);
+    if (s != nullptr) { cudaStreamDestroy(s); }
     return rc;
 }
 

@@ -99,7 +99,8 @@ def selfcheck_lib(tmp_path_factory):
                     'uint32_t a, uint32_t b, uint32_t c, size_t k, uint32_t m) { (void)s; (void)dev; (void)p; (void)n; (void)w; (void)a; '
                     '(void)b; (void)c; (void)k; (void)m; return ENODEV; }\n'
                     'int sqz_gpu_stream_next(sqz_gpu_stream* s, const uint32_t** t, size_t* c) { (void)s; (void)t; (void)c; return ENODEV; }\n'
-                    'void sqz_gpu_stream_close(sqz_gpu_stream* s) { (void)s; }\n')
+                    'void sqz_gpu_stream_close(sqz_gpu_stream* s) { (void)s; }\n'
+                    'int sqz_gpu_expand_tokens(const uint32_t* t, size_t n, uint8_t* o, size_t b) { (void)t; (void)n; (void)o; (void)b; return ENODEV; }\n')
     so = d / "libsqzcheck.so"
     subprocess.check_call(["gcc", "-std=gnu11", "-O2", "-fPIC", "-shared", "-DSQZ_SELFCHECK",
                            "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "sqz_b200", "csrc", "sqz_codec.c"),
@@ -146,6 +147,15 @@ def test_quick_walk_plans_stay_valid(case, selfcheck_lib, inputs, oracle, refere
                                              C.byref(got))
     assert rc == 0 and got.value == nbytes
     assert out.tobytes() == sq.decompress(ours) == reference.decompress(ours)
+
+
+@pytest.mark.parametrize("name", ["hello", "abc40", "zeros4096", "empty", "one", "laozi.txt", "x64.elf"])
+def test_decode_tokens_returns_what_was_encoded(name, inputs, oracle):
+    """sqz_decode_tokens: the serial half of the decoder alone (the copy phase is sqz_gpu_expand_tokens)."""
+    d = inputs[name]
+    t = oracle_tokens(oracle, d, 15)
+    got = sq.decode_tokens(sq.encode_tokens(t, d.size, 15))
+    assert got.size == t.size and (got == t).all()
 
 
 def test_header_bytes():

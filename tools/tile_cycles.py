@@ -23,6 +23,13 @@ for it in range(2):
 call = cyc.cpu().numpy(); c = call[:tiles]; dbg = call[1 << 20:] // 2
 print('search reasons: neighbour open %d, neighbour has no match %d, neighbour at max_len %d, byte differs %d, shard end %d, other %d' % tuple(int(x) for x in dbg[16:22]))
 print('finish: searched %d (%.3f%%), inherited %d (%.3f%%), word-steps/search %.1f, verifies/search %.1f, improvements/search %.2f' % (dbg[0], 100.0*dbg[0]/size, dbg[5], 100.0*dbg[5]/size, dbg[1]/max(dbg[0],1), dbg[2]/max(dbg[0],1), dbg[3]/max(dbg[0],1)))
+raw = call[1 << 20:]
+surv, better, tie_fresh, reject, hand, it_slow = (int(x) // 2 for x in raw[8:14])
+warp_iters = tiles * 4 * ((32767 + 127) // 128) * 32
+print('phase 1 scalar path: survivors %d (%.2f per position), improvements %d, fresh ties %d, rejects %d, handed over %d; '
+      'thread-iterations that entered it %d = %.2f%% of %d thread-iterations (%.1f%% of warp-iterations if spread evenly)'
+      % (surv, surv / size, better, tie_fresh, reject, hand, it_slow, 100.0 * it_slow / (warp_iters * 32), warp_iters * 32,
+         100.0 * min(1.0, it_slow / warp_iters)))
 print("tiles", tiles, "sum Gcyc", c.sum() / 1e9, "median", np.median(c), "p90", np.percentile(c, 90), "max", c.max())
 order = np.argsort(-c)[:12]
 B = corpus.base().size
