@@ -127,7 +127,8 @@ void sqz_encode_tokens(struct sqz* s, struct sqz_bitstream* bs,
 
 /* The same for symbol words -- tokens with the bucket arithmetic of
  * squeeze.h:290-315 already done, which is what the GPU parse emits in
- * `symbols` mode (include/sqz_gpu.h has the layout).  Words are trusted.     */
+ * `symbols` mode (include/sqz_gpu.h has the layout).  A word whose symbols are
+ * out of range sets s->error = EINVAL; extra-bit fields are taken as they are. */
 void sqz_encode_symbols(struct sqz* s, struct sqz_bitstream* bs,
                         const uint32_t* words, uint64_t count);
 /* token -> symbol word on the host (0xFFFFFFFF for a token the decoder would

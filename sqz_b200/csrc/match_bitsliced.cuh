@@ -151,11 +151,6 @@ __device__ __forceinline__ int pick_second_window(const uint32_t* __restrict__ W
     return 0xFFFF - (int)(mine & 0xFFFFu);
 }
 
-#ifndef SQZ_FINISH_AHEAD
-#define SQZ_FINISH_AHEAD 1
-#endif
-constexpr int kAhead = SQZ_FINISH_AHEAD;  // search steps whose words are loaded ahead of their use
-
 __device__ __noinline__ void finish_position(const uint8_t* __restrict__ S, int xi, int x_end,
                                              uint32_t d_from, uint32_t reach, uint32_t room, uint32_t min_len,
                                              uint32_t& best, uint32_t& bdist, int lane,
@@ -181,21 +176,7 @@ __device__ __noinline__ void finish_position(const uint8_t* __restrict__ S, int 
         const int c_hi = a - (int)d0;                      // nearest candidate still open
         const int c_lo = a - (int)reach;                   // farthest candidate
         bool improved = false;
-        // kAhead steps (32 words each) are loaded before the first of them is looked at: the image
-        // lives in global memory and a step is one dependent load otherwise
-        for (int wtop0 = c_hi >> 2; (wtop0 << 2) + 3 >= c_lo && !improved; wtop0 -= 32 * kAhead) {
-            uint32_t lows[kAhead], hiws[kAhead];
-#pragma unroll
-            for (int u = 0; u < kAhead; u++) {
-                const int w = wtop0 - 32 * u - lane;
-                const bool wanted = (w << 2) + 3 >= c_lo && w >= 0;      // below: no candidate in reach
-                lows[u] = wanted ? word_at(W, w, w_last) : 0u;
-                hiws[u] = wanted ? word_at(W, w + 1, w_last) : 0u;
-            }
-#pragma unroll
-            for (int u = 0; u < kAhead; u++) {
-            const int wtop = wtop0 - 32 * u;
-            if (improved || (wtop << 2) + 3 < c_lo) { break; }
+        for (int wtop = c_hi >> 2; (wtop << 2) + 3 >= c_lo && !improved; wtop -= 32) {
             const int w = wtop - lane;                     // lane 0 holds the nearest word
             uint32_t hb = 0;
             n_steps++;
@@ -203,7 +184,7 @@ __device__ __noinline__ void finish_position(const uint8_t* __restrict__ S, int 
             const bool interior = (wtop << 2) + 3 <= c_hi && ((wtop - 31) << 2) >= c_lo;
             if (interior || (w << 2) + 3 >= c_lo) {
                 SQZ_CHECK(w >= 0 && w <= w_last, "finish: candidate word outside the image");
-                const uint32_t low = lows[u], hiw = hiws[u];
+                const uint32_t low = W[w], hiw = word_at(W, w + 1, w_last);
                 const uint32_t t0 = (low ^ key) & mask;
                 const uint32_t t1 = (__byte_perm(low, hiw, 0x4321) ^ key) & mask;
                 const uint32_t t2 = (__byte_perm(low, hiw, 0x5432) ^ key) & mask;
@@ -250,7 +231,6 @@ __device__ __noinline__ void finish_position(const uint8_t* __restrict__ S, int 
                 }
                 if (m >= need) { best = m; bdist = hit_d; improved = true; n_improve++; break; }
                 if (lane == src) { hb &= ~(1u << kk); }
-            }
             }
         }
         if (!improved) { break; }

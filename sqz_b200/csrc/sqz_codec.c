@@ -637,6 +637,10 @@ static void code_symbols(struct sqz* s, const uint32_t* words, uint64_t count) {
     for (uint64_t k = 0; k < count; k++) {
         const uint32_t w = words[k];
         const uint32_t sym = w & 0x1FF;
+        if (sym > 0xFF && (sym < len_symbol0 || sym > len_symbol0 + 27 || ((w >> 14) & 31) > 29)) {
+            s->error = EINVAL;                       /* not a symbol word: the decoder would reject it */
+            goto done;
+        }
         if (lit->bits[sym] == 0) {                   /* first occurrence: escape + raw symbol */
             SQZ_SYNC_OUT();
             code_lit(s, sym);

@@ -201,6 +201,13 @@ def test_tokens_the_decoder_would_reject_are_einval(bad):
     assert e.value.errno == errno.EINVAL
 
 
+@pytest.mark.parametrize("bad", [256, 285, 511, 257 | 30 << 14, 0xFFFFFFFF])
+def test_words_that_are_not_symbol_words_are_einval(bad):
+    with pytest.raises(sq.SqzError) as e:
+        sq.encode_symbols(np.array([65, 66, 67, bad], np.uint32), 300, 15)
+    assert e.value.errno == errno.EINVAL
+
+
 def test_corrupt_streams_fail_cleanly(inputs, oracle):
     d = inputs["laozi.txt"]
     comp = bytearray(sq.encode_tokens(oracle_tokens(oracle, d, 15), d.size, 15))
