@@ -520,21 +520,31 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
 //
 // counters[0] is the segment cursor.
 // ---------------------------------------------------------------------------
-constexpr int kSegment = 1024;            // positions per work item of phase 2
+constexpr int kSegment = 1024;            // positions per work item of phase 2 (large shards)
+
+// A warp closes its segment's positions one after the other, so the slowest segment bounds the
+// latency of a small shard (x64.elf, 0.9 MB: 17 ms with 1024-position segments).  Small shards
+// get shorter segments, two per resident warp; each segment boundary costs at most one search
+// that inheritance would have saved.
+inline int finish_segment(long long n, int resident_warps) {
+    long long seg = n / (2LL * resident_warps);
+    seg = (seg + 31) / 32 * 32;
+    return (int)(seg < 64 ? 64 : (seg > kSegment ? kSegment : seg));
+}
 
 __global__ void __launch_bounds__(kThreads)
 finish_marked(const uint8_t* __restrict__ shard, long long back, long long n, long long ahead,
               uint32_t min_len, uint32_t max_len, uint32_t max_dist, uint32_t* __restrict__ table,
-              unsigned int* __restrict__ counters, unsigned long long* __restrict__ dbg) {
+              unsigned int* __restrict__ counters, unsigned long long* __restrict__ dbg, int segment) {
     const int lane = threadIdx.x & 31;
-    const long long segments = (n + kSegment - 1) / kSegment;
+    const long long segments = (n + segment - 1) / segment;
     for (;;) {
         unsigned int seg = 0;
         if (lane == 0) { seg = atomicAdd(counters, 1u); }
         seg = __shfl_sync(0xFFFFFFFFu, seg, 0);
         if ((long long)seg >= segments) { break; }
-        const long long s0 = (long long)seg * kSegment;
-        const long long s1 = min(s0 + kSegment, n);
+        const long long s0 = (long long)seg * segment;
+        const long long s1 = min(s0 + segment, n);
         long long known_pos = -1;                      // position closed last by this warp ...
         uint32_t known_word = 0;                       // ... and its final word
         for (long long top = s1; top > s0; top -= 32) {

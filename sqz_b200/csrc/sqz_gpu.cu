@@ -618,7 +618,8 @@ static int launch_v2(const uint8_t* d_shard, size_t back, size_t n, size_t ahead
     if (fork != nullptr) { CU(cudaEventDestroy(fork)); }
     v2::finish_marked<<<148 * 16, v2::kThreads, 0, s>>>(d_shard, (long long)back, (long long)n, (long long)ahead,
                                                      (uint32_t)kMinLen, max_len, max_dist, d_table, d_counters,
-                                                     g_tile_cycles ? g_tile_cycles + (1 << 20) : nullptr);
+                                                     g_tile_cycles ? g_tile_cycles + (1 << 20) : nullptr,
+                                                     v2::finish_segment((long long)n, 148 * 16 * v2::kWarps));
     LAUNCHED("match_finish_marked");
     return 0;
 }
