@@ -79,6 +79,9 @@ struct sqz_tree {
     int32_t next;       /* internal nodes are handed out downward from here */
     int32_t depth;      /* high-water mark, reset by a root-level relabel */
     int32_t complete;   /* frozen: no more frequency updates */
+    int32_t lazy;       /* symbols that may still be coded without touching the top internal nodes */
+    int32_t lazy_start; /* value of `lazy` when the top internal nodes were last exact */
+    int32_t eager;      /* symbols left to code with full walks before the top is looked at again */
 };
 
 #define SQZ_TREE_STORE(N) struct {                                          \

@@ -35,7 +35,8 @@ class Tree(C.Structure):
     _fields_ = [("freq", u64p), ("path", u64p), ("code", u64p),
                 ("up", C.POINTER(C.c_int16)), ("lo", C.POINTER(C.c_int16)), ("hi", C.POINTER(C.c_int16)),
                 ("plan", u16p), ("steps", u8p), ("bits", u8p), ("lut", u16p), ("lut_bits", C.c_int32),
-                ("n", C.c_int32), ("next", C.c_int32), ("depth", C.c_int32), ("complete", C.c_int32)]
+                ("n", C.c_int32), ("next", C.c_int32), ("depth", C.c_int32), ("complete", C.c_int32),
+                ("lazy", C.c_int32), ("lazy_start", C.c_int32), ("eager", C.c_int32)]
 
 
 def _store(n: int):

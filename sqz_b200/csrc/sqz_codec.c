@@ -178,6 +178,7 @@ static void tree_init(struct sqz_tree* t) {
     t->next = 2 * t->n - 2;
     t->depth = 0;
     t->complete = 0;
+    t->lazy = t->lazy_start = t->eager = 0;
     for (int32_t k = 0; k < nodes; k++) {
         t->freq[k] = 0; t->path[k] = 0; t->bits[k] = 0;
         t->up[k] = none; t->lo[k] = none; t->hi[k] = none;
@@ -339,7 +340,10 @@ static uint32_t comparator(const struct sqz_tree* t, int32_t i) {
 }
 
 enum { plan_levels = 16, plan_too_deep = 0xFF,
-       lit_plan = 9, pos_plan = 6 };   /* covers 98 % / 97 % of the symbols of the bench corpus */
+       lit_plan = 9, pos_plan = 6,     /* covers 98 % / 97 % of the symbols of the bench corpus */
+       top_levels = 3,                 /* internal nodes this close to the root are kept up to date lazily */
+       lazy_least = 32,                /* a lazy stretch shorter than this is not worth its bookkeeping */
+       eager_run = 32 };               /* symbols coded with full walks before the top is looked at again */
 
 /* plan of leaf `s`: one cache line, plan[0..15] the nodes from the leaf up to
  * the root's child, plan[16..31] their comparators, padded with spare nodes
@@ -348,24 +352,36 @@ enum { plan_levels = 16, plan_too_deep = 0xFF,
  * signed numbers; a path that already carries 2^61 gets no plan.             */
 static int plan_for(const struct sqz_tree* t, int32_t s, uint16_t* plan) {
     const int usual = t->n == sqz_lit_symbols ? lit_plan : pos_plan;
-    int k = 0;
+    int32_t chain[plan_levels];                      /* chain[0] = the leaf ... chain[d-1] = the root's child */
+    int d = 0;
     for (int32_t i = s; t->up[i] >= 0; i = t->up[i]) {
-        if (k == plan_levels || t->freq[i] >> 61 != 0) { return plan_too_deep; }
-        plan[k] = (uint16_t)i;
-        plan[plan_levels + k] = (uint16_t)comparator(t, i);
-        k++;
+        if (d == plan_levels || t->freq[i] >> 61 != 0) { return plan_too_deep; }
+        chain[d++] = i;
     }
+    /* order: [0] the leaf, [1..3] its ancestors at depth 1, 2, 3 -- the entries the lazy walk
+     * leaves out --, [4..] the ancestors at depth 4 and below; spare nodes where there is none */
+    int k = 0, pad = 0;
+#define SQZ_PLAN_PUT(node_) do { plan[k] = (uint16_t)(node_);                                   \
+                                 plan[plan_levels + k] = (uint16_t)comparator(t, (int32_t)(node_)); k++; } while (0)
+#define SQZ_PLAN_PAD() do { plan[k] = (uint16_t)spare_node(t, pad++);                            \
+                            plan[plan_levels + k] = (uint16_t)never_node(t); k++; } while (0)
+    SQZ_PLAN_PUT(chain[0]);
+    for (int depth = 1; depth <= top_levels; depth++) {
+        if (d - depth >= 1) { SQZ_PLAN_PUT(chain[d - depth]); } else { SQZ_PLAN_PAD(); }
+    }
+    for (int depth = top_levels + 1; depth <= d - 1; depth++) { SQZ_PLAN_PUT(chain[d - depth]); }
     const int padded = k <= usual ? usual : plan_levels;
-    for (int pad = 0; k < padded; pad++, k++) {
-        plan[k] = (uint16_t)spare_node(t, pad);
-        plan[plan_levels + k] = (uint16_t)never_node(t);
-    }
+    while (k < padded) { SQZ_PLAN_PAD(); }
+#undef SQZ_PLAN_PUT
+#undef SQZ_PLAN_PAD
     return padded;
 }
 
 static void make_plan(struct sqz_tree* t, int32_t s) {
     t->steps[s] = (uint8_t)plan_for(t, s, t->plan + (size_t)s * 2 * plan_levels);
 }
+
+static void settle(struct sqz_tree* t);
 
 #ifdef SQZ_SELFCHECK
 /* Test builds only (tests/test_codec.py): after every symbol, every plan that
@@ -374,8 +390,9 @@ static void make_plan(struct sqz_tree* t, int32_t s) {
  * the lighter child is on the left.                                          */
 #include <stdio.h>
 #include <stdlib.h>
-static void selfcheck(const struct sqz_tree* t) {
+static void selfcheck(struct sqz_tree* t) {
     const int32_t root = tree_root(t);
+    settle(t);                          /* the checks below are about exact weights */
     for (int32_t s = 0; s < t->n; s++) {
         if (t->up[s] < 0 || t->steps[s] == 0) { continue; }
         uint16_t fresh[2 * plan_levels];
@@ -419,24 +436,89 @@ static void selfcheck(const struct sqz_tree* t) {
         fires |= (int64_t)freq[plan[plan_levels + (k_)]] - w_;   /* negative: outweighs */ \
         freq[plan[k_]] = (uint64_t)w_; } while (0)
 
+/* The weights of the internal nodes at depth 1..top_levels, from their children.  Only when
+ * lazy walks went by since they were last exact: then every one of them was in order and the
+ * sum of its children (lazy_budget checks), so the sums are what full walks would have left. */
+static void settle(struct sqz_tree* t) {
+    if (t->lazy == t->lazy_start) { return; }
+    int32_t level[top_levels][1 << top_levels];
+    int count[top_levels];
+    int32_t above[1] = { tree_root(t) };
+    const int32_t* from = above;
+    int from_count = 1;
+    for (int l = 0; l < top_levels; l++) {
+        count[l] = 0;
+        for (int k = 0; k < from_count; k++) {
+            const int32_t lo = t->lo[from[k]], hi = t->hi[from[k]];
+            if (lo >= t->n) { level[l][count[l]++] = lo; }
+            if (hi >= t->n) { level[l][count[l]++] = hi; }
+        }
+        from = level[l];
+        from_count = count[l];
+    }
+    for (int l = top_levels - 1; l >= 0; l--) {
+        for (int k = 0; k < count[l]; k++) { sum_children(t, level[l][k]); }
+    }
+    t->lazy_start = t->lazy;
+}
+
+/* How many symbols can be coded without looking at the internal nodes at depth 1..top_levels:
+ * each symbol moves each of their weights by at most one, so none of them can outweigh its
+ * comparator before the smallest margin among them is used up.  0 when one of them is not in
+ * the state the quick walk relies on.  Call with the top exact (settle).                     */
+static int32_t lazy_budget(const struct sqz_tree* t) {
+    int64_t least = 1 << 20;
+    int32_t frontier[1 << top_levels], next[1 << top_levels];
+    int n_frontier = 1;
+    frontier[0] = tree_root(t);
+    for (int l = 0; l < top_levels; l++) {
+        int n_next = 0;
+        for (int k = 0; k < n_frontier; k++) {
+            const int32_t kids[2] = { t->lo[frontier[k]], t->hi[frontier[k]] };
+            for (int c = 0; c < 2; c++) {
+                const int32_t i = kids[c];
+                if (i < t->n) { continue; }              /* a leaf (or no child): leaves are always walked */
+                const int32_t lo = t->lo[i], hi = t->hi[i];
+                if (t->freq[i] != weight_or_zero(t, lo) + weight_or_zero(t, hi) || lo < 0 || hi < 0 ||
+                    t->freq[lo] > t->freq[hi]) {
+                    return 0;
+                }
+                const uint32_t cmp = comparator(t, i);
+                if (cmp == always_node(t)) { return 0; }
+                if (cmp != never_node(t)) {
+                    const int64_t margin = (int64_t)t->freq[cmp] - (int64_t)t->freq[i];
+                    if (margin < least) { least = margin; }
+                }
+                next[n_next++] = i;
+            }
+        }
+        memcpy(frontier, next, sizeof(int32_t) * (size_t)n_next);
+        n_frontier = n_next;
+    }
+    return least < lazy_least ? 0 : (int32_t)least;
+}
+
 static inline __attribute__((always_inline))
-int quick_count(struct sqz_tree* t, int32_t s, const int usual) {
+int quick_count(struct sqz_tree* t, int32_t s, const int usual, const int lazily) {
     uint64_t* const freq = t->freq;
-    if (t->steps[s] == 0) { make_plan(t, s); }
+    if (t->steps[s] == 0) { settle(t); make_plan(t, s); }              /* plans are made from exact weights */
     const int steps = t->steps[s];
     const uint16_t* const plan = t->plan + (size_t)s * 2 * plan_levels;
     int64_t fires = 0;
     if (steps == usual) {
+        SQZ_PLAN_STEP(0);
 #pragma GCC unroll 16
-        for (int k = 0; k < usual; k++) { SQZ_PLAN_STEP(k); }           /* usual is a constant here */
+        for (int k = lazily ? top_levels + 1 : 1; k < usual; k++) { SQZ_PLAN_STEP(k); }   /* usual is a constant here */
     } else if (steps == plan_levels) {
+        SQZ_PLAN_STEP(0);
 #pragma GCC unroll 16
-        for (int k = 0; k < plan_levels; k++) { SQZ_PLAN_STEP(k); }
+        for (int k = lazily ? top_levels + 1 : 1; k < plan_levels; k++) { SQZ_PLAN_STEP(k); }
     } else {
         return 0;                                                       /* deeper than a plan */
     }
     if (fires >= 0) { return 1; }
-    for (int k = 0; k < steps; k++) { freq[plan[k]]--; }
+    freq[plan[0]]--;
+    for (int k = lazily ? top_levels + 1 : 1; k < steps; k++) { freq[plan[k]]--; }
     return 0;
 }
 
@@ -446,6 +528,8 @@ int quick_count(struct sqz_tree* t, int32_t s, const int usual) {
 static int tree_insert(struct sqz_tree* t, int32_t s) {
     int ok = 1;
     int32_t at = tree_root(t);
+    settle(t);                          /* what follows reads and reorders exact weights */
+    t->lazy = t->lazy_start = t->eager = 0;
     t->freq[s] = 1;
     while (at >= t->n) {
         if (t->hi[at] < 0)      { t->hi[at] = (int16_t)s; t->up[s] = (int16_t)at; break; }
@@ -491,7 +575,21 @@ void tree_count_as(struct sqz_tree* t, int32_t s, const int usual) {   /* huffma
     if (t->up[s] < 0) {
         (void)tree_insert(t, s);
     } else if (!t->complete && t->depth < 63 && t->freq[s] < UINT64_MAX - 1) {
-        if (quick_count(t, s, usual)) { return; }
+        if (t->lazy == 0 && t->eager == 0) {            /* decide how the next stretch is walked */
+            settle(t);
+            t->lazy = t->lazy_start = lazy_budget(t);
+            if (t->lazy == 0) { t->eager = eager_run; }
+        }
+        if (t->lazy > 0) {
+            if (quick_count(t, s, usual, 1)) { t->lazy--; return; }
+            /* something may outweigh its comparator -- possibly only because the comparator's weight
+             * is behind: make the top exact and let the full walk decide */
+            settle(t);
+            t->lazy = t->lazy_start = 0;
+            t->eager = eager_run;
+        }
+        if (quick_count(t, s, usual, 0)) { t->eager--; return; }
+        t->eager = 0;
         t->freq[s]++;
         weight_changed(t, s);
     } else {

@@ -158,6 +158,21 @@ def test_decode_tokens_returns_what_was_encoded(name, inputs, oracle):
     assert got.size == t.size and (got == t).all()
 
 
+def test_long_mixed_stream_equals_the_reference_encoder(oracle, reference):
+    """2.4 M tokens over text, ELF and image data (6 MiB of the bench corpus across its file seams): the
+    quick, lazy and exact walks of the coder all take part; bytes must equal the unmodified reference's
+    encoder on the same tokens, and both decoders must return the input."""
+    from sqz_b200 import corpus
+    d = corpus.synthetic(6 << 20, 3276897 - (1 << 20))
+    t = oracle_tokens(oracle, d, 15)
+    ours = sq.encode_tokens(t, d.size, 15)
+    assert ours == reference.encode_tokens(t, d.size, 15)
+    assert sq.encode_symbols(sq.symbols_of_tokens(t), d.size, 15) == ours
+    assert sq.decompress(ours) == d.tobytes()
+    got = sq.decode_tokens(ours)
+    assert got.size == t.size and (got == t).all()
+
+
 def test_header_bytes():
     """LSB-first fields in an MSB-first register, big-endian words."""
     c = sq.encode_tokens(np.zeros(0, np.uint32), 4096, 15)
