@@ -572,6 +572,19 @@ static int tree_insert(struct sqz_tree* t, int32_t s) {
 
 static inline __attribute__((always_inline))
 void tree_count_as(struct sqz_tree* t, int32_t s, const int usual) {   /* huffman.h:218-235 */
+    /* the common case first: a lazy stretch is on (which implies the tree is neither complete nor
+     * 63 deep: both only change where `lazy` is reset) and the leaf has a plan of the usual length */
+    if (t->lazy > 0 && t->steps[s] == usual) {
+        uint64_t* const freq = t->freq;
+        const uint16_t* const plan = t->plan + (size_t)s * 2 * plan_levels;
+        int64_t fires = 0;
+        SQZ_PLAN_STEP(0);
+#pragma GCC unroll 16
+        for (int k = top_levels + 1; k < usual; k++) { SQZ_PLAN_STEP(k); }
+        if (fires >= 0) { t->lazy--; return; }
+        freq[plan[0]]--;
+        for (int k = top_levels + 1; k < usual; k++) { freq[plan[k]]--; }
+    }
     if (t->up[s] < 0) {
         (void)tree_insert(t, s);
     } else if (!t->complete && t->depth < 63 && t->freq[s] < UINT64_MAX - 1) {
