@@ -339,9 +339,12 @@ static uint32_t comparator(const struct sqz_tree* t, int32_t i) {
     return u >= 0 ? (uint32_t)u : always_node(t);
 }
 
+#ifndef SQZ_TOP_LEVELS
+#define SQZ_TOP_LEVELS 3
+#endif
 enum { plan_levels = 16, plan_too_deep = 0xFF,
        lit_plan = 9, pos_plan = 6,     /* covers 98 % / 97 % of the symbols of the bench corpus */
-       top_levels = 3,                 /* internal nodes this close to the root are kept up to date lazily */
+       top_levels = SQZ_TOP_LEVELS,                 /* internal nodes this close to the root are kept up to date lazily */
        lazy_least = 32,                /* a lazy stretch shorter than this is not worth its bookkeeping */
        eager_run = 32 };               /* symbols coded with full walks before the top is looked at again */
 
@@ -352,7 +355,7 @@ enum { plan_levels = 16, plan_too_deep = 0xFF,
  * signed numbers; a path that already carries 2^61 gets no plan.             */
 static int plan_for(const struct sqz_tree* t, int32_t s, uint16_t* plan) {
     const int usual = t->n == sqz_lit_symbols ? lit_plan : pos_plan;
-    int32_t chain[plan_levels];                      /* chain[0] = the leaf ... chain[d-1] = the root's child */
+    int32_t chain[plan_levels] = { s };              /* chain[0] = the leaf ... chain[d-1] = the root's child */
     int d = 0;
     for (int32_t i = s; t->up[i] >= 0; i = t->up[i]) {
         if (d == plan_levels || t->freq[i] >> 61 != 0) { return plan_too_deep; }
