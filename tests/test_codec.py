@@ -173,6 +173,59 @@ def test_long_mixed_stream_equals_the_reference_encoder(oracle, reference):
     assert got.size == t.size and (got == t).all()
 
 
+def _random_stream(rng):
+    """A decodable token stream with a random alphabet, distribution and burstiness."""
+    n = int(rng.integers(1, 30000))
+    alphabet = rng.permutation(256)[: int(rng.integers(1, 257))]
+    kind = int(rng.integers(0, 4))
+    if kind == 0:        # uniform over the alphabet: constant near-ties, reorderings all the time
+        lit = alphabet[rng.integers(0, alphabet.size, n)]
+    elif kind == 1:      # zipf: a deep, lopsided tree
+        lit = alphabet[np.minimum(rng.zipf(1.3, n) - 1, alphabet.size - 1)]
+    elif kind == 2:      # phases: the distribution changes every few thousand tokens
+        lit = np.concatenate([alphabet[(rng.integers(0, max(1, alphabet.size // 4), 2500) + off) % alphabet.size]
+                              for off in rng.integers(0, alphabet.size, n // 2500 + 1)])[:n]
+    else:                # two symbols taking turns: ties at the top of the tree
+        lit = alphabet[np.arange(n) % min(2, alphabet.size)]
+    p_match = float(rng.choice([0.0, 0.05, 0.5]))
+    want_match = rng.random(n) < p_match
+    lens = rng.integers(3, 258, n)
+    dists = np.minimum(2 ** rng.integers(0, 15, n) + rng.integers(0, 9, n), 32767)
+    toks, made = [], 0
+    for k in range(n):
+        if want_match[k] and made >= 1:
+            toks.append(int(lens[k]) << 16 | int(min(dists[k], made)))
+            made += int(lens[k])
+        else:
+            toks.append(int(lit[k]))
+            made += 1
+    return np.array(toks, np.uint32), made
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_streams_equal_the_reference_encoder(seed, reference):
+    toks, nbytes = _random_stream(np.random.default_rng(1000 + seed))
+    ours = sq.encode_tokens(toks, nbytes, 15)
+    assert ours == reference.encode_tokens(toks, nbytes, 15)
+    assert sq.encode_symbols(sq.symbols_of_tokens(toks), nbytes, 15) == ours
+    got = sq.decode_tokens(ours)
+    assert got.size == toks.size and (got == toks).all()
+    assert sq.decompress(ours) == reference.decompress(ours)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_streams_keep_the_self_check_quiet(seed, selfcheck_lib, reference):
+    toks, nbytes = _random_stream(np.random.default_rng(2000 + seed))
+    ours = sq.encode_tokens(toks, nbytes, 15, lib=selfcheck_lib)       # aborts on a stale plan or table
+    assert ours == reference.encode_tokens(toks, nbytes, 15)
+    c = np.frombuffer(ours, np.uint8)
+    out = np.zeros(max(nbytes, 1), np.uint8)
+    got = C.c_uint64()
+    assert selfcheck_lib.sqz_decompress_buffer(c.ctypes.data_as(_lib.u8p), c.size, out.ctypes.data_as(_lib.u8p),
+                                               out.size, C.byref(got)) == 0
+    assert out[:nbytes].tobytes() == reference.decompress(ours)
+
+
 def test_header_bytes():
     """LSB-first fields in an MSB-first register, big-endian words."""
     c = sq.encode_tokens(np.zeros(0, np.uint32), 4096, 15)
