@@ -942,6 +942,9 @@ static int stream_launch_next(sqz_gpu_stream* st, uint16_t* len_out, uint16_t* d
         }
         CU(cudaEventRecord(st->prev_parsed, s.stream));
         st->prev_result = s.d_result;
+        // the tokens follow right away, all n slots of them (the count is only known on the device):
+        // the copy engine is idle anyway and the consumer finds them in pinned memory when it asks
+        CU(cudaMemcpyAsync(s.h_tokens, s.d_tokens, n * 4, cudaMemcpyDeviceToHost, s.stream));
     } else {
         if (int r = sqz_gpu_unpack_table_device(s.d_table, n, s.d_len, s.d_dist, s.stream)) { return r; }
         CU(cudaMemcpyAsync(len_out + first, s.d_len, n * 2, cudaMemcpyDeviceToHost, s.stream));
@@ -1028,8 +1031,6 @@ extern "C" int sqz_gpu_stream_next(sqz_gpu_stream* st, const uint32_t** tokens, 
     CU(cudaEventSynchronize(s.done));
     const uint64_t n_tok = s.h_result[0];
     if (n_tok > s.n) { return fail(EIO, "parse produced more tokens than positions"); }
-    CU(cudaMemcpyAsync(s.h_tokens, s.d_tokens, n_tok * 4, cudaMemcpyDeviceToHost, s.stream));
-    CU(cudaStreamSynchronize(s.stream));
     s.busy = false;
     st->delivered = s.first + s.n;
     st->read_slot ^= 1;
