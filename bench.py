@@ -354,6 +354,12 @@ def ours(args) -> None:
     try:
         import sqz_b200 as sq
         sample = np.ascontiguousarray(host[back: back + min(n, args.compress_sample)])
+        # one untimed call first, like the W warm-up steps of the main metric: it allocates the
+        # pipeline's pinned and device buffers (two slots of 32 MiB chunks), which later calls reuse
+        warm = sample[: min(sample.size, (33 << 20))]
+        t0 = time.perf_counter()
+        sq.compress(warm, 15)
+        dt_warm = time.perf_counter() - t0
         st = {}
         t0 = time.perf_counter()
         blob = sq.compress(sample, 15, stats=st)
@@ -365,6 +371,8 @@ def ours(args) -> None:
                 "compressed_bytes": len(blob), "seconds": dt, "search_wait_seconds": st["search_seconds"],
                 "entropy_seconds": st["entropy_seconds"], "tokens": st["tokens"],
                 "entropy_ns_per_token": st["entropy_seconds"] * 1e9 / max(st["tokens"], 1),
+                "warmup": "one untimed sqz_compress of the first %d MiB (%.2f s: it allocates the pipeline's "
+                          "pinned and device buffers)" % (warm.size >> 20, dt_warm),
                 "decompress": {"value": sample.size / 1e6 / dt_dec, "unit": "MB/s", "seconds": dt_dec,
                                "round_trip_identical": back_again == sample.tobytes()},
                 "note": "sqz_compress(host in, host bitstream out): the serial adaptive-Huffman stage on one "
