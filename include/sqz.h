@@ -149,7 +149,7 @@ void sqz_decode_tokens(struct sqz* s, struct sqz_bitstream* bs, uint64_t bytes,
                        uint32_t* tokens, uint64_t cap, uint64_t* count);
 
 /* sqz_decompress with the copy phase on the GPU: tokens are
- * read on the host, then sqz_gpu_expand_tokens executes them.  bytes < 4 GiB.
+ * read on the host, then sqz_gpu_expand_tokens executes them.  bytes < 2 GiB.
  * Host memory for the tokens is allocated inside (4 bytes per token).         */
 void sqz_decompress_gpu(struct sqz* s, struct sqz_bitstream* bs,
                         uint8_t* data, uint64_t bytes);

@@ -142,7 +142,7 @@ int sqz_gpu_parse_exit_map_device(const uint32_t* d_table, size_t n,
  * copies are a parallel problem: a scan of the token lengths places every
  * token, every output byte starts with a hop of `dist` to its source, and
  * pointer doubling shortens all chains to one hop onto a literal.  Plain
- * tokens (not symbol words); bytes < 4 GiB per call.  EINVAL when the tokens
+ * tokens (not symbol words); bytes < 2 GiB per call.  EINVAL when the tokens
  * do not describe exactly `bytes` bytes or a match reaches before the start. */
 int sqz_gpu_expand_tokens(const uint32_t* tokens, size_t n_tokens, uint8_t* out, size_t bytes);
 /* device pointers; d_work holds sqz_gpu_expand_workspace(n_tokens, bytes) bytes.

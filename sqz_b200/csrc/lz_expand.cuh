@@ -11,10 +11,12 @@
 //      byte of a match (`hop`);
 //   3. pointer doubling: hop[j] += hop[j - hop[j]] until the byte j - hop[j] is a literal.  A chain
 //      only ever walks towards the start, so in-place updates are safe: whatever a thread reads
-//      from a neighbour is a valid (possibly already longer) hop of the same chain;
+//      from a neighbour is a valid (possibly already longer) hop of the same chain.  A hop that
+//      has reached its literal is marked (bit 31) and never looked at again, and whoever lands
+//      on a marked hop is done as well: after two or three rounds most bytes cost one read;
 //   4. out[j] = out[j - hop[j]].
 //
-// Distances accumulate along a chain, so hops are 32-bit and one call handles < 4 GiB.
+// Distances accumulate along a chain, so hops are 31-bit and one call handles < 2 GiB.
 #pragma once
 
 #include <cstdint>
@@ -23,6 +25,7 @@
 namespace expand {
 
 constexpr int kScanBlock = 2048;          // tokens per block of the length scan (256 threads x 8)
+constexpr uint32_t kLanded = 0x80000000u; // hop mark: the byte this hop points at is a literal
 
 __device__ __forceinline__ uint32_t token_len(uint32_t t) { return (t >> 16) != 0 ? (t >> 16) : 1u; }
 
@@ -139,16 +142,22 @@ place_tokens(const uint32_t* __restrict__ tokens, size_t n_tokens, const uint64_
     }
 }
 
-// one round of pointer doubling; *changed is set when any hop grew
+// one round of pointer doubling; *changed is set when some hop has not reached its literal yet
 __global__ void __launch_bounds__(256)
 double_hops(uint32_t* __restrict__ hop, uint64_t bytes, int* __restrict__ changed) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     bool any = false;
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < bytes; j += stride) {
         const uint32_t h = hop[j];
-        if (h != 0) {
-            const uint32_t g = hop[j - h];
-            if (g != 0) { hop[j] = h + g; any = true; }
+        if (h == 0 || (h & kLanded) != 0) { continue; }       // a literal, or already on its literal
+        const uint32_t g = hop[j - h];
+        if (g == 0) {
+            hop[j] = h | kLanded;
+        } else if ((g & kLanded) != 0) {
+            hop[j] = (h + (g & ~kLanded)) | kLanded;
+        } else {
+            hop[j] = h + g;
+            any = true;                                       // still on its way
         }
     }
     if (__syncthreads_or(any) && threadIdx.x == 0) { *changed = 1; }
@@ -158,7 +167,7 @@ __global__ void __launch_bounds__(256)
 fetch_bytes(const uint32_t* __restrict__ hop, uint8_t* __restrict__ out, uint64_t bytes) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < bytes; j += stride) {
-        const uint32_t h = hop[j];
+        const uint32_t h = hop[j] & ~kLanded;
         if (h != 0) { out[j] = out[j - h]; }
     }
 }

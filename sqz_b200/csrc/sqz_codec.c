@@ -1046,7 +1046,7 @@ void sqz_decode_tokens(struct sqz* s, struct sqz_bitstream* bs, uint64_t bytes,
 
 void sqz_decompress_gpu(struct sqz* s, struct sqz_bitstream* bs,
                         uint8_t* data, uint64_t bytes) {
-    if (bytes >= ((uint64_t)1 << 32)) { s->error = EINVAL; return; }
+    if (bytes >= ((uint64_t)1 << 31)) { s->error = EINVAL; return; }
     uint32_t* tokens = (uint32_t*)malloc((size_t)(bytes > 0 ? bytes : 1) * 4);   /* at most one token per byte */
     if (tokens == NULL) { s->error = ENOMEM; return; }
     uint64_t count = 0;

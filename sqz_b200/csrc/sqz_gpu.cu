@@ -1119,7 +1119,7 @@ extern "C" size_t sqz_gpu_expand_workspace(size_t n_tokens, size_t bytes) {
 
 extern "C" int sqz_gpu_expand_tokens_device(const uint32_t* d_tokens, size_t n_tokens, uint8_t* d_out,
                                             size_t bytes, void* d_work, void* stream) {
-    if (bytes >= ((size_t)1 << 32)) { return fail(EINVAL, "one expand call handles less than 4 GiB"); }
+    if (bytes >= ((size_t)1 << 31)) { return fail(EINVAL, "one expand call handles less than 2 GiB"); }
     if (n_tokens > bytes) { return fail(EINVAL, "more tokens than bytes"); }
     if (bytes == 0) { return 0; }
     if (n_tokens == 0) { return fail(EINVAL, "tokens describe fewer bytes than announced"); }

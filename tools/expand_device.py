@@ -24,5 +24,5 @@ launches = (sq.launch_count() - before) // 3
 rounds = launches - 4
 same = bool((out.cpu().numpy() == d).all())
 alg = toks.size * 4 * 2 + d.size * (4 + 1) + rounds * d.size * 12 + d.size * 5      # scan + place, doubling rounds, fetch
-print("%d MiB, %d tokens: %.2f ms = %.1f GB/s of output, %d doubling rounds, ~%.0f GB/s of HBM traffic by the algorithm's count; identical %s"
+print("%d MiB, %d tokens: %.2f ms = %.1f GB/s of output, %d doubling rounds, at most %.0f GB/s of HBM traffic by the algorithm's count (every round counted in full); identical %s"
       % (mb, toks.size, ms, d.size / 1e6 / ms, rounds, alg / 1e6 / ms, same))
