@@ -375,9 +375,11 @@ def ours(args) -> None:
                           "pinned and device buffers)" % (warm.size >> 20, dt_warm),
                 "decompress": {"value": sample.size / 1e6 / dt_dec, "unit": "MB/s", "seconds": dt_dec,
                                "round_trip_identical": back_again == sample.tobytes()},
-                "note": "sqz_compress(host in, host bitstream out): the serial adaptive-Huffman stage on one "
-                        "host core bounds it (SURVEY 7 H4); the search runs ahead on the GPU and hands over "
-                        "symbol words (SURVEY 8f N3); sqz_decompress is host only"}
+                "host_threads": 2,
+                "note": "sqz_compress(host in, host bitstream out): the serial adaptive-Huffman model bounds it "
+                        "(SURVEY 7 H4) -- it runs on one host thread, a second one packs the bits; the search "
+                        "runs ahead on the GPU and hands over symbol words (SURVEY 8f N3); sqz_decompress is "
+                        "host only, one thread"}
     except Exception as e:
         comp = {"value": None, "error": repr(e)}
 

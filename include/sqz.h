@@ -73,6 +73,7 @@ struct sqz_tree {
     uint16_t* plan;     /* per leaf 16 nodes (leaf to root) + their 16 comparators: one cache line */
     uint8_t*  steps;    /* per leaf: plan length; 0 = no plan yet, 255 = deeper than a plan */
     uint8_t*  bits;     /* code length; 0 = root or unseen leaf */
+    void*     watcher;  /* two-thread coder only: where the model thread logs code changes */
     uint16_t* lut;      /* decoder only: node reached by the next lut_bits bits of the stream */
     int32_t lut_bits;
     int32_t n;          /* leaves; nodes = 2n-1 */
@@ -99,6 +100,10 @@ struct sqz {
     uint64_t matches;
     double   search_seconds;            /* GPU search + parse + copies */
     double   entropy_seconds;           /* host adaptive-Huffman stage */
+    int32_t  coder_threads;             /* 0 = automatic (two threads for streams of 64 Ki tokens and more),
+                                           1 = one thread, 2 = two threads: the model on a thread of its own,
+                                           the caller's thread packs the bits (sqz_codec.c); same bytes either way */
+    int32_t  reserved;
     struct sqz_tree lit;
     struct sqz_tree pos;
     uint8_t len_index[sqz_max_len + 2]; /* len -> length bucket, squeeze.h:151-161 */

@@ -34,7 +34,7 @@ Bitstream._fields_ = [
 class Tree(C.Structure):
     _fields_ = [("freq", u64p), ("path", u64p), ("code", u64p),
                 ("up", C.POINTER(C.c_int16)), ("lo", C.POINTER(C.c_int16)), ("hi", C.POINTER(C.c_int16)),
-                ("plan", u16p), ("steps", u8p), ("bits", u8p), ("lut", u16p), ("lut_bits", C.c_int32),
+                ("plan", u16p), ("steps", u8p), ("bits", u8p), ("watcher", C.c_void_p), ("lut", u16p), ("lut_bits", C.c_int32),
                 ("n", C.c_int32), ("next", C.c_int32), ("depth", C.c_int32), ("complete", C.c_int32),
                 ("lazy", C.c_int32), ("lazy_start", C.c_int32), ("eager", C.c_int32)]
 
@@ -54,6 +54,7 @@ class State(C.Structure):
         ("error", C.c_int32), ("device", C.c_int32), ("bs", C.POINTER(Bitstream)),
         ("tokens", C.c_uint64), ("matches", C.c_uint64),
         ("search_seconds", C.c_double), ("entropy_seconds", C.c_double),
+        ("coder_threads", C.c_int32), ("reserved", C.c_int32),
         ("lit", Tree), ("pos", Tree),
         ("len_index", C.c_uint8 * 259),
         ("lit_store", _store(512)), ("pos_store", _store(32)),

@@ -94,7 +94,8 @@ def _capacity(nbytes: int) -> int:
     return nbytes * 10 + 4096
 
 
-def compress(data, win_bits: int = 15, file_mode: bool = False, stats: dict | None = None) -> bytes:
+def compress(data, win_bits: int = 15, file_mode: bool = False, stats: dict | None = None,
+             threads: int = 0) -> bytes:
     """squeeze.write_header + squeeze.compress: GPU search, host entropy stage."""
     L = _lib.load()
     d = _u8(data)
@@ -117,6 +118,7 @@ def compress(data, win_bits: int = 15, file_mode: bool = False, stats: dict | No
     _check(bs.error, "sqz_write_header")
     s = State()
     L.sqz_init(C.byref(s))
+    s.coder_threads = threads
     L.sqz_compress(C.byref(s), C.byref(bs), d.ctypes.data_as(u8p), d.size, 1 << win_bits)
     _check(s.error, "sqz_compress")
     if stats is not None:
@@ -125,7 +127,7 @@ def compress(data, win_bits: int = 15, file_mode: bool = False, stats: dict | No
     return out[: bs.bytes].tobytes()
 
 
-def _encode(entry: str, arr, nbytes: int, win_bits: int, file_mode: bool, lib=None) -> bytes:
+def _encode(entry: str, arr, nbytes: int, win_bits: int, file_mode: bool, lib=None, threads: int = 0) -> bytes:
     L = lib or _lib.load()
     t = np.ascontiguousarray(arr, dtype=np.uint32)
     out = np.empty(_capacity(nbytes) + 64, dtype=np.uint8)
@@ -146,6 +148,7 @@ def _encode(entry: str, arr, nbytes: int, win_bits: int, file_mode: bool, lib=No
     _check(bs.error, "sqz_write_header")
     s = State()
     L.sqz_init(C.byref(s))
+    s.coder_threads = threads
     getattr(L, entry)(C.byref(s), C.byref(bs), t.ctypes.data_as(u32p), t.size)
     _check(s.error, entry)
     return out[: bs.bytes].tobytes()
@@ -156,9 +159,11 @@ def encode_tokens(toks, nbytes: int, win_bits: int = 15, file_mode: bool = False
     return _encode("sqz_encode_tokens", toks, nbytes, win_bits, file_mode, lib)
 
 
-def encode_symbols(words, nbytes: int, win_bits: int = 15, file_mode: bool = False, lib=None) -> bytes:
-    """The same on symbol words (include/sqz_gpu.h), the form the GPU parse emits for the coder."""
-    return _encode("sqz_encode_symbols", words, nbytes, win_bits, file_mode, lib)
+def encode_symbols(words, nbytes: int, win_bits: int = 15, file_mode: bool = False, lib=None,
+                   threads: int = 0) -> bytes:
+    """The same on symbol words (include/sqz_gpu.h), the form the GPU parse emits for the coder.
+    threads: 0 = automatic, 1 = one thread, 2 = model and bit packing on two threads (same bytes)."""
+    return _encode("sqz_encode_symbols", words, nbytes, win_bits, file_mode, lib, threads)
 
 
 def symbols_of_tokens(toks) -> np.ndarray:

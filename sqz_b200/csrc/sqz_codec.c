@@ -11,6 +11,10 @@
 #include "sqz_gpu.h"
 
 #include <errno.h>
+#include <pthread.h>
+#include <sched.h>
+#include <stdatomic.h>
+#include <stdlib.h>
 #include <string.h>
 #include <time.h>
 
@@ -161,6 +165,8 @@ static inline uint64_t get_bits(struct sqz_bitstream* bs, int count) {
 enum { none = -1, no_node = 0xFFFF,
        lit_lut_bits = 10, pos_lut_bits = 6 };   /* sizes of sqz.h's lit_lut / pos_lut */
 
+static void note_change(struct sqz_tree* t, int32_t leaf);
+
 static inline int32_t tree_root(const struct sqz_tree* t) { return 2 * t->n - 2; }
 static inline uint32_t always_node(const struct sqz_tree* t) { return 2 * (uint32_t)t->n - 1; } /* weight 0 */
 static inline uint32_t never_node(const struct sqz_tree* t) { return 2 * (uint32_t)t->n; }       /* weight 2^63-1 */
@@ -170,7 +176,7 @@ static inline uint32_t spare_node(const struct sqz_tree* t, int k) { return 2 * 
     (t)->freq = (store).freq; (t)->path = (store).path; (t)->code = (store).code; \
     (t)->up = (store).up; (t)->lo = (store).lo; (t)->hi = (store).hi;             \
     (t)->plan = &(store).plan[0][0]; (t)->steps = (store).steps;                  \
-    (t)->bits = (store).bits; (t)->n = (leaves); (t)->lut = NULL;                 \
+    (t)->bits = (store).bits; (t)->n = (leaves); (t)->lut = NULL; (t)->watcher = NULL; \
     (t)->lut_bits = (leaves) == sqz_lit_symbols ? lit_lut_bits : pos_lut_bits; } while (0)
 
 static void tree_init(struct sqz_tree* t) {
@@ -206,7 +212,10 @@ static void relabel(struct sqz_tree* t, int32_t top) {
         if (lo >= 0) { t->bits[lo] = (uint8_t)(bits + 1); t->path[lo] = path; stack[sp++] = (int16_t)lo; }
         if (hi >= 0) { t->bits[hi] = (uint8_t)(bits + 1); t->path[hi] = path | ((uint64_t)1 << bits); stack[sp++] = (int16_t)hi; }
         if (i < t->n) {
-            if (bits > 0) { t->code[i] = reverse64(path) >> (64 - bits); }
+            if (bits > 0) {
+                t->code[i] = reverse64(path) >> (64 - bits);
+                if (t->watcher != NULL) { note_change(t, i); }      /* two-thread coder: tell the emitter */
+            }
             t->steps[i] = 0;            /* the shape above this leaf changed: its plan is void */
         }
         /* decoder only: every lut_bits-bit look-ahead that starts with this node's code leads here */
@@ -809,6 +818,260 @@ static void code_tokens(struct sqz* s, const uint32_t* tokens, uint64_t count) {
     }
 }
 
+/* ======================================================================== *
+ *  the coder on two threads                                                 *
+ *  What is serial about the adaptive coder is the model: every symbol       *
+ *  changes the weights the next one is judged by.  Turning a symbol into    *
+ *  bits only needs the code table, and that changes about once per 2700     *
+ *  symbols.  So the model runs ahead on a thread of its own (walks, exact   *
+ *  reorderings, insertions -- no output) and notes every change of a code   *
+ *  in a log, stamped with the index of the first token it applies to; the   *
+ *  calling thread follows, keeps its own copy of both code tables current   *
+ *  from the log and packs the bits.  Same bytes as code_symbols, by         *
+ *  construction: token k is emitted with the codes as they were when the    *
+ *  model reached token k.                                                   *
+ * ======================================================================== */
+
+struct change { uint64_t at; uint64_t code; uint16_t leaf; uint8_t tree; uint8_t bits; };
+
+enum { log_size = 1 << 16, publish_every = 256, duo_least = 1 << 16 };
+
+struct duo {                            /* one cache line per writer: the two threads never share a dirty line */
+    struct sqz* s;
+    /* written by the emitter, read by the model */
+    _Alignas(64) const uint32_t* words; /* the current chunk */
+    uint64_t count;
+    uint64_t base;                      /* index of its first token in the whole stream */
+    _Atomic uint64_t chunks;            /* chunks handed over so far */
+    _Atomic int finish;                 /* no more chunks */
+    _Alignas(64) _Atomic uint64_t log_head;   /* changes consumed */
+    /* written by the model (every 256 tokens), read by the emitter */
+    _Alignas(64) _Atomic uint64_t modelled;   /* tokens of the current chunk the model is done with */
+    _Atomic uint64_t log_tail;          /* changes written */
+    int model_error;
+    /* either side gives up (written once) */
+    _Alignas(64) _Atomic int stop;
+    /* model thread only (written for every token) */
+    _Alignas(64) uint64_t now;          /* stamp for changes: index of the token being modelled + 1 */
+    uint64_t k_now;                     /* its index within the chunk */
+    uint64_t model_base;
+    /* emitter only: the code tables as of the token being emitted */
+    _Alignas(64)
+    uint64_t lit_code[sqz_lit_symbols], pos_code[sqz_pos_symbols];
+    uint8_t lit_bits[sqz_lit_symbols], pos_bits[sqz_pos_symbols];
+    struct change log[log_size];
+};
+
+static inline void spin_wait(unsigned* spins) {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+    if (++*spins > 2000) { sched_yield(); *spins = 0; }
+}
+
+static void note_change(struct sqz_tree* t, int32_t leaf) {
+    struct duo* d = (struct duo*)t->watcher;
+    const uint64_t tail = atomic_load_explicit(&d->log_tail, memory_order_relaxed);
+    unsigned spins = 0;
+    while (tail - atomic_load_explicit(&d->log_head, memory_order_acquire) >= log_size) {
+        /* the emitter can only drain what belongs to tokens it may emit: let it come up to this one */
+        atomic_store_explicit(&d->modelled, d->k_now, memory_order_release);
+        if (atomic_load_explicit(&d->stop, memory_order_relaxed)) { return; }
+        spin_wait(&spins);
+    }
+    struct change* c = &d->log[tail & (log_size - 1)];
+    c->at = d->now;
+    c->code = t->code[leaf];
+    c->leaf = (uint16_t)leaf;
+    c->tree = t->n == sqz_lit_symbols ? 0 : 1;
+    c->bits = t->bits[leaf];
+    atomic_store_explicit(&d->log_tail, tail + 1, memory_order_release);
+}
+
+static inline int word_is_valid(uint32_t w) {
+    const uint32_t sym = w & 0x1FF;
+    return sym <= 0xFF || (sym >= len_symbol0 && sym <= len_symbol0 + 27 && ((w >> 14) & 31) <= 29);
+}
+
+static void* model_main(void* arg) {
+    struct duo* d = (struct duo*)arg;
+    struct sqz_tree* const lit = &d->s->lit;
+    struct sqz_tree* const pos = &d->s->pos;
+    uint64_t seen = 0;
+    unsigned spins = 0;
+    for (;;) {
+        while (atomic_load_explicit(&d->chunks, memory_order_acquire) == seen) {
+            if (atomic_load_explicit(&d->finish, memory_order_acquire) ||
+                atomic_load_explicit(&d->stop, memory_order_relaxed)) { return NULL; }
+            spin_wait(&spins);
+        }
+        seen++;
+        const uint32_t* const words = d->words;
+        const uint64_t count = d->count;
+        d->model_base = d->base;
+        for (uint64_t k = 0; k < count; k++) {
+            if ((k & (publish_every - 1)) == 0) {
+                atomic_store_explicit(&d->modelled, k, memory_order_release);
+                if (atomic_load_explicit(&d->stop, memory_order_relaxed)) { return NULL; }
+            }
+            const uint32_t w = words[k];
+            const uint32_t sym = w & 0x1FF;
+            d->k_now = k;
+            d->now = d->model_base + k + 1;
+            if (!word_is_valid(w)) {                 /* the emitter reports it when it gets there */
+                atomic_store_explicit(&d->modelled, k + 1, memory_order_release);
+                return NULL;
+            }
+            if (lit->bits[sym] == 0) {               /* squeeze.h:278-288: escape, then the new symbol */
+                tree_count(lit, sqz_lit_nyt);
+                if (!tree_insert(lit, (int32_t)sym)) { d->model_error = E2BIG; }
+            } else {
+                tree_count_as(lit, (int32_t)sym, lit_plan);
+            }
+            if (sym >= len_symbol0) {
+                const uint32_t pb = (w >> 14) & 31;
+                if (pos->bits[pb] == 0) {
+                    tree_count(pos, sqz_pos_nyt);
+                    if (!tree_insert(pos, (int32_t)pb)) { d->model_error = E2BIG; }
+                } else {
+                    tree_count_as(pos, (int32_t)pb, pos_plan);
+                }
+            }
+            if (d->model_error != 0) {
+                atomic_store_explicit(&d->stop, 1, memory_order_release);
+                return NULL;
+            }
+        }
+        atomic_store_explicit(&d->modelled, count, memory_order_release);
+    }
+}
+
+/* the emitter's half of one chunk */
+static void duo_emit(struct sqz* s, struct duo* d, const uint32_t* words, uint64_t count) {
+    struct sqz_bitstream* const bs = s->bs;
+    uint64_t acc = bs->b64;
+    uint32_t fill = (uint32_t)bs->bits;
+    uint64_t matches = 0;
+    uint64_t head = atomic_load_explicit(&d->log_head, memory_order_relaxed);
+    uint64_t tail = atomic_load_explicit(&d->log_tail, memory_order_acquire);
+    uint64_t avail = 0;
+    unsigned spins = 0;
+    const uint64_t base = d->base;
+    d->words = words;
+    d->count = count;
+    atomic_store_explicit(&d->modelled, 0, memory_order_relaxed);
+    atomic_fetch_add_explicit(&d->chunks, 1, memory_order_release);
+
+#define DUO_APPEND(seq_, count_) do {                                            \
+        const uint64_t q_ = (seq_); const uint32_t c_ = (count_);                \
+        const uint32_t f_ = fill + c_;                                           \
+        if (f_ < 64) { acc = (acc << c_) | q_; fill = f_; }                      \
+        else {                                                                   \
+            const uint32_t rest_ = f_ - 64;                                      \
+            const uint64_t word_ = (fill == 0 ? 0 : acc << (64 - fill)) | (q_ >> rest_); \
+            if (bs->data != NULL && bs->capacity - bs->bytes >= 8 && bs->capacity >= bs->bytes) { \
+                const uint64_t be_ = __builtin_bswap64(word_);                   \
+                memcpy(bs->data + bs->bytes, &be_, 8);                           \
+                bs->bytes += 8;                                                  \
+            } else {                                                             \
+                bs->b64 = word_; bs->bits = 64;                                  \
+                word_out(bs);                                                    \
+                if (bs->error != 0) { s->error = bs->error; goto done; }         \
+            }                                                                    \
+            acc = rest_ == 0 ? 0 : (q_ & (((uint64_t)1 << rest_) - 1));          \
+            fill = rest_;                                                        \
+        } } while (0)
+
+    for (uint64_t k = 0; k < count; k++) {
+        if (k >= avail) {                            /* wait for the model to be past this token */
+            for (;;) {
+                avail = atomic_load_explicit(&d->modelled, memory_order_acquire);
+                if (avail > k) { break; }
+                if (atomic_load_explicit(&d->stop, memory_order_acquire)) {
+                    s->error = d->model_error != 0 ? d->model_error : EIO;
+                    goto done;
+                }
+                /* the model may be waiting for room in the log: hand back what has been applied */
+                atomic_store_explicit(&d->log_head, head, memory_order_release);
+                spin_wait(&spins);
+            }
+            tail = atomic_load_explicit(&d->log_tail, memory_order_acquire);
+        }
+        /* code changes made by tokens before this one */
+        const uint64_t stamp = base + k;
+        while (head != tail && d->log[head & (log_size - 1)].at <= stamp) {
+            const struct change* c = &d->log[head & (log_size - 1)];
+            if (c->tree == 0) { d->lit_code[c->leaf] = c->code; d->lit_bits[c->leaf] = c->bits; }
+            else              { d->pos_code[c->leaf] = c->code; d->pos_bits[c->leaf] = c->bits; }
+            head++;
+            if ((head & 1023) == 0) { atomic_store_explicit(&d->log_head, head, memory_order_release); }
+        }
+        const uint32_t w = words[k];
+        const uint32_t sym = w & 0x1FF;
+        if (!word_is_valid(w)) { s->error = EINVAL; goto done; }
+        if (d->lit_bits[sym] == 0) {                 /* first occurrence: escape, then 9 raw bits */
+            DUO_APPEND(d->lit_code[sqz_lit_nyt], d->lit_bits[sqz_lit_nyt]);
+            DUO_APPEND(reverse_field(sym, 9), 9);
+        } else {
+            DUO_APPEND(d->lit_code[sym], d->lit_bits[sym]);
+        }
+        if (sym >= len_symbol0) {                    /* length first, then distance: squeeze.h:379-380 */
+            const uint32_t pb = (w >> 14) & 31;
+            DUO_APPEND((w >> 9) & 31, len_extra[sym - len_symbol0]);
+            if (d->pos_bits[pb] == 0) {
+                DUO_APPEND(d->pos_code[sqz_pos_nyt], d->pos_bits[sqz_pos_nyt]);
+                DUO_APPEND(reverse_field(pb, 5), 5);
+            } else {
+                DUO_APPEND(d->pos_code[pb], d->pos_bits[pb]);
+            }
+            DUO_APPEND(w >> 19, pos_extra[pb]);
+            matches++;
+        }
+    }
+done:
+    atomic_store_explicit(&d->log_head, head, memory_order_release);
+    if (s->error != 0) { atomic_store_explicit(&d->stop, 1, memory_order_release); }
+    bs->b64 = acc;
+    bs->bits = (int32_t)fill;
+    d->base = base + count;
+    s->matches += matches;
+    s->tokens += count;
+#undef DUO_APPEND
+}
+
+struct duo_run { struct duo* d; pthread_t model; };
+
+/* after coder_begin: start the model thread; NULL (and no error) when two threads are not wanted */
+static int duo_start(struct sqz* s, struct duo_run* run, uint64_t expected_tokens) {
+    run->d = NULL;
+    if (s->coder_threads == 1 || (s->coder_threads == 0 && expected_tokens < duo_least)) { return 0; }
+    struct duo* d = (struct duo*)calloc(1, sizeof(struct duo));
+    if (d == NULL) { return 0; }                    /* no memory for the log: one thread will do */
+    d->s = s;
+    memcpy(d->lit_code, s->lit.code, sizeof(d->lit_code));
+    memcpy(d->pos_code, s->pos.code, sizeof(d->pos_code));
+    memcpy(d->lit_bits, s->lit.bits, sizeof(d->lit_bits));
+    memcpy(d->pos_bits, s->pos.bits, sizeof(d->pos_bits));
+    s->lit.watcher = d;
+    s->pos.watcher = d;
+    if (pthread_create(&run->model, NULL, model_main, d) != 0) {
+        s->lit.watcher = s->pos.watcher = NULL;
+        free(d);
+        return 0;
+    }
+    run->d = d;
+    return 1;
+}
+
+static void duo_finish(struct sqz* s, struct duo_run* run) {
+    if (run->d == NULL) { return; }
+    atomic_store_explicit(&run->d->finish, 1, memory_order_release);
+    pthread_join(run->model, NULL);
+    s->lit.watcher = s->pos.watcher = NULL;
+    free(run->d);
+    run->d = NULL;
+}
+
 void sqz_write_header(struct sqz_bitstream* bs, uint64_t bytes, uint8_t win_bits) {
     if (win_bits < sqz_min_win_bits || win_bits > sqz_max_win_bits) {
         bs->error = EINVAL;
@@ -848,7 +1111,13 @@ void sqz_encode_symbols(struct sqz* s, struct sqz_bitstream* bs,
                         const uint32_t* words, uint64_t count) {
     coder_begin(s, bs);
     double t0 = now_seconds();
-    code_symbols(s, words, count);
+    struct duo_run run;
+    if (s->error == 0 && duo_start(s, &run, count)) {
+        duo_emit(s, run.d, words, count);
+        duo_finish(s, &run);
+    } else {
+        code_symbols(s, words, count);
+    }
     if (s->error == 0) { pad_to_word(bs); s->error = bs->error; }
     s->entropy_seconds += now_seconds() - t0;
 }
@@ -870,6 +1139,8 @@ void sqz_compress(struct sqz* s, struct sqz_bitstream* bs,
                                 sqz_min_len, sqz_max_len, window - 1, 0, SQZ_GPU_STREAM_SYMBOLS);
     t_search += now_seconds() - t0;
     if (r != 0) { s->error = r; return; }
+    struct duo_run run;
+    const int two = duo_start(s, &run, bytes / 2);     /* about 0.6 tokens per byte on mixed data */
     for (;;) {
         const uint32_t* words = NULL;
         size_t count = 0;
@@ -879,10 +1150,11 @@ void sqz_compress(struct sqz* s, struct sqz_bitstream* bs,
         if (r != 0) { s->error = r; break; }
         if (count == 0) { break; }
         t0 = now_seconds();
-        code_symbols(s, words, count);
+        if (two) { duo_emit(s, run.d, words, count); } else { code_symbols(s, words, count); }
         t_code += now_seconds() - t0;
         if (s->error != 0) { break; }
     }
+    duo_finish(s, &run);
     sqz_gpu_stream_close(st);
     if (s->error == 0) { pad_to_word(bs); s->error = bs->error; }
     s->search_seconds = t_search;

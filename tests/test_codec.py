@@ -226,6 +226,40 @@ def test_random_streams_keep_the_self_check_quiet(seed, selfcheck_lib, reference
     assert out[:nbytes].tobytes() == reference.decompress(ours)
 
 
+@pytest.mark.parametrize("seed", range(30))
+def test_two_thread_coder_gives_the_same_bytes(seed, reference):
+    """coder_threads = 2: the model runs ahead on its own thread and logs code changes, the caller's
+    thread packs the bits.  Forced here on streams of every size (the automatic choice starts at 64 Ki
+    tokens); callback sinks too."""
+    toks, nbytes = _random_stream(np.random.default_rng(3000 + seed))
+    words = sq.symbols_of_tokens(toks)
+    one = sq.encode_symbols(words, nbytes, 15, threads=1)
+    two = sq.encode_symbols(words, nbytes, 15, threads=2)
+    assert one == two == reference.encode_tokens(toks, nbytes, 15)
+    if seed % 5 == 0:
+        assert sq.encode_symbols(words, nbytes, 15, file_mode=True, threads=2) == \
+            sq.encode_symbols(words, nbytes, 15, file_mode=True, threads=1)
+
+
+def test_two_thread_coder_errors():
+    """A full sink and a word that is no symbol word stop both threads cleanly."""
+    words = sq.symbols_of_tokens(np.random.default_rng(5).integers(0, 256, 200000).astype(np.uint32))
+    L = _lib.load()
+    buf = np.zeros(4096, np.uint8)
+    bs = _bs(buf)
+    L.sqz_write_header(C.byref(bs), 200000, 15)
+    s = _lib.State()
+    L.sqz_init(C.byref(s))
+    s.coder_threads = 2
+    L.sqz_encode_symbols(C.byref(s), C.byref(bs), words.ctypes.data_as(_lib.u32p), words.size)
+    assert s.error == errno.E2BIG
+    bad = words.copy()
+    bad[150000] = 256
+    with pytest.raises(sq.SqzError) as e:
+        sq.encode_symbols(bad, 200000, 15, threads=2)
+    assert e.value.errno == errno.EINVAL
+
+
 def test_header_bytes():
     """LSB-first fields in an MSB-first register, big-endian words."""
     c = sq.encode_tokens(np.zeros(0, np.uint32), 4096, 15)
