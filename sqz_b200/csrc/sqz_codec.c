@@ -1045,8 +1045,9 @@ struct duo_run { struct duo* d; pthread_t model; };
 static int duo_start(struct sqz* s, struct duo_run* run, uint64_t expected_tokens) {
     run->d = NULL;
     if (s->coder_threads == 1 || (s->coder_threads == 0 && expected_tokens < duo_least)) { return 0; }
-    struct duo* d = (struct duo*)calloc(1, sizeof(struct duo));
+    struct duo* d = (struct duo*)aligned_alloc(64, (sizeof(struct duo) + 63) & ~(size_t)63);
     if (d == NULL) { return 0; }                    /* no memory for the log: one thread will do */
+    memset(d, 0, sizeof(struct duo));
     d->s = s;
     memcpy(d->lit_code, s->lit.code, sizeof(d->lit_code));
     memcpy(d->pos_code, s->pos.code, sizeof(d->pos_code));
