@@ -834,7 +834,10 @@ static void code_tokens(struct sqz* s, const uint32_t* tokens, uint64_t count) {
 
 struct change { uint64_t at; uint64_t code; uint16_t leaf; uint8_t tree; uint8_t bits; };
 
-enum { log_size = 1 << 16, publish_every = 256, duo_least = 1 << 16 };
+#ifndef SQZ_LOG_SIZE
+#define SQZ_LOG_SIZE (1 << 16)        /* a power of two; tests build with a tiny one */
+#endif
+enum { log_size = SQZ_LOG_SIZE, publish_every = 256, duo_least = 1 << 16 };
 
 struct duo {                            /* one cache line per writer: the two threads never share a dirty line */
     struct sqz* s;
@@ -855,8 +858,11 @@ struct duo {                            /* one cache line per writer: the two th
     _Alignas(64) uint64_t now;          /* stamp for changes: index of the token being modelled + 1 */
     uint64_t k_now;                     /* its index within the chunk */
     uint64_t model_base;
-    /* emitter only: the code tables as of the token being emitted */
-    _Alignas(64)
+    /* emitter only: changes taken out of the log before they were due (so that the model never waits
+     * for room while the emitter waits for the model), and the code tables as of the token being emitted */
+    _Alignas(64) struct change* early;
+    size_t early_count, early_room, early_next;
+
     uint64_t lit_code[sqz_lit_symbols], pos_code[sqz_pos_symbols];
     uint8_t lit_bits[sqz_lit_symbols], pos_bits[sqz_pos_symbols];
     struct change log[log_size];
@@ -874,7 +880,7 @@ static void note_change(struct sqz_tree* t, int32_t leaf) {
     const uint64_t tail = atomic_load_explicit(&d->log_tail, memory_order_relaxed);
     unsigned spins = 0;
     while (tail - atomic_load_explicit(&d->log_head, memory_order_acquire) >= log_size) {
-        /* the emitter can only drain what belongs to tokens it may emit: let it come up to this one */
+        /* let the emitter come up to this token; once it waits for the model it empties the log */
         atomic_store_explicit(&d->modelled, d->k_now, memory_order_release);
         if (atomic_load_explicit(&d->stop, memory_order_relaxed)) { return; }
         spin_wait(&spins);
@@ -991,15 +997,33 @@ static void duo_emit(struct sqz* s, struct duo* d, const uint32_t* words, uint64
                     s->error = d->model_error != 0 ? d->model_error : EIO;
                     goto done;
                 }
-                /* the model may be waiting for room in the log: hand back what has been applied */
-                atomic_store_explicit(&d->log_head, head, memory_order_release);
+                /* The model may be waiting for room in the log.  Nothing in there is due yet (this token
+                 * has not been modelled), so set it aside: the log empties and the model goes on. */
+                tail = atomic_load_explicit(&d->log_tail, memory_order_acquire);
+                if (head != tail) {
+                    if (d->early_next == d->early_count) { d->early_next = d->early_count = 0; }
+                    if (d->early_count + (tail - head) > d->early_room) {
+                        const size_t room = 2 * (d->early_count + (size_t)(tail - head)) + 1024;
+                        struct change* grown = (struct change*)realloc(d->early, room * sizeof(struct change));
+                        if (grown == NULL) { s->error = ENOMEM; goto done; }
+                        d->early = grown;
+                        d->early_room = room;
+                    }
+                    while (head != tail) { d->early[d->early_count++] = d->log[head++ & (log_size - 1)]; }
+                }
+                atomic_store_explicit(&d->log_head, head, memory_order_release);   /* everything is taken */
                 spin_wait(&spins);
             }
             tail = atomic_load_explicit(&d->log_tail, memory_order_acquire);
         }
-        /* code changes made by tokens before this one */
+        /* code changes made by tokens before this one: those set aside first, they are older */
         const uint64_t stamp = base + k;
-        while (head != tail && d->log[head & (log_size - 1)].at <= stamp) {
+        while (d->early_next != d->early_count && d->early[d->early_next].at <= stamp) {
+            const struct change* c = &d->early[d->early_next++];
+            if (c->tree == 0) { d->lit_code[c->leaf] = c->code; d->lit_bits[c->leaf] = c->bits; }
+            else              { d->pos_code[c->leaf] = c->code; d->pos_bits[c->leaf] = c->bits; }
+        }
+        while (d->early_next == d->early_count && head != tail && d->log[head & (log_size - 1)].at <= stamp) {
             const struct change* c = &d->log[head & (log_size - 1)];
             if (c->tree == 0) { d->lit_code[c->leaf] = c->code; d->lit_bits[c->leaf] = c->bits; }
             else              { d->pos_code[c->leaf] = c->code; d->pos_bits[c->leaf] = c->bits; }
@@ -1069,6 +1093,7 @@ static void duo_finish(struct sqz* s, struct duo_run* run) {
     atomic_store_explicit(&run->d->finish, 1, memory_order_release);
     pthread_join(run->model, NULL);
     s->lit.watcher = s->pos.watcher = NULL;
+    free(run->d->early);
     free(run->d);
     run->d = NULL;
 }

@@ -87,12 +87,10 @@ def test_symbol_word_layout():
     assert (sq.symbols_of_tokens(bad) == 0xFFFFFFFF).all()
 
 
-@pytest.fixture(scope="module")
-def selfcheck_lib(tmp_path_factory):
-    """The codec alone, built with -DSQZ_SELFCHECK: after every coded symbol it verifies that every
-    leaf's cached plan equals a fresh one and that the tree is in the state the quick walk assumes."""
+def _codec_variant(tmp_path_factory, name, *flags):
+    """The codec alone (no GPU half) built with extra flags, as a ctypes library."""
     import subprocess
-    d = tmp_path_factory.mktemp("selfcheck")
+    d = tmp_path_factory.mktemp(name)
     stub = d / "stub.c"
     stub.write_text('#include "sqz_gpu.h"\n#include <errno.h>\n'
                     'int sqz_gpu_stream_open(sqz_gpu_stream** s, int dev, const uint8_t* p, size_t n, uint32_t w, '
@@ -101,15 +99,28 @@ def selfcheck_lib(tmp_path_factory):
                     'int sqz_gpu_stream_next(sqz_gpu_stream* s, const uint32_t** t, size_t* c) { (void)s; (void)t; (void)c; return ENODEV; }\n'
                     'void sqz_gpu_stream_close(sqz_gpu_stream* s) { (void)s; }\n'
                     'int sqz_gpu_expand_tokens(const uint32_t* t, size_t n, uint8_t* o, size_t b) { (void)t; (void)n; (void)o; (void)b; return ENODEV; }\n')
-    so = d / "libsqzcheck.so"
-    subprocess.check_call(["gcc", "-std=gnu11", "-O2", "-fPIC", "-shared", "-DSQZ_SELFCHECK",
+    so = d / ("lib%s.so" % name)
+    subprocess.check_call(["gcc", "-std=gnu11", "-O2", "-fPIC", "-shared", "-pthread", *flags,
                            "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "sqz_b200", "csrc", "sqz_codec.c"),
                            str(stub), "-o", str(so)])
     L = C.CDLL(str(so))
-    for name in ("sqz_write_header", "sqz_init", "sqz_encode_tokens", "sqz_encode_symbols", "sqz_decompress_buffer"):
-        fn = getattr(L, name)
-        fn.restype, fn.argtypes = _lib.SYMBOLS[name]
+    for fn_name in ("sqz_write_header", "sqz_init", "sqz_encode_tokens", "sqz_encode_symbols", "sqz_decompress_buffer"):
+        fn = getattr(L, fn_name)
+        fn.restype, fn.argtypes = _lib.SYMBOLS[fn_name]
     return L
+
+
+@pytest.fixture(scope="module")
+def selfcheck_lib(tmp_path_factory):
+    """Built with -DSQZ_SELFCHECK: after every coded symbol it verifies that every leaf's cached plan
+    equals a fresh one and that the tree is in the state the quick walk assumes."""
+    return _codec_variant(tmp_path_factory, "sqzcheck", "-DSQZ_SELFCHECK")
+
+
+@pytest.fixture(scope="module")
+def tiny_log_lib(tmp_path_factory):
+    """Built with a 64-entry change log: the two-thread coder's hand-off runs full all the time."""
+    return _codec_variant(tmp_path_factory, "sqztinylog", "-DSQZ_LOG_SIZE=64")
 
 
 def _skewed(n, seed):
@@ -239,6 +250,15 @@ def test_two_thread_coder_gives_the_same_bytes(seed, reference):
     if seed % 5 == 0:
         assert sq.encode_symbols(words, nbytes, 15, file_mode=True, threads=2) == \
             sq.encode_symbols(words, nbytes, 15, file_mode=True, threads=1)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_two_thread_coder_with_a_full_log(seed, tiny_log_lib, reference):
+    """A 64-entry log is full after one reordering: the model has to wait for room, the emitter has to
+    set changes aside that are not due yet -- and neither may wait for the other forever."""
+    toks, nbytes = _random_stream(np.random.default_rng(4000 + seed))
+    words = sq.symbols_of_tokens(toks)
+    assert sq.encode_symbols(words, nbytes, 15, threads=2, lib=tiny_log_lib) == reference.encode_tokens(toks, nbytes, 15)
 
 
 def test_two_thread_coder_errors():
