@@ -823,16 +823,17 @@ static void code_tokens(struct sqz* s, const uint32_t* tokens, uint64_t count) {
  *  What is serial about the adaptive coder is the model: every symbol       *
  *  changes the weights the next one is judged by.  Turning a symbol into    *
  *  bits only needs the code table, and that changes about once per 2700     *
- *  symbols.  So the model runs ahead on a thread of its own (walks, exact   *
- *  reorderings, insertions -- no output) and notes every change of a code   *
- *  in a log, stamped with the index of the first token it applies to; the   *
- *  calling thread follows, keeps its own copy of both code tables current   *
- *  from the log and packs the bits.  Same bytes as code_symbols, by         *
+ *  symbols.  So the model of the literal/length tree runs ahead on a thread *
+ *  of its own (walks, exact reorderings, insertions -- no output) and notes *
+ *  every change of a code in a log, stamped with the index of the first     *
+ *  token it applies to; the calling thread follows, keeps its own copy of   *
+ *  that code table current from the log, packs the bits and models the      *
+ *  small distance tree itself.  Same bytes as code_symbols, by              *
  *  construction: token k is emitted with the codes as they were when the    *
  *  model reached token k.                                                   *
  * ======================================================================== */
 
-struct change { uint64_t at; uint64_t code; uint16_t leaf; uint8_t tree; uint8_t bits; };
+struct change { uint64_t at; uint64_t code; uint16_t leaf; uint8_t bits; };
 
 #ifndef SQZ_LOG_SIZE
 #define SQZ_LOG_SIZE (1 << 16)        /* a power of two; tests build with a tiny one */
@@ -863,8 +864,8 @@ struct duo {                            /* one cache line per writer: the two th
     _Alignas(64) struct change* early;
     size_t early_count, early_room, early_next;
 
-    uint64_t lit_code[sqz_lit_symbols], pos_code[sqz_pos_symbols];
-    uint8_t lit_bits[sqz_lit_symbols], pos_bits[sqz_pos_symbols];
+    uint64_t lit_code[sqz_lit_symbols];
+    uint8_t lit_bits[sqz_lit_symbols];
     struct change log[log_size];
 };
 
@@ -889,7 +890,6 @@ static void note_change(struct sqz_tree* t, int32_t leaf) {
     c->at = d->now;
     c->code = t->code[leaf];
     c->leaf = (uint16_t)leaf;
-    c->tree = t->n == sqz_lit_symbols ? 0 : 1;
     c->bits = t->bits[leaf];
     atomic_store_explicit(&d->log_tail, tail + 1, memory_order_release);
 }
@@ -901,8 +901,7 @@ static inline int word_is_valid(uint32_t w) {
 
 static void* model_main(void* arg) {
     struct duo* d = (struct duo*)arg;
-    struct sqz_tree* const lit = &d->s->lit;
-    struct sqz_tree* const pos = &d->s->pos;
+    struct sqz_tree* const lit = &d->s->lit;      /* the distance tree belongs to the emitting thread */
     uint64_t seen = 0;
     unsigned spins = 0;
     for (;;) {
@@ -934,15 +933,6 @@ static void* model_main(void* arg) {
             } else {
                 tree_count_as(lit, (int32_t)sym, lit_plan);
             }
-            if (sym >= len_symbol0) {
-                const uint32_t pb = (w >> 14) & 31;
-                if (pos->bits[pb] == 0) {
-                    tree_count(pos, sqz_pos_nyt);
-                    if (!tree_insert(pos, (int32_t)pb)) { d->model_error = E2BIG; }
-                } else {
-                    tree_count_as(pos, (int32_t)pb, pos_plan);
-                }
-            }
             if (d->model_error != 0) {
                 atomic_store_explicit(&d->stop, 1, memory_order_release);
                 return NULL;
@@ -955,6 +945,7 @@ static void* model_main(void* arg) {
 /* the emitter's half of one chunk */
 static void duo_emit(struct sqz* s, struct duo* d, const uint32_t* words, uint64_t count) {
     struct sqz_bitstream* const bs = s->bs;
+    struct sqz_tree* const pos = &s->pos;           /* small and touched by every sixth token: modelled here */
     uint64_t acc = bs->b64;
     uint32_t fill = (uint32_t)bs->bits;
     uint64_t matches = 0;
@@ -1020,13 +1011,13 @@ static void duo_emit(struct sqz* s, struct duo* d, const uint32_t* words, uint64
         const uint64_t stamp = base + k;
         while (d->early_next != d->early_count && d->early[d->early_next].at <= stamp) {
             const struct change* c = &d->early[d->early_next++];
-            if (c->tree == 0) { d->lit_code[c->leaf] = c->code; d->lit_bits[c->leaf] = c->bits; }
-            else              { d->pos_code[c->leaf] = c->code; d->pos_bits[c->leaf] = c->bits; }
+            d->lit_code[c->leaf] = c->code;
+            d->lit_bits[c->leaf] = c->bits;
         }
         while (d->early_next == d->early_count && head != tail && d->log[head & (log_size - 1)].at <= stamp) {
             const struct change* c = &d->log[head & (log_size - 1)];
-            if (c->tree == 0) { d->lit_code[c->leaf] = c->code; d->lit_bits[c->leaf] = c->bits; }
-            else              { d->pos_code[c->leaf] = c->code; d->pos_bits[c->leaf] = c->bits; }
+            d->lit_code[c->leaf] = c->code;
+            d->lit_bits[c->leaf] = c->bits;
             head++;
             if ((head & 1023) == 0) { atomic_store_explicit(&d->log_head, head, memory_order_release); }
         }
@@ -1042,11 +1033,14 @@ static void duo_emit(struct sqz* s, struct duo* d, const uint32_t* words, uint64
         if (sym >= len_symbol0) {                    /* length first, then distance: squeeze.h:379-380 */
             const uint32_t pb = (w >> 14) & 31;
             DUO_APPEND((w >> 9) & 31, len_extra[sym - len_symbol0]);
-            if (d->pos_bits[pb] == 0) {
-                DUO_APPEND(d->pos_code[sqz_pos_nyt], d->pos_bits[sqz_pos_nyt]);
+            if (pos->bits[pb] == 0) {                /* squeeze.h:300-315: escape, 5 raw bits, new symbol */
+                DUO_APPEND(pos->code[sqz_pos_nyt], pos->bits[sqz_pos_nyt]);
+                tree_count(pos, sqz_pos_nyt);
                 DUO_APPEND(reverse_field(pb, 5), 5);
+                if (!tree_insert(pos, (int32_t)pb)) { s->error = E2BIG; goto done; }
             } else {
-                DUO_APPEND(d->pos_code[pb], d->pos_bits[pb]);
+                DUO_APPEND(pos->code[pb], pos->bits[pb]);
+                tree_count_as(pos, (int32_t)pb, pos_plan);
             }
             DUO_APPEND(w >> 19, pos_extra[pb]);
             matches++;
@@ -1074,13 +1068,10 @@ static int duo_start(struct sqz* s, struct duo_run* run, uint64_t expected_token
     memset(d, 0, sizeof(struct duo));
     d->s = s;
     memcpy(d->lit_code, s->lit.code, sizeof(d->lit_code));
-    memcpy(d->pos_code, s->pos.code, sizeof(d->pos_code));
     memcpy(d->lit_bits, s->lit.bits, sizeof(d->lit_bits));
-    memcpy(d->pos_bits, s->pos.bits, sizeof(d->pos_bits));
     s->lit.watcher = d;
-    s->pos.watcher = d;
     if (pthread_create(&run->model, NULL, model_main, d) != 0) {
-        s->lit.watcher = s->pos.watcher = NULL;
+        s->lit.watcher = NULL;
         free(d);
         return 0;
     }
@@ -1092,7 +1083,7 @@ static void duo_finish(struct sqz* s, struct duo_run* run) {
     if (run->d == NULL) { return; }
     atomic_store_explicit(&run->d->finish, 1, memory_order_release);
     pthread_join(run->model, NULL);
-    s->lit.watcher = s->pos.watcher = NULL;
+    s->lit.watcher = NULL;
     free(run->d->early);
     free(run->d);
     run->d = NULL;
