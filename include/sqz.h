@@ -139,6 +139,10 @@ void sqz_encode_tokens(struct sqz* s, struct sqz_bitstream* bs,
  * out of range sets s->error = EINVAL; extra-bit fields are taken as they are. */
 void sqz_encode_symbols(struct sqz* s, struct sqz_bitstream* bs,
                         const uint32_t* words, uint64_t count);
+/* The same, handing the words to the coder `chunk` at a time -- the way
+ * sqz_compress receives them from the GPU stream (0 = all at once).         */
+void sqz_encode_symbols_chunked(struct sqz* s, struct sqz_bitstream* bs,
+                                const uint32_t* words, uint64_t count, uint64_t chunk);
 /* token -> symbol word on the host (0xFFFFFFFF for a token the decoder would
  * reject); the reference for what the GPU emits.                             */
 void sqz_symbols_of_tokens(const uint32_t* tokens, uint64_t count, uint32_t* words);

@@ -72,6 +72,7 @@ SYMBOLS = {
     "sqz_compress": (None, [C.POINTER(State), C.POINTER(Bitstream), u8p, C.c_uint64, C.c_uint32]),
     "sqz_encode_tokens": (None, [C.POINTER(State), C.POINTER(Bitstream), u32p, C.c_uint64]),
     "sqz_encode_symbols": (None, [C.POINTER(State), C.POINTER(Bitstream), u32p, C.c_uint64]),
+    "sqz_encode_symbols_chunked": (None, [C.POINTER(State), C.POINTER(Bitstream), u32p, C.c_uint64, C.c_uint64]),
     "sqz_symbols_of_tokens": (None, [u32p, C.c_uint64, u32p]),
     "sqz_decode_tokens": (None, [C.POINTER(State), C.POINTER(Bitstream), C.c_uint64, u32p, C.c_uint64, u64p]),
     "sqz_decompress_gpu": (None, [C.POINTER(State), C.POINTER(Bitstream), u8p, C.c_uint64]),

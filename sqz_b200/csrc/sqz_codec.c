@@ -1139,6 +1139,20 @@ void sqz_encode_symbols(struct sqz* s, struct sqz_bitstream* bs,
     s->entropy_seconds += now_seconds() - t0;
 }
 
+void sqz_encode_symbols_chunked(struct sqz* s, struct sqz_bitstream* bs,
+                                const uint32_t* words, uint64_t count, uint64_t chunk) {
+    coder_begin(s, bs);
+    struct duo_run run;
+    const int two = s->error == 0 && duo_start(s, &run, count);
+    if (chunk == 0) { chunk = count; }
+    for (uint64_t at = 0; at < count && s->error == 0; at += chunk) {
+        const uint64_t n = count - at < chunk ? count - at : chunk;
+        if (two) { duo_emit(s, run.d, words + at, n); } else { code_symbols(s, words + at, n); }
+    }
+    if (two) { duo_finish(s, &run); }
+    if (s->error == 0) { pad_to_word(bs); s->error = bs->error; }
+}
+
 void sqz_compress(struct sqz* s, struct sqz_bitstream* bs,
                   const uint8_t* data, uint64_t bytes, uint32_t window) {
     if (window < (1u << sqz_min_win_bits) || window > (1u << sqz_max_win_bits) ||

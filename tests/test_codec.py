@@ -261,6 +261,25 @@ def test_two_thread_coder_with_a_full_log(seed, tiny_log_lib, reference):
     assert sq.encode_symbols(words, nbytes, 15, threads=2, lib=tiny_log_lib) == reference.encode_tokens(toks, nbytes, 15)
 
 
+@pytest.mark.parametrize("threads", [1, 2])
+@pytest.mark.parametrize("chunk", [1, 255, 256, 257, 5000, 100000])
+def test_chunked_hand_over_like_sqz_compress(chunk, threads, oracle, reference, inputs):
+    """sqz_compress feeds the coder chunk by chunk from the GPU stream; here the same from a host array."""
+    d = inputs["arm64.elf"][:300000]
+    t = oracle_tokens(oracle, d, 15)
+    words = sq.symbols_of_tokens(t)
+    L = _lib.load()
+    out = np.zeros(d.size * 2 + 4096, np.uint8)
+    bs = _bs(out)
+    L.sqz_write_header(C.byref(bs), d.size, 15)
+    s = _lib.State()
+    L.sqz_init(C.byref(s))
+    s.coder_threads = threads
+    L.sqz_encode_symbols_chunked(C.byref(s), C.byref(bs), words.ctypes.data_as(_lib.u32p), words.size, chunk)
+    assert s.error == 0 and s.tokens == t.size
+    assert out[: bs.bytes].tobytes() == reference.encode_tokens(t, d.size, 15)
+
+
 def test_two_thread_coder_errors():
     """A full sink and a word that is no symbol word stop both threads cleanly."""
     words = sq.symbols_of_tokens(np.random.default_rng(5).integers(0, 256, 200000).astype(np.uint32))
