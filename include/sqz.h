@@ -105,8 +105,11 @@ struct sqz {
                                            the caller's thread packs the bits (sqz_codec.c); same bytes either way */
     int32_t  reserved;
     struct sqz_tree lit;
+    uint8_t len_index[sqz_max_len + 2]; /* len -> length bucket, squeeze.h:151-161.  Also keeps the two tree
+                                           headers on different cache lines: with two coder threads each
+                                           tree's counters are written by another thread for every token */
+    uint8_t apart[64];
     struct sqz_tree pos;
-    uint8_t len_index[sqz_max_len + 2]; /* len -> length bucket, squeeze.h:151-161 */
     SQZ_TREE_STORE(sqz_lit_symbols) lit_store;
     SQZ_TREE_STORE(sqz_pos_symbols) pos_store;
     uint16_t lit_lut[1 << 10];          /* decoder look-ahead tables (sqz_codec.c: lit_lut_bits, pos_lut_bits) */
