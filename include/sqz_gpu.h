@@ -5,8 +5,10 @@
  * (/root/reference/attic/map_experiment/squeeze.h:338-358) followed by the
  * greedy token dispatch (squeeze.h:377-394).  These entry points are what a
  * maintainer would call at exactly that place: plain
- * pointers and sizes, int errno return values, no global state visible to the
- * caller, callable from C99.
+ * pointers and sizes, int errno return values, callable from C99.  No call
+ * changes the calling thread's current CUDA device.  State that outlives a call
+ * is limited to recycled staging buffers (sqz_gpu_release frees them) and the
+ * measurement aids at the end of this file, which are off unless switched on.
  *
  * Rule parameters:
  *   window    the LZ window the stream header announces (power of two)
@@ -31,7 +33,8 @@
  * Extra bits are stored in emission order, i.e. bit-reversed within their field
  * width, because the bitstream takes values least significant bit first
  * (bitstream.h:49-63).  Symbol words exist only within the bitstream's own
- * limits: min_len >= 3, max_len <= 258, max_dist <= 32767.
+ * limits: min_len >= 3, max_len <= 257 (what the decoders accept, squeeze.h:529-545),
+ * max_dist <= 32767.
  *
  * Errors: 0, EINVAL (bad rule parameters), E2BIG (output capacity), ENOMEM,
  * ENODEV (no CUDA device / driver: there is NO CPU fallback), EIO (CUDA error;
@@ -47,7 +50,7 @@
 extern "C" {
 #endif
 
-#define SQZ_GPU_ABI_VERSION 2
+#define SQZ_GPU_ABI_VERSION 3
 
 enum {
     sqz_gpu_max_len_limit  = 512,     /* parse hand-off tables are sized for this */
@@ -75,6 +78,26 @@ int sqz_gpu_tokens(const uint8_t* data, size_t bytes,
                    uint32_t max_dist,
                    uint32_t* tokens_out, size_t tokens_cap, size_t* n_tokens);
 
+/* The same token stream computed on several devices at once (SURVEY.md section 8e;
+ * squeeze.h:345,377-394 is where the seam dependency comes from).  The input is cut
+ * into n_devices contiguous shards (sizes differ by at most one byte), each uploaded
+ * with a look-back halo of max_dist bytes and a look-ahead halo of max_len bytes, so
+ * the match tables are independent.  The parse depends on one number per seam -- where
+ * the previous shard's last token ends -- which every device prepares for as a 1 KiB
+ * exit map and the host chains with one lookup per seam.  The token arrays are then
+ * concatenated in shard order by copies sized by their counts: device -> host when
+ * tokens_out is host memory (pinned memory takes them by DMA from all devices at
+ * once), peer-to-peer over NVLink when tokens_out is device memory.  No collective
+ * library is involved.  The result is identical to sqz_gpu_tokens() for every
+ * n_devices.  A device may be listed more than once (its shards then share it).
+ * shard_tokens (optional, n_devices entries) receives the per-shard counts.       */
+int sqz_gpu_tokens_multi(const int* devices, int n_devices,
+                         const uint8_t* data, size_t bytes,
+                         uint32_t window, uint32_t min_len, uint32_t max_len,
+                         uint32_t max_dist,
+                         uint32_t* tokens_out, size_t tokens_cap, size_t* n_tokens,
+                         size_t* shard_tokens);
+
 /* Streaming form used by sqz_compress(): tokens arrive chunk by chunk, in
  * parse order, from double-buffered pinned memory while the device already
  * works on the next chunk.  *tokens stays valid until the next call.        */
@@ -95,7 +118,15 @@ void sqz_gpu_stream_close(sqz_gpu_stream* st);
  * max_len) is enough).  All pointers are device pointers on the current
  * device; `stream` is a cudaStream_t (NULL = default stream).  Asynchronous. */
 
-/* table[i] for the n positions of the shard, packed (len << 16) | dist.     */
+/* table[i] for the n positions of the shard, packed (len << 16) | dist.
+ * The kernels need sqz_gpu_match_workspace(n) bytes of scratch device memory (the
+ * work list the first kernel leaves for the second): the _ws form takes it from the
+ * caller, the plain form borrows it from a per-device pool of the library.   */
+size_t sqz_gpu_match_workspace(size_t n);
+int sqz_gpu_match_table_device_ws(const uint8_t* d_shard, size_t back, size_t n,
+                                  size_t ahead, uint32_t min_len, uint32_t max_len,
+                                  uint32_t max_dist, uint32_t* d_table, void* d_work,
+                                  void* stream);
 int sqz_gpu_match_table_device(const uint8_t* d_shard, size_t back, size_t n,
                                size_t ahead, uint32_t min_len, uint32_t max_len,
                                uint32_t max_dist, uint32_t* d_table, void* stream);
@@ -134,6 +165,20 @@ int sqz_gpu_parse_exit_map_device(const uint32_t* d_table, size_t n,
                                   uint32_t min_len, uint32_t max_len,
                                   void* d_work, uint16_t* d_exit_map, void* stream);
 
+/* ---- one process per device ------------------------------------------------ *
+ * Jobs that run one process per GPU (torchrun and the like) concatenate their
+ * shards' tokens the same way as sqz_gpu_tokens_multi, except that the destination
+ * buffer lives in one process and has to be mapped into the others: CUDA IPC, no
+ * collective.  The owner allocates and exports, the others open; every process then
+ * puts its tokens at its offset (the sum of the earlier shards' counts).       */
+#define SQZ_GPU_IPC_HANDLE_BYTES 64
+int  sqz_gpu_device_alloc(void** d_ptr, size_t bytes);
+void sqz_gpu_device_free(void* d_ptr);
+int  sqz_gpu_ipc_export(const void* d_ptr, uint8_t handle[SQZ_GPU_IPC_HANDLE_BYTES]);
+int  sqz_gpu_ipc_open(const uint8_t handle[SQZ_GPU_IPC_HANDLE_BYTES], void** d_ptr);
+int  sqz_gpu_ipc_close(void* d_ptr);
+int  sqz_gpu_put_tokens(uint32_t* d_dst, size_t at, const uint32_t* d_tokens, size_t count, void* stream);
+
 /* ---- decoder side: the LZ copy phase (replaces squeeze.h:533-539) --------- *
  * The reference's decoder executes every token as it reads it: a literal is
  * stored, a match copies len bytes from dist back, one byte at a time because
@@ -159,12 +204,14 @@ const char* sqz_gpu_last_error(void);            /* thread-local text */
 void*       sqz_gpu_host_alloc(size_t bytes);    /* pinned host memory (NULL on failure) */
 void        sqz_gpu_host_free(void* p);
 /* The host-buffer entry points keep their device and pinned staging buffers
- * (up to four slots) for the next call; this frees them.                     */
+ * for the next call (at most four slots and 3 GiB, oldest out first), and the
+ * plain device entry point keeps its scratch buffers; this frees them all.   */
 void        sqz_gpu_release(void);
 /* Which match-table kernel serves sqz_gpu_match_table_device: 0 = automatic
  * (bit-sliced kernel for min_len 2 or 3, thread-per-position kernel otherwise),
  * 1 = thread-per-position, 2 = bit-sliced where applicable.  Both are exact;
- * the switch exists for A/B measurements and tests.                          */
+ * the switch exists for A/B measurements and tests and applies to the calling
+ * thread only.                                                               */
 int         sqz_gpu_select_kernel(int which);
 /* Debugging aid: when d_buf (device, one u64 per tile of 16256 positions) is not
  * NULL the bit-sliced kernel stores every tile's duration in SM cycles.      */

@@ -6,7 +6,7 @@ the token stream unchanged (csrc/sqz_codec.c), and this thin ctypes mirror of
 the reference's codec interface.  See DESIGN.md.
 """
 from .api import (SqzError, compress, decode_tokens, decompress, decompress_gpu, device_count, expand_tokens, encode_symbols, encode_tokens, launch_count,
-                  match_table, read_header, select_kernel, symbols_of_tokens, tokens)
+                  match_table, read_header, release, select_kernel, symbols_of_tokens, tokens, tokens_multi)
 
 __all__ = ["SqzError", "compress", "decode_tokens", "decompress", "decompress_gpu", "device_count", "expand_tokens", "encode_symbols", "encode_tokens",
-           "launch_count", "match_table", "read_header", "select_kernel", "symbols_of_tokens", "tokens"]
+           "launch_count", "match_table", "read_header", "release", "select_kernel", "symbols_of_tokens", "tokens", "tokens_multi"]

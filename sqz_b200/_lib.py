@@ -82,10 +82,15 @@ SYMBOLS = {
     "sqz_gpu_match_table": (C.c_int, [u8p, size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u16p, u16p]),
     "sqz_gpu_tokens": (C.c_int, [u8p, size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u32p, size_t,
                                  C.POINTER(size_t)]),
+    "sqz_gpu_tokens_multi": (C.c_int, [C.POINTER(C.c_int), C.c_int, u8p, size_t, C.c_uint32, C.c_uint32, C.c_uint32,
+                                       C.c_uint32, C.c_void_p, size_t, C.POINTER(size_t), C.POINTER(size_t)]),
     "sqz_gpu_stream_open": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, u8p, size_t, C.c_uint32, C.c_uint32,
                                       C.c_uint32, C.c_uint32, size_t, C.c_uint32]),
     "sqz_gpu_stream_next": (C.c_int, [C.c_void_p, C.POINTER(u32p), C.POINTER(size_t)]),
     "sqz_gpu_stream_close": (None, [C.c_void_p]),
+    "sqz_gpu_match_workspace": (size_t, [size_t]),
+    "sqz_gpu_match_table_device_ws": (C.c_int, [C.c_void_p, size_t, size_t, size_t, C.c_uint32, C.c_uint32,
+                                                C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sqz_gpu_match_table_device": (C.c_int, [C.c_void_p, size_t, size_t, size_t, C.c_uint32, C.c_uint32,
                                              C.c_uint32, C.c_void_p, C.c_void_p]),
     "sqz_gpu_unpack_table_device": (C.c_int, [C.c_void_p, size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -96,6 +101,12 @@ SYMBOLS = {
                                                C.c_void_p, size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sqz_gpu_parse_exit_map_device": (C.c_int, [C.c_void_p, size_t, C.c_uint32, C.c_uint32, C.c_void_p,
                                                 C.c_void_p, C.c_void_p]),
+    "sqz_gpu_device_alloc": (C.c_int, [C.POINTER(C.c_void_p), size_t]),
+    "sqz_gpu_device_free": (None, [C.c_void_p]),
+    "sqz_gpu_ipc_export": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "sqz_gpu_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "sqz_gpu_ipc_close": (C.c_int, [C.c_void_p]),
+    "sqz_gpu_put_tokens": (C.c_int, [C.c_void_p, size_t, C.c_void_p, size_t, C.c_void_p]),
     "sqz_gpu_expand_tokens": (C.c_int, [u32p, size_t, u8p, size_t]),
     "sqz_gpu_expand_workspace": (size_t, [size_t, size_t]),
     "sqz_gpu_expand_tokens_device": (C.c_int, [C.c_void_p, size_t, C.c_void_p, size_t, C.c_void_p, C.c_void_p]),

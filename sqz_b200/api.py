@@ -67,6 +67,10 @@ def match_table(data, window: int = 1 << 15, min_len: int = G1_MIN_LEN, max_len:
         ds = np.empty(d.size, dtype=np.uint16)
     else:
         ln, ds = out
+        for name, a in (("len", ln), ("dist", ds)):     # the library writes d.size uint16 values into each
+            if not (isinstance(a, np.ndarray) and a.dtype == np.uint16 and a.flags.c_contiguous
+                    and a.flags.writeable and a.size >= d.size):
+                raise ValueError(f"out[{name}] must be a writeable C-contiguous uint16 array of at least {d.size} elements")
     rc = L.sqz_gpu_match_table(d.ctypes.data_as(u8p), d.size, w, lo, hi, md,
                                ln.ctypes.data_as(u16p), ds.ctypes.data_as(u16p))
     _check(rc, "sqz_gpu_match_table")
@@ -85,6 +89,30 @@ def tokens(data, window: int = 1 << 15, min_len: int = G1_MIN_LEN, max_len: int 
                           out.ctypes.data_as(u32p), out.size, C.byref(n))
     _check(rc, "sqz_gpu_tokens")
     return out[: n.value].copy()
+
+
+def tokens_multi(data, devices, window: int = 1 << 15, min_len: int = G1_MIN_LEN, max_len: int = G1_MAX_LEN,
+                 max_dist: int | None = None, return_shard_counts: bool = False):
+    """The same token stream computed on several GPUs of this process (sqz_gpu_tokens_multi):
+    contiguous shards with halos, seams chained on the host, token arrays concatenated in shard
+    order by copies sized by their counts.  Identical to tokens() for every device list."""
+    L = _lib.load()
+    d = _u8(data)
+    w, lo, hi, md = _rules(window, min_len, max_len, max_dist)
+    devs = (C.c_int * len(devices))(*[int(x) for x in devices])
+    out = np.empty(max(d.size, 1), dtype=np.uint32)
+    n = C.c_size_t()
+    per = (C.c_size_t * len(devices))()
+    rc = L.sqz_gpu_tokens_multi(devs, len(devices), d.ctypes.data_as(u8p), d.size, w, lo, hi, md,
+                                out.ctypes.data, out.size, C.byref(n), per)
+    _check(rc, "sqz_gpu_tokens_multi")
+    t = out[: n.value].copy()
+    return (t, [int(x) for x in per]) if return_shard_counts else t
+
+
+def release() -> None:
+    """Free the device and pinned staging buffers the library keeps between calls (sqz_gpu_release)."""
+    _lib.load().sqz_gpu_release()
 
 
 # ---- codec (sqz.h) ----------------------------------------------------------

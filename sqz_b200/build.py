@@ -45,20 +45,27 @@ def stale() -> bool:
     return any(os.path.getmtime(s) > t for s in sources())
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not stale():
+def build(force: bool = False, verbose: bool = False, variant: str | None = None,
+          defines: tuple[str, ...] = ()) -> str:
+    """The product library, or -- variant="name", defines=("-DSQZ_DEBUG_COUNTERS", ...) -- an
+    experimental build of the same ABI under tools/variants/ (loaded through SQZ_B200_LIB)."""
+    out_dir, lib = OUT_DIR, LIB
+    if variant:
+        out_dir = os.path.join(ROOT, "tools", "variants", variant + ".build")
+        lib = os.path.join(ROOT, "tools", "variants", variant + ".so")
+    elif not force and not stale():
         return LIB
-    os.makedirs(OUT_DIR, exist_ok=True)
+    os.makedirs(out_dir, exist_ok=True)
     inc = ["-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
     objs = []
     log = []
     for f in sorted(os.listdir(CSRC)):
         src = os.path.join(CSRC, f)
-        obj = os.path.join(OUT_DIR, f + ".o")
+        obj = os.path.join(out_dir, f + ".o")
         if f.endswith(".cu"):
-            cmd = [_nvcc(), *NVCC_FLAGS, *inc, "-c", src, "-o", obj]
+            cmd = [_nvcc(), *NVCC_FLAGS, *defines, *inc, "-c", src, "-o", obj]
         elif f.endswith(".c"):
-            cmd = ["gcc", *CC_FLAGS, *inc, "-c", src, "-o", obj]
+            cmd = ["gcc", *CC_FLAGS, *defines, *inc, "-c", src, "-o", obj]
         else:
             continue
         p = subprocess.run(cmd, capture_output=True, text=True)
@@ -67,18 +74,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(p.stdout + p.stderr)
             raise RuntimeError("compile failed: " + " ".join(cmd))
         objs.append(obj)
-    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs,
+    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib, *objs,
            "-Xlinker", "--version-script=" + os.path.join(CSRC, "exports.map")]
     p = subprocess.run(cmd, capture_output=True, text=True)
     if p.returncode != 0:
         sys.stderr.write(p.stdout + p.stderr)
         raise RuntimeError("link failed")
-    with open(os.path.join(OUT_DIR, "build.log"), "w") as fh:
+    with open(os.path.join(out_dir, "build.log"), "w") as fh:
         fh.write("\n".join(log))
     if verbose:
         sys.stderr.write("\n".join(log))
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    # python -m sqz_b200.build [--force] [--variant NAME -DFLAG ...]
+    name = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose=True, variant=name,
+                defines=tuple(a for a in sys.argv[1:] if a.startswith("-D"))))

@@ -154,7 +154,7 @@ __device__ __forceinline__ int pick_second_window(const uint32_t* __restrict__ W
 __device__ __noinline__ void finish_position(const uint8_t* __restrict__ S, int xi, int x_end,
                                              uint32_t d_from, uint32_t reach, uint32_t room, uint32_t min_len,
                                              uint32_t& best, uint32_t& bdist, int lane,
-                                             unsigned long long* dbg = nullptr) {
+                                             unsigned long long* dbg = nullptr, uint32_t* runner_up = nullptr) {
     const uint32_t* W = reinterpret_cast<const uint32_t*>(S);
     const int w_last = (x_end - 1) >> 2;
     unsigned int n_steps = 0, n_verify = 0, n_rounds = 0, n_improve = 0;
@@ -229,7 +229,11 @@ __device__ __noinline__ void finish_position(const uint8_t* __restrict__ S, int 
                     const uint32_t bal = __ballot_sync(0xFFFFFFFFu, diff);
                     if (bal != 0) { m = base + (uint32_t)(__ffs((int)bal) - 1); break; }
                 }
-                if (m >= need) { best = m; bdist = hit_d; improved = true; n_improve++; break; }
+                if (m >= need) {
+                    if (runner_up != nullptr) { *runner_up = best; }   // longest run among the nearer candidates
+                    best = m; bdist = hit_d; improved = true; n_improve++;
+                    break;
+                }
                 if (lane == src) { hb &= ~(1u << kk); }
             }
         }
@@ -243,12 +247,23 @@ __device__ __noinline__ void finish_position(const uint8_t* __restrict__ S, int 
     }
 }
 
+// A position leaves phase 1: its table word keeps what was found so far, marked open, with the
+// distance below which everything is settled.  No value comes back (RED, not a load + store); a
+// fresh best may still have a nearer equal inside the current group, so phase 2 starts it over.
+__device__ __forceinline__ void hand_over(uint32_t* slot, bool fresh, uint32_t resume_tag) {
+    if (fresh) { *slot = kOpenBit; }
+    else       { atomicOr(slot, kOpenBit | resume_tag); }
+}
+
 template <int kMinLen, bool kEdge>
 __global__ void __launch_bounds__(kThreads, 3)
 match_table(const uint8_t* __restrict__ shard, long long back, long long n, long long ahead,
-            uint32_t max_len, uint32_t max_dist, uint32_t* __restrict__ table, int tile_first,
+            uint32_t max_len, uint32_t max_dist, uint32_t* __restrict__ table,
+            uint32_t* __restrict__ open_mask, int tile_first,
             unsigned long long* __restrict__ tile_cycles) {
+#ifdef SQZ_DEBUG_COUNTERS
     const long long t_begin = clock64();
+#endif
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const Geometry geo = geometry(max_len, max_dist, kEdge);
     const uint4* PL = reinterpret_cast<const uint4*>(smem_raw);           // [plane_blocks][2]
@@ -359,8 +374,13 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
     uint32_t fresh[kQ];
 #pragma unroll
     for (int q = 0; q < kQ; q++) { fresh[q] = 0; }
-    // debugging aid (tools/tile_cycles.py): what the scalar path sees
+    // debugging aid (tools/tile_cycles.py, -DSQZ_DEBUG_COUNTERS builds only): what the scalar path sees
+#ifdef SQZ_DEBUG_COUNTERS
     unsigned int c_surv = 0, c_better = 0, c_tie_fresh = 0, c_reject = 0, c_hand = 0, c_iter_slow = 0;
+#define SQZ_COUNT(x) ((x)++)
+#else
+#define SQZ_COUNT(x) ((void)0)
+#endif
 
     for (int m0 = 1; m0 <= m_end; m0 += kQ) {
         // raw candidate words j = 0..2*kQ-1 <-> plane block blk0 - m0 - (kQ-1) + j
@@ -429,7 +449,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
             }
             if (none != 0xFFFFFFFFu) {
                 // ---- scalar path: exact decision for the few surviving positions ----
-                c_iter_slow++;
+                SQZ_COUNT(c_iter_slow);
 #pragma unroll
                 for (int t = 0; t < kQ; t++) {
                     const uint32_t d = (uint32_t)(32 * (m0 + t) - sh);
@@ -442,7 +462,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                             todo &= todo - 1;
                             const uint32_t bit = 1u << p;
                             const int k = (own0 + q) * 32 + p;          // tile-relative position
-                            c_surv++;
+                            SQZ_COUNT(c_surv);
                             SQZ_CHECK(k >= 0 && k < kTilePos && tile_pos0 + k < n, "phase 1: survivor outside the tile or the shard");
                             const uint32_t state = best_len[k];         // low 5 bits: best, high 3: near-ties seen
                             const uint32_t have = state & 31u;
@@ -453,16 +473,16 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                                 // at least 32 equal bytes: longer than the window, phase 2 finishes it.
                                 // A fresh best may still have a nearer equal: let phase 2 start over.
                                 best_len[k] = kHandOver;
-                                *slot = (fresh[q] & bit) ? kOpenBit : (*slot | kOpenBit | resume_tag);
+                                hand_over(slot, (fresh[q] & bit) != 0, resume_tag);
                                 closed_m[q] |= bit;
-                                c_hand++;
+                                SQZ_COUNT(c_hand);
                                 continue;
                             }
                             const uint32_t run = (uint32_t)(__ffs((int)win) - 1);
                             bool better = run > have;
-                            if (run == have && (fresh[q] & bit)) { better = d < (*slot & 0xFFFFu); c_tie_fresh++; }
+                            if (run == have && (fresh[q] & bit)) { better = d < (*slot & 0xFFFFu); SQZ_COUNT(c_tie_fresh); }
                             if (better) {
-                                c_better++;
+                                SQZ_COUNT(c_better);
                                 best_len[k] = (uint8_t)run;
                                 *slot = (run << 16) | d;
                                 fresh[q] |= bit;
@@ -470,12 +490,12 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                                 for (int g = 0; g < kGated; g++) {
                                     if (run > (uint32_t)(kMinLen + g)) { G[g][q] |= bit; }
                                 }
-                            } else if ((c_reject++, (d & kTieMask) == 0)) {
+                            } else if ((SQZ_COUNT(c_reject), (d & kTieMask) == 0)) {
                                 // a candidate that only ties or falls short: count a sample of them; a
                                 // position that keeps attracting them is cheaper to finish in phase 2
                                 if (state >= (kTieLimit << 5)) {
                                     best_len[k] = kHandOver;
-                                    *slot = (fresh[q] & bit) ? kOpenBit : (*slot | kOpenBit | resume_tag);
+                                    hand_over(slot, (fresh[q] & bit) != 0, resume_tag);
                                     closed_m[q] |= bit;
                                 } else {
                                     best_len[k] = (uint8_t)(state + 32u);
@@ -495,6 +515,19 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
             fresh[q] = 0;
         }
     }
+    // Work list of phase 2: one bit per position handed over, one word per block of 32 positions.
+    // Every block of the shard is owned by exactly one thread, so the list needs no zeroing and no
+    // atomics, and phase 2 reads n/8 bytes instead of scanning the table for marks.
+#pragma unroll
+    for (int q = 0; q < kQ; q++) {
+        if (lane == 31 && q == kQ - 1) { continue; }               // look-ahead block: the next warp owns it
+        const long long p0 = tile_pos0 + (long long)(own0 + q) * 32;
+        if (p0 < n) {
+            const uint32_t past_end = p0 + 32 > n ? (0xFFFFFFFFu << (int)(n - p0)) : 0u;
+            open_mask[p0 >> 5] = closed_m[q] & ~past_end;
+        }
+    }
+#ifdef SQZ_DEBUG_COUNTERS
     if (tile_cycles != nullptr) {          // debugging aid: per-tile duration and scalar-path counts
         unsigned long long* dbg2 = tile_cycles + (1 << 20) + 8;
         atomicAdd(dbg2 + 0, (unsigned long long)c_surv); atomicAdd(dbg2 + 1, (unsigned long long)c_better);
@@ -503,12 +536,16 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
         __syncthreads();
         if (threadIdx.x == 0) { tile_cycles[tile] = (unsigned long long)(clock64() - t_begin); }
     }
+#else
+    (void)tile_cycles;
+#endif
 }
 
 // ---------------------------------------------------------------------------
-// phase 2 kernel.  Phase 1 left the open positions marked in the table itself
-// (bit 31).  A warp takes a segment of the table, walks it from the top down
-// and closes every marked position:
+// phase 2 kernel.  Phase 1 left a work list: open_mask has one bit per position it handed over
+// (the table word of such a position carries kOpenBit, what was found so far and the distance
+// below which everything is settled).  A warp takes a segment of positions, reads the segment's
+// mask words in one go and closes every listed position from the top down:
 //
 //   inheritance -- if position p+1 ended with (b', d'), b' < max_len, and byte p
 //     equals byte p-d', then position p ends with exactly (b'+1, d'): no
@@ -516,11 +553,21 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
 //     nearer one with b'+1 would have been p+1's nearest b'.  Inside a long match
 //     every position but the last inherits, so a match costs one search, not one
 //     per position.
+//   capped inheritance -- if p+1 ended with (max_len, d') and byte p equals byte p-d', position
+//     p reaches max_len at d' as well, and only a candidate nearer than d' with a full max_len
+//     run can replace d' (the reference stops at the nearest one, squeeze.h:353).  Such a
+//     candidate d'' has run(p+1, d'') = max_len-1 exactly.  So one search at p for the nearest
+//     candidates below d' with a run of at least max_len-kSlack settles p, and tells how long
+//     the longest nearer run m* is: the next max_len-1-m* positions below p cannot have a nearer
+//     full run either (it would be a run > m* at p) and inherit (max_len, d') on a byte compare.
+//     A block repeated at a large distance costs one search per ~kSlack positions instead of one
+//     per position (BASELINE config 2, csrc.cat: 17 % of the positions).  d' = 1 needs no search.
 //   search -- otherwise the exact warp-wide search (finish_position).
 //
 // counters[0] is the segment cursor.
 // ---------------------------------------------------------------------------
 constexpr int kSegment = 1024;            // positions per work item of phase 2 (large shards)
+constexpr uint32_t kSlack = 64;           // capped inheritance looks for nearer runs >= max_len - kSlack
 
 // A warp closes its segment's positions one after the other, so the slowest segment bounds the
 // latency of a small shard (x64.elf, 0.9 MB: 17 ms with 1024-position segments).  Small shards
@@ -535,27 +582,39 @@ inline int finish_segment(long long n, int resident_warps) {
 __global__ void __launch_bounds__(kThreads)
 finish_marked(const uint8_t* __restrict__ shard, long long back, long long n, long long ahead,
               uint32_t min_len, uint32_t max_len, uint32_t max_dist, uint32_t* __restrict__ table,
-              unsigned int* __restrict__ counters, unsigned long long* __restrict__ dbg, int segment) {
+              const uint32_t* __restrict__ open_mask, unsigned int* __restrict__ counters,
+              unsigned long long* __restrict__ dbg, int segment) {
     const int lane = threadIdx.x & 31;
     const long long segments = (n + segment - 1) / segment;
+    const long long mask_words = (n + 31) >> 5;
+    const int seg_words = segment >> 5;                // segment is a multiple of 32, at most 1024
+    // runs a nearer candidate must reach to matter for capped inheritance: never below 32, the
+    // longest run phase 1 can have settled without handing the position over
+    const uint32_t slack = max_len > 32 + kSlack ? kSlack : (max_len > 32 ? max_len - 32 : 0u);
     for (;;) {
         unsigned int seg = 0;
         if (lane == 0) { seg = atomicAdd(counters, 1u); }
         seg = __shfl_sync(0xFFFFFFFFu, seg, 0);
         if ((long long)seg >= segments) { break; }
         const long long s0 = (long long)seg * segment;
-        const long long s1 = min(s0 + segment, n);
+        const long long w0 = s0 >> 5;
+        const uint32_t my_words = (lane < seg_words && w0 + lane < mask_words) ? open_mask[w0 + lane] : 0u;
+        uint32_t listed = __ballot_sync(0xFFFFFFFFu, my_words != 0);
         long long known_pos = -1;                      // position closed last by this warp ...
         uint32_t known_word = 0;                       // ... and its final word
-        for (long long top = s1; top > s0; top -= 32) {
-            const long long i = top - 32 + lane;       // lanes ascend with position
-            const uint32_t mine = i >= s0 ? table[i] : 0u;
-            uint32_t marks = __ballot_sync(0xFFFFFFFFu, (mine & kOpenBit) != 0);
+        uint32_t cert = 0;                             // positions below known_pos that may inherit its capped result
+        while (listed != 0) {
+            const int wi = 31 - __clz((int)listed);    // highest block first
+            listed &= ~(1u << wi);
+            uint32_t marks = __shfl_sync(0xFFFFFFFFu, my_words, wi);
+            const long long base = s0 + 32LL * wi;
             while (marks != 0) {
                 const int src = 31 - __clz((int)marks);             // highest position first
                 marks &= ~(1u << src);
-                const long long p = top - 32 + src;
-                const uint32_t raw = __shfl_sync(0xFFFFFFFFu, mine, src);
+                const long long p = base + src;
+                SQZ_CHECK(p < n, "phase 2: listed position outside the shard");
+                const uint32_t raw = table[p];
+                SQZ_CHECK((raw & kOpenBit) != 0, "phase 2: listed position is not open");
                 const uint32_t word = raw & kStateMask;
                 const uint32_t resume = ((raw >> kResumeShift) & 31u) << 10;   // phase 1 settled every nearer distance
                 uint32_t best = word >> 16, bdist = word & 0xFFFFu;
@@ -565,31 +624,46 @@ finish_marked(const uint8_t* __restrict__ shard, long long back, long long n, lo
                 uint32_t nb = 0;
                 if (p + 1 < n) { nb = (p + 1 == known_pos) ? known_word : table[p + 1]; }
                 const uint32_t nlen = (nb >> 16) & 0x7FFFu, ndist = nb & 0xFFFFu;
-                bool inherited = false;
+                bool done = false;
                 const bool usable = (nb & kOpenBit) == 0 && nlen >= min_len && ndist >= 1 && ndist <= far;
                 // local byte image for a search: starts at the farthest candidate, rounded down to a word
                 const uint8_t* lo = shard + p - (long long)far;
                 const int mis = (int)(reinterpret_cast<uintptr_t>(lo) & 3);
                 const long long left = n + ahead - p;
                 const int x_end = mis + (int)far + (int)min(left, (long long)max_len + 8);
+                uint32_t cert_next = 0;
                 if (usable && nlen + 1 <= room && nlen < max_len) {
                     SQZ_CHECK(p - (long long)ndist >= -back && p < n + ahead, "phase 2: inheritance byte outside the data");
                     if (shard[p] == shard[p - (long long)ndist]) {
                         best = nlen + 1;
                         bdist = ndist;
-                        inherited = true;
+                        done = true;
                     }
-                } else if (usable && nlen == max_len && room == max_len && ndist == 1) {
-                    // inside a run of one byte value: the position above holds max_len at distance 1;
-                    // if byte p continues the run, so does this one, and nothing is nearer than 1
-                    if (shard[p] == shard[p - 1]) {
+                } else if (usable && nlen == max_len && room == max_len && shard[p] == shard[p - (long long)ndist]) {
+                    if (ndist == 1) {
+                        // inside a run of one byte value: nothing is nearer than 1
                         best = max_len;
                         bdist = 1;
-                        inherited = true;
+                        done = true;
+                    } else if (cert > 0 && p + 1 == known_pos) {
+                        // the search a few positions above saw no nearer run long enough to matter here
+                        best = max_len;
+                        bdist = ndist;
+                        cert_next = cert - 1;
+                        done = true;
+                    } else if (slack > 0) {
+                        uint32_t b2 = max_len - slack - 1, d2 = 0, runner_up = b2;
+                        SQZ_CHECK(p - (long long)far >= -back && p + (long long)room <= n + ahead, "phase 2: search window outside the data");
+                        finish_position(lo - mis, mis + (int)far, x_end, resume, ndist - 1, room, min_len, b2, d2, lane, dbg, &runner_up);
+                        best = max_len;
+                        bdist = b2 == max_len ? d2 : ndist;
+                        cert_next = max_len - 1 - (b2 == max_len ? runner_up : b2);
+                        done = true;
+                        if (dbg != nullptr && lane == 0) { atomicAdd(dbg + 22, 1ull); }
                     }
                 }
-                if (!inherited && dbg != nullptr && lane == 0) {
-                    // why not: 16 neighbour open, 17 neighbour without a match, 18 neighbour at max_len (d != 1 or byte differs),
+                if (!done && dbg != nullptr && lane == 0) {
+                    // why not: 16 neighbour open, 17 neighbour without a match, 18 neighbour at max_len (byte differs),
                     // 19 byte differs, 20 no neighbour in this shard, 21 other
                     int why = 21;
                     if (p + 1 >= n) { why = 20; }
@@ -599,12 +673,13 @@ finish_marked(const uint8_t* __restrict__ shard, long long back, long long n, lo
                     else if (usable && nlen + 1 <= room) { why = 19; }
                     atomicAdd(dbg + why, 1ull);
                 }
-                if (!inherited) {
+                if (!done) {
                     SQZ_CHECK(p - (long long)far >= -back && p + (long long)room <= n + ahead, "phase 2: search window outside the data");
                     finish_position(lo - mis, mis + (int)far, x_end, resume, far, room, min_len, best, bdist, lane, dbg);
                 } else if (dbg != nullptr && lane == 0) {
                     atomicAdd(dbg + 5, 1ull);
                 }
+                cert = cert_next;
                 known_pos = p;
                 known_word = best >= min_len ? ((best << 16) | bdist) : 0u;
                 if (lane == 0) { table[p] = known_word; }

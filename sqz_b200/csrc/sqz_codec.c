@@ -726,6 +726,14 @@ static inline uint32_t symbols_of_token(const struct sqz* s, uint32_t t) {
  * full word goes straight to memory when the sink is a buffer with room;
  * everything unusual (first occurrence of a symbol, callback sinks, a full
  * buffer) goes through the general functions above with the register synced. */
+static inline int word_is_valid(uint32_t w) {
+    const uint32_t sym = w & 0x1FF;
+    /* bucket 27 with all five extra bits set would be length 258, which no decoder accepts
+     * (squeeze.h:529-545) */
+    return sym <= 0xFF || (sym >= len_symbol0 && sym <= len_symbol0 + 27 && ((w >> 14) & 31) <= 29 &&
+                           !(sym == len_symbol0 + 27 && ((w >> 9) & 31) == 31));
+}
+
 static void code_symbols(struct sqz* s, const uint32_t* words, uint64_t count) {
     struct sqz_bitstream* const bs = s->bs;
     struct sqz_tree* const lit = &s->lit;
@@ -760,7 +768,7 @@ static void code_symbols(struct sqz* s, const uint32_t* words, uint64_t count) {
     for (uint64_t k = 0; k < count; k++) {
         const uint32_t w = words[k];
         const uint32_t sym = w & 0x1FF;
-        if (sym > 0xFF && (sym < len_symbol0 || sym > len_symbol0 + 27 || ((w >> 14) & 31) > 29)) {
+        if (!word_is_valid(w)) {
             s->error = EINVAL;                       /* not a symbol word: the decoder would reject it */
             goto done;
         }
@@ -869,11 +877,22 @@ struct duo {                            /* one cache line per writer: the two th
     struct change log[log_size];
 };
 
+/* Waiting for the other thread: a short spin (the usual wait is a few hundred nanoseconds), then
+ * yields, then sleeps of 20 and finally 200 microseconds -- the model thread waits tens of
+ * milliseconds for the GPU search of the next chunk and must not keep a core busy meanwhile. */
 static inline void spin_wait(unsigned* spins) {
+    const unsigned n = ++*spins;
+    if (n <= 2000) {
 #if defined(__x86_64__) || defined(__i386__)
-    __builtin_ia32_pause();
+        __builtin_ia32_pause();
 #endif
-    if (++*spins > 2000) { sched_yield(); *spins = 0; }
+    } else if (n <= 2064) {
+        sched_yield();
+    } else {
+        const struct timespec nap = { 0, n <= 2564 ? 20000 : 200000 };
+        nanosleep(&nap, NULL);
+        if (n > (1u << 30)) { *spins = 2565; }
+    }
 }
 
 static void note_change(struct sqz_tree* t, int32_t leaf) {
@@ -894,10 +913,6 @@ static void note_change(struct sqz_tree* t, int32_t leaf) {
     atomic_store_explicit(&d->log_tail, tail + 1, memory_order_release);
 }
 
-static inline int word_is_valid(uint32_t w) {
-    const uint32_t sym = w & 0x1FF;
-    return sym <= 0xFF || (sym >= len_symbol0 && sym <= len_symbol0 + 27 && ((w >> 14) & 31) <= 29);
-}
 
 static void* model_main(void* arg) {
     struct duo* d = (struct duo*)arg;
@@ -1328,8 +1343,23 @@ static void decode_stream(struct sqz* s, struct sqz_bitstream* bs, uint8_t* data
     }
     if (count != NULL) { *count = n_tokens; }
     if (tokens != NULL && n_tokens > cap && s->error == 0) { s->error = E2BIG; }
-    bs->b64 = w.acc;                    /* what is left of the window (any bits in `pend` are dropped) */
-    bs->bits = w.have;
+    /* Leave the bitstream where the reference's bit-at-a-time reader would stand
+     * (bitstream.h:65-95): it has taken ceil(consumed / 64) words, and the rest of the last one
+     * is in b64.  The window reads ahead, so up to one whole word may have to go back: in memory
+     * mode `read` is rewound; a callback source cannot take a word back, there the bits of that
+     * word are lost to a caller who keeps reading from the same bitstream (see sqz.h). */
+    {
+        const int32_t unread = w.have + w.pend_bits;            /* < 96 */
+        const int32_t rest = unread & 63;                       /* bits of the word the reference is in */
+        if (unread >= 64) {
+            bs->b64 = rest > 0 ? w.acc & ~(~(uint64_t)0 >> rest) : 0;
+            bs->bits = rest;
+            if (bs->data != NULL && bs->read >= 8) { bs->read -= 8; }
+        } else {
+            bs->b64 = w.acc | (w.have < 64 ? w.pend >> w.have : 0);
+            bs->bits = unread;
+        }
+    }
     if (s->error != 0 && bs->error == 0) { bs->error = s->error; }
 }
 

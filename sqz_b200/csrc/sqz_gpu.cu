@@ -509,20 +509,155 @@ static unsigned long long* g_tile_cycles = nullptr;   // debugging aid, see sqz_
 
 extern "C" void sqz_gpu_debug_tile_cycles(unsigned long long* d_buf) { g_tile_cycles = d_buf; }
 
-static std::atomic<int> g_kernel_choice{0};   // 0 auto, 1 thread-per-position (v1), 2 bit-sliced (v2)
+// A/B switch for tests and measurements; per calling thread, so that it is no process-wide state
+static thread_local int g_kernel_choice = 0;   // 0 auto, 1 thread-per-position (v1), 2 bit-sliced (v2)
 
 extern "C" int sqz_gpu_select_kernel(int which) {
     if (which < 0 || which > 2) { return fail(EINVAL, "kernel choice must be 0, 1 or 2"); }
-    g_kernel_choice.store(which);
+    g_kernel_choice = which;
     return 0;
+}
+
+// ---------------------------------------------------------------------------
+// per-device set-up: function attributes, the two side streams of the edge tiles, SM count
+// ---------------------------------------------------------------------------
+constexpr int kMaxDevices = 64;
+
+struct DeviceState {
+    std::once_flag once;
+    cudaError_t err = cudaSuccess;
+    cudaStream_t side = nullptr, side2 = nullptr;
+    int sms = 0;
+};
+static DeviceState g_dev[kMaxDevices];
+
+template <typename K>
+static cudaError_t allow_smem(K kernel, int bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    // several CTAs per SM only fit when the L1/shared split favours shared memory
+    if (e == cudaSuccess) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
+    return e;
+}
+
+static int device_state(DeviceState** out) {
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) { return fail(ENODEV, "device index out of range"); }
+    DeviceState& d = g_dev[dev];
+    std::call_once(d.once, [&d, dev] {
+        const int big = v2::geometry(sqz_gpu_max_len_limit, sqz_gpu_max_dist_limit, true).smem_bytes;
+        cudaError_t e = allow_smem(v2::match_table<3, false>, big);
+        if (e == cudaSuccess) { e = allow_smem(v2::match_table<3, true>, big); }
+        if (e == cudaSuccess) { e = allow_smem(v2::match_table<2, false>, big); }
+        if (e == cudaSuccess) { e = allow_smem(v2::match_table<2, true>, big); }
+        if (e == cudaSuccess) {
+            e = cudaFuncSetAttribute(v1::match_table, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)v1::smem_bytes(sqz_gpu_max_len_limit, sqz_gpu_max_dist_limit));
+        }
+        if (e == cudaSuccess) { e = cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev); }
+        if (e == cudaSuccess) { e = cudaStreamCreateWithFlags(&d.side, cudaStreamNonBlocking); }
+        if (e == cudaSuccess) { e = cudaStreamCreateWithFlags(&d.side2, cudaStreamNonBlocking); }
+        d.err = e;
+    });
+    if (d.err != cudaSuccess) { return fail(cuda_code(d.err), "per-device set-up", d.err); }
+    *out = &d;
+    return 0;
+}
+
+static int sm_count() {
+    DeviceState* d = nullptr;
+    return device_state(&d) == 0 ? d->sms : 148;
+}
+
+// an event that lives as long as one launcher call, whatever way the call ends
+struct ScopedEvent {
+    cudaEvent_t e = nullptr;
+    ~ScopedEvent() { if (e != nullptr) { cudaEventDestroy(e); } }
+    cudaError_t create() { return cudaEventCreateWithFlags(&e, cudaEventDisableTiming); }
+};
+
+// ---------------------------------------------------------------------------
+// workspace of the match table: the segment cursor of phase 2 and phase 1's work list
+// (one bit per position).  Callers of the _ws entry point own it; the plain entry point
+// borrows one from a small per-device pool and hands it back when the stream has passed.
+// ---------------------------------------------------------------------------
+constexpr size_t kCursorBytes = 256;
+
+extern "C" size_t sqz_gpu_match_workspace(size_t n) {
+    return kCursorBytes + (((n + 31) / 32 + 8) * 4 + 255) / 256 * 256;
+}
+
+struct PoolBuffer { void* ptr; size_t bytes; cudaEvent_t passed; int device; };
+static std::mutex g_pool_mu;
+static std::vector<PoolBuffer> g_pool;          // idle or in flight (passed not yet reached)
+constexpr size_t kPoolMax = 16;
+
+static int pool_take(size_t bytes, PoolBuffer* out) {
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        for (size_t k = 0; k < g_pool.size(); k++) {
+            PoolBuffer& b = g_pool[k];
+            if (b.device == dev && b.bytes >= bytes && b.bytes <= 4 * bytes + (1u << 20) &&
+                cudaEventQuery(b.passed) == cudaSuccess) {
+                *out = b;
+                g_pool.erase(g_pool.begin() + (long)k);
+                return 0;
+            }
+        }
+        cudaGetLastError();                      // cudaErrorNotReady of a busy buffer is not an error
+    }
+    PoolBuffer b{nullptr, bytes, nullptr, dev};
+    CU(cudaMalloc(&b.ptr, bytes));
+    cudaError_t ce = cudaEventCreateWithFlags(&b.passed, cudaEventDisableTiming);
+    if (ce != cudaSuccess) { cudaFree(b.ptr); return fail(cuda_code(ce), "cudaEventCreate", ce); }
+    *out = b;
+    return 0;
+}
+
+static void pool_free(PoolBuffer& b) {
+    cudaEventSynchronize(b.passed);
+    cudaEventDestroy(b.passed);
+    cudaFree(b.ptr);
+}
+
+// the work queued on `s` so far is the last user of the buffer
+static void pool_give_back(PoolBuffer b, cudaStream_t s) {
+    cudaEventRecord(b.passed, s);
+    PoolBuffer victim{nullptr, 0, nullptr, 0};
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        g_pool.push_back(b);
+        if (g_pool.size() > kPoolMax) { victim = g_pool.front(); g_pool.erase(g_pool.begin()); }
+    }
+    if (victim.ptr != nullptr) {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        cudaSetDevice(victim.device);
+        pool_free(victim);
+        cudaSetDevice(cur);
+    }
+}
+
+static void pool_release_all() {
+    std::vector<PoolBuffer> all;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        all.swap(g_pool);
+    }
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (PoolBuffer& b : all) { cudaSetDevice(b.device); pool_free(b); }
+    cudaSetDevice(cur);
 }
 
 static int launch_v1(const uint8_t* d_shard, size_t back, size_t n, size_t ahead, uint32_t min_len,
                      uint32_t max_len, uint32_t max_dist, uint32_t* d_table, cudaStream_t s) {
-    // (cheap and idempotent: set on every call so that every device's context has it)
-    cudaError_t attr_err = cudaFuncSetAttribute(v1::match_table, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                (int)v1::smem_bytes(sqz_gpu_max_len_limit, sqz_gpu_max_dist_limit));
-    if (attr_err != cudaSuccess) { return fail(cuda_code(attr_err), "cudaFuncSetAttribute", attr_err); }
+    DeviceState* dv = nullptr;
+    if (int r = device_state(&dv)) { return r; }
     const size_t tiles = (n + v1::kThreads - 1) / v1::kThreads;
     if (tiles > 0x7FFFFFFFull) { return fail(EINVAL, "shard too large for one launch"); }
     v1::match_table<<<(unsigned)tiles, v1::kThreads, v1::smem_bytes(max_len, max_dist), s>>>(
@@ -533,37 +668,9 @@ static int launch_v1(const uint8_t* d_shard, size_t back, size_t n, size_t ahead
 
 template <int kMinLen>
 static int launch_v2(const uint8_t* d_shard, size_t back, size_t n, size_t ahead, uint32_t max_len,
-                     uint32_t max_dist, uint32_t* d_table, cudaStream_t s) {
-    // function attributes and the side stream live in the device's context: set up once per device
-    constexpr int kMaxDevices = 64;
-    static std::once_flag once[kMaxDevices];
-    static cudaError_t attr_errs[kMaxDevices];
-    static cudaStream_t sides[kMaxDevices], sides2[kMaxDevices];
-    int dev = 0;
-    CU(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= kMaxDevices) { return fail(ENODEV, "device index out of range"); }
-    std::call_once(once[dev], [dev] {
-        const int big = v2::geometry(sqz_gpu_max_len_limit, sqz_gpu_max_dist_limit, true).smem_bytes;
-        cudaError_t e = cudaFuncSetAttribute(v2::match_table<kMinLen, false>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-        if (e == cudaSuccess) {
-            e = cudaFuncSetAttribute(v2::match_table<kMinLen, true>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-        }
-        // several CTAs per SM only fit when the L1/shared split favours shared memory
-        cudaFuncSetAttribute(v2::match_table<kMinLen, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                             cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(v2::match_table<kMinLen, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                             cudaSharedmemCarveoutMaxShared);
-        sides[dev] = nullptr;
-        sides2[dev] = nullptr;
-        cudaStreamCreateWithFlags(&sides[dev], cudaStreamNonBlocking);
-        cudaStreamCreateWithFlags(&sides2[dev], cudaStreamNonBlocking);
-        attr_errs[dev] = e;
-    });
-    const cudaError_t attr_err = attr_errs[dev];
-    cudaStream_t side = sides[dev], side2 = sides2[dev];
-    if (attr_err != cudaSuccess) { return fail(cuda_code(attr_err), "cudaFuncSetAttribute", attr_err); }
+                     uint32_t max_dist, uint32_t* d_table, void* d_work, cudaStream_t s) {
+    DeviceState* dv = nullptr;
+    if (int r = device_state(&dv)) { return r; }
     // Tiles whose every position sees the full max_dist window and max_len of
     // look-ahead run the plain variant; the rest (start of the first shard, end
     // of the last one, a partial last tile) run the variant with a validity plane.
@@ -576,71 +683,57 @@ static int launch_v2(const uint8_t* d_shard, size_t back, size_t n, size_t ahead
     t_lo = std::min(t_lo, tiles);
     t_hi = std::max(std::min(t_hi, tiles), t_lo);
     if ((unsigned long long)n > 0xFFFFFFFFull) { return fail(EINVAL, "shard too large for one launch"); }
-    // segment cursor of phase 2: one of a small ring of device counters set up once per device
-    // (no stream-ordered allocation on the hot path: the pool ties streams together)
-    constexpr unsigned kRing = 256;
-    static unsigned int* rings[kMaxDevices];
-    static std::atomic<unsigned> ring_next[kMaxDevices];
-    static std::once_flag ring_once[kMaxDevices];
-    std::call_once(ring_once[dev], [dev] {
-        rings[dev] = nullptr;
-        if (cudaMalloc((void**)&rings[dev], kRing * 16) != cudaSuccess) { rings[dev] = nullptr; cudaGetLastError(); }
-    });
-    if (rings[dev] == nullptr) { return fail(ENOMEM, "cannot allocate the phase 2 cursors"); }
-    unsigned int* d_counters = rings[dev] + 4 * (ring_next[dev].fetch_add(1) % kRing);
+    unsigned int* d_counters = static_cast<unsigned int*>(d_work);
+    uint32_t* d_open = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(d_work) + kCursorBytes);
     CU(cudaMemsetAsync(d_counters, 0, 16, s));
     const int smem_main = v2::geometry(max_len, max_dist, false).smem_bytes;
     const int smem_edge = v2::geometry(max_len, max_dist, true).smem_bytes;
-    // The few edge tiles run on a side stream, concurrently with the interior tiles.
-    // leading and trailing edge tiles each get a side stream of their own
+    // The few edge tiles run concurrently with the interior tiles: leading and trailing edge
+    // tiles each on a side stream of the device, forked from and joined back into `s`.
     const bool lead = t_lo > 0, trail = tiles > t_hi;
-    cudaStream_t es1 = side != nullptr ? side : s, es2 = side2 != nullptr ? side2 : s;
-    cudaEvent_t fork = nullptr, join1 = nullptr, join2 = nullptr;
+    ScopedEvent fork, join1, join2;
     if (lead || trail) {
-        CU(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
-        CU(cudaEventRecord(fork, s));
+        CU(fork.create());
+        CU(cudaEventRecord(fork.e, s));
     }
     if (lead) {
-        if (es1 != s) { CU(cudaStreamWaitEvent(es1, fork, 0)); }
-        v2::match_table<kMinLen, true><<<(unsigned)t_lo, v2::kThreads, smem_edge, es1>>>(
-            d_shard, (long long)back, (long long)n, (long long)ahead, max_len, max_dist, d_table, 0, g_tile_cycles);
+        CU(cudaStreamWaitEvent(dv->side, fork.e, 0));
+        v2::match_table<kMinLen, true><<<(unsigned)t_lo, v2::kThreads, smem_edge, dv->side>>>(
+            d_shard, (long long)back, (long long)n, (long long)ahead, max_len, max_dist, d_table, d_open, 0, g_tile_cycles);
         LAUNCHED("match_table_v2_edge");
-        if (es1 != s) {
-            CU(cudaEventCreateWithFlags(&join1, cudaEventDisableTiming));
-            CU(cudaEventRecord(join1, es1));
-        }
+        CU(join1.create());
+        CU(cudaEventRecord(join1.e, dv->side));
     }
     if (trail) {
-        if (es2 != s) { CU(cudaStreamWaitEvent(es2, fork, 0)); }
-        v2::match_table<kMinLen, true><<<(unsigned)(tiles - t_hi), v2::kThreads, smem_edge, es2>>>(
-            d_shard, (long long)back, (long long)n, (long long)ahead, max_len, max_dist, d_table, (int)t_hi, g_tile_cycles);
+        CU(cudaStreamWaitEvent(dv->side2, fork.e, 0));
+        v2::match_table<kMinLen, true><<<(unsigned)(tiles - t_hi), v2::kThreads, smem_edge, dv->side2>>>(
+            d_shard, (long long)back, (long long)n, (long long)ahead, max_len, max_dist, d_table, d_open, (int)t_hi, g_tile_cycles);
         LAUNCHED("match_table_v2_edge");
-        if (es2 != s) {
-            CU(cudaEventCreateWithFlags(&join2, cudaEventDisableTiming));
-            CU(cudaEventRecord(join2, es2));
-        }
+        CU(join2.create());
+        CU(cudaEventRecord(join2.e, dv->side2));
     }
     if (t_hi > t_lo) {
         v2::match_table<kMinLen, false><<<(unsigned)(t_hi - t_lo), v2::kThreads, smem_main, s>>>(
-            d_shard, (long long)back, (long long)n, (long long)ahead, max_len, max_dist, d_table, (int)t_lo, g_tile_cycles);
+            d_shard, (long long)back, (long long)n, (long long)ahead, max_len, max_dist, d_table, d_open, (int)t_lo, g_tile_cycles);
         LAUNCHED("match_table_v2");
     }
-    if (join1 != nullptr) { CU(cudaStreamWaitEvent(s, join1, 0)); CU(cudaEventDestroy(join1)); }
-    if (join2 != nullptr) { CU(cudaStreamWaitEvent(s, join2, 0)); CU(cudaEventDestroy(join2)); }
-    if (fork != nullptr) { CU(cudaEventDestroy(fork)); }
-    v2::finish_marked<<<148 * 16, v2::kThreads, 0, s>>>(d_shard, (long long)back, (long long)n, (long long)ahead,
-                                                     (uint32_t)kMinLen, max_len, max_dist, d_table, d_counters,
-                                                     g_tile_cycles ? g_tile_cycles + (1 << 20) : nullptr,
-                                                     v2::finish_segment((long long)n, 148 * 16 * v2::kWarps));
+    if (join1.e != nullptr) { CU(cudaStreamWaitEvent(s, join1.e, 0)); }
+    if (join2.e != nullptr) { CU(cudaStreamWaitEvent(s, join2.e, 0)); }
+    const int finish_ctas = dv->sms * 16;
+    v2::finish_marked<<<finish_ctas, v2::kThreads, 0, s>>>(d_shard, (long long)back, (long long)n, (long long)ahead,
+                                                           (uint32_t)kMinLen, max_len, max_dist, d_table, d_open, d_counters,
+                                                           g_tile_cycles ? g_tile_cycles + (1 << 20) : nullptr,
+                                                           v2::finish_segment((long long)n, finish_ctas * v2::kWarps));
     LAUNCHED("match_finish_marked");
     return 0;
 }
 
-extern "C" int sqz_gpu_match_table_device(const uint8_t* d_shard, size_t back, size_t n,
-                                          size_t ahead, uint32_t min_len, uint32_t max_len,
-                                          uint32_t max_dist, uint32_t* d_table, void* stream) {
+extern "C" int sqz_gpu_match_table_device_ws(const uint8_t* d_shard, size_t back, size_t n,
+                                             size_t ahead, uint32_t min_len, uint32_t max_len,
+                                             uint32_t max_dist, uint32_t* d_table, void* d_work, void* stream) {
     if (int r = check_rules(min_len, max_len, max_dist)) { return r; }
     if (n == 0) { return 0; }
+    if (d_work == nullptr) { return fail(EINVAL, "null workspace"); }
     cudaStream_t s = (cudaStream_t)stream;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     bool timed = false;
@@ -654,25 +747,40 @@ extern "C" int sqz_gpu_match_table_device(const uint8_t* d_shard, size_t back, s
         CU(cudaEventCreate(&e1));
         CU(cudaEventRecord(e0, s));
     }
-    const int choice = g_kernel_choice.load();
+    const int choice = g_kernel_choice;
     int r;
     const bool v2_ok = max_len > 32;      // the bit-sliced kernel measures runs in a 32-bit window
-    if (choice != 1 && v2_ok && min_len == 3)      { r = launch_v2<3>(d_shard, back, n, ahead, max_len, max_dist, d_table, s); }
-    else if (choice != 1 && v2_ok && min_len == 2) { r = launch_v2<2>(d_shard, back, n, ahead, max_len, max_dist, d_table, s); }
+    if (choice != 1 && v2_ok && min_len == 3)      { r = launch_v2<3>(d_shard, back, n, ahead, max_len, max_dist, d_table, d_work, s); }
+    else if (choice != 1 && v2_ok && min_len == 2) { r = launch_v2<2>(d_shard, back, n, ahead, max_len, max_dist, d_table, d_work, s); }
     else { r = launch_v1(d_shard, back, n, ahead, min_len, max_len, max_dist, d_table, s); }
-    if (r != 0) { return r; }
     if (timed) {
-        CU(cudaEventRecord(e1, s));
-        std::lock_guard<std::mutex> lk(g_time_mu);
-        g_pending.emplace_back(e0, e1);
+        if (r == 0 && cudaEventRecord(e1, s) == cudaSuccess) {
+            std::lock_guard<std::mutex> lk(g_time_mu);
+            g_pending.emplace_back(e0, e1);
+        } else {
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+        }
     }
-    return 0;
+    return r;
+}
+
+extern "C" int sqz_gpu_match_table_device(const uint8_t* d_shard, size_t back, size_t n,
+                                          size_t ahead, uint32_t min_len, uint32_t max_len,
+                                          uint32_t max_dist, uint32_t* d_table, void* stream) {
+    if (int r = check_rules(min_len, max_len, max_dist)) { return r; }
+    if (n == 0) { return 0; }
+    PoolBuffer b;
+    if (int r = pool_take(sqz_gpu_match_workspace(n), &b)) { return r; }
+    const int r = sqz_gpu_match_table_device_ws(d_shard, back, n, ahead, min_len, max_len, max_dist, d_table, b.ptr, stream);
+    pool_give_back(b, (cudaStream_t)stream);
+    return r;
 }
 
 extern "C" int sqz_gpu_unpack_table_device(const uint32_t* d_table, size_t n,
                                            uint16_t* d_len, uint16_t* d_dist, void* stream) {
     if (n == 0) { return 0; }
-    const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 16);
+    const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)sm_count() * 16);
     unpack_table<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_table, n, d_len, d_dist);
     LAUNCHED("unpack_table");
     return 0;
@@ -742,8 +850,10 @@ extern "C" int sqz_gpu_parse_device(const uint8_t* d_shard, const uint32_t* d_ta
 
 // symbol words only exist for the bitstream's own limits (squeeze.h:13-15, 529-545)
 static int check_symbol_rules(uint32_t min_len, uint32_t max_len, uint32_t max_dist) {
-    if (min_len < 3 || max_len > 258 || max_dist > 0x7FFF) {
-        return fail(EINVAL, "symbol words need min_len >= 3, max_len <= 258, max_dist <= 32767");
+    // 258 has a bucket (27, extra bits 31) but no decoder accepts it: squeeze.h:529-545 and
+    // sqz_decompress reject every length above 257 with EINVAL
+    if (min_len < 3 || max_len > 257 || max_dist > 0x7FFF) {
+        return fail(EINVAL, "symbol words need min_len >= 3, max_len <= 257, max_dist <= 32767");
     }
     return 0;
 }
@@ -775,26 +885,48 @@ extern "C" int sqz_gpu_parse_exit_map_device(const uint32_t* d_table, size_t n,
 // ---------------------------------------------------------------------------
 // host-buffer ABI: chunked, double-buffered pipeline
 // ---------------------------------------------------------------------------
+
+// Tokens leave the device sized by their count, which only the device knows when the copy is
+// queued: this kernel reads the count the parse left in result[0] and stores exactly that many
+// words into pinned host memory (mapped into the device's address space by cudaHostAlloc) with
+// 16-byte stores.  No host round trip, no copy of unused slots.
+__global__ void __launch_bounds__(256)
+tokens_to_host(const uint32_t* __restrict__ d_tokens, const uint64_t* __restrict__ d_result,
+               uint32_t* __restrict__ h_tokens) {
+    const size_t count = (size_t)d_result[0];
+    const size_t quads = (count + 3) / 4;               // both buffers are 16-byte aligned and padded
+    const uint4* src = reinterpret_cast<const uint4*>(d_tokens);
+    uint4* dst = reinterpret_cast<uint4*>(h_tokens);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < quads; i += (size_t)gridDim.x * blockDim.x) {
+        dst[i] = src[i];
+    }
+}
+
 struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;       // everything of the chunk has been issued and finished
+    cudaEvent_t parsed = nullptr;     // the chunk's token count and overshoot are in h_result
     uint8_t* d_data = nullptr;        // back halo + chunk + ahead halo
     uint32_t* d_table = nullptr;
     uint32_t* d_tokens = nullptr;
     uint16_t* d_len = nullptr;        // table mode only
     uint16_t* d_dist = nullptr;
-    void* d_work = nullptr;
+    void* d_work = nullptr;           // parse workspace
+    void* d_mwork = nullptr;          // match workspace (cursor + work list of phase 2)
     uint64_t* d_result = nullptr;     // [0] tokens, [1] overshoot (next chunk's entry)
     uint64_t* h_result = nullptr;     // pinned
-    uint32_t* h_tokens = nullptr;     // pinned
+    uint32_t* h_tokens = nullptr;     // pinned (streaming consumers only)
     size_t first = 0, n = 0;          // chunk = [first, first + n) of the input
     bool busy = false;
     // what the buffers were sized for (slots are recycled between calls, see slot_take)
     int device = -1;
     size_t cap_chunk = 0;
     uint32_t cap_len = 0, cap_dist = 0;
-    bool cap_tokens = false;
+    int cap_mode = 0;
+    size_t device_bytes = 0, pinned_bytes = 0;
 };
+
+enum { kModeTable = 0, kModeTokensPinned = 1, kModeTokensDirect = 2 };
 
 struct sqz_gpu_stream {
     int device = 0;
@@ -806,50 +938,70 @@ struct sqz_gpu_stream {
     size_t launched = 0;              // input bytes handed to the device so far
     size_t delivered = 0;             // input bytes whose tokens were returned
     int next_slot = 0, read_slot = 0;
-    bool want_tokens = true;
+    int mode = kModeTokensPinned;
     bool symbols = false;             // emit symbol words instead of plain tokens
     Slot slot[2];
     const uint64_t* prev_result = nullptr;   // device: previous chunk's result (entry hand-off)
     cudaEvent_t prev_parsed = nullptr;
 };
 
+// the calling thread's current device is the caller's business: every entry point that has to
+// switch (an explicit stream device, the multi-device call) puts it back on the way out
+struct DeviceScope {
+    int saved = -1;
+    DeviceScope() { if (cudaGetDevice(&saved) != cudaSuccess) { saved = -1; cudaGetLastError(); } }
+    ~DeviceScope() { if (saved >= 0) { cudaSetDevice(saved); } }
+};
+
 static void slot_free(Slot& s) {
     if (s.stream) { cudaStreamSynchronize(s.stream); }
     cudaFree(s.d_data); cudaFree(s.d_table); cudaFree(s.d_tokens); cudaFree(s.d_len);
-    cudaFree(s.d_dist); cudaFree(s.d_work); cudaFree(s.d_result);
+    cudaFree(s.d_dist); cudaFree(s.d_work); cudaFree(s.d_mwork); cudaFree(s.d_result);
     cudaFreeHost(s.h_result); cudaFreeHost(s.h_tokens);
     if (s.done) { cudaEventDestroy(s.done); }
+    if (s.parsed) { cudaEventDestroy(s.parsed); }
     if (s.stream) { cudaStreamDestroy(s.stream); }
     s = Slot();
 }
 
-static int slot_alloc(Slot& s, int device, size_t chunk, uint32_t max_len, uint32_t max_dist, bool tokens) {
-    s.device = device; s.cap_chunk = chunk; s.cap_len = max_len; s.cap_dist = max_dist; s.cap_tokens = tokens;
+static int slot_alloc(Slot& s, int device, size_t chunk, uint32_t max_len, uint32_t max_dist, int mode) {
+    s.device = device; s.cap_chunk = chunk; s.cap_len = max_len; s.cap_dist = max_dist; s.cap_mode = mode;
     CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
-    CU(cudaMalloc(&s.d_data, (size_t)max_dist + chunk + max_len + 64));
+    CU(cudaEventCreateWithFlags(&s.parsed, cudaEventDisableTiming));
+    const size_t data_bytes = (size_t)max_dist + chunk + max_len + 64;
+    CU(cudaMalloc(&s.d_data, data_bytes));
     CU(cudaMalloc(&s.d_table, chunk * 4));
+    CU(cudaMalloc(&s.d_mwork, sqz_gpu_match_workspace(chunk)));
     CU(cudaMalloc(&s.d_result, 16));
     CU(cudaHostAlloc(&s.h_result, 16, cudaHostAllocDefault));
-    if (tokens) {
-        CU(cudaMalloc(&s.d_tokens, chunk * 4));
+    s.device_bytes = data_bytes + chunk * 4 + sqz_gpu_match_workspace(chunk);
+    if (mode != kModeTable) {
+        CU(cudaMalloc(&s.d_tokens, chunk * 4 + 16));
         CU(cudaMalloc(&s.d_work, parse::workspace(chunk)));
-        CU(cudaHostAlloc(&s.h_tokens, chunk * 4, cudaHostAllocDefault));
+        s.device_bytes += chunk * 4 + parse::workspace(chunk);
+        if (mode == kModeTokensPinned) {
+            CU(cudaHostAlloc(&s.h_tokens, chunk * 4 + 16, cudaHostAllocDefault));
+            s.pinned_bytes = chunk * 4 + 16;
+        }
     } else {
         CU(cudaMalloc(&s.d_len, chunk * 2));
         CU(cudaMalloc(&s.d_dist, chunk * 2));
+        s.device_bytes += chunk * 4;
     }
     return 0;
 }
 
 // Allocating and freeing gigabytes of device and pinned memory per call costs more than the
 // search of a small input and stalls the device; finished calls park their slots here and the
-// next call with the same shape takes them back.  sqz_gpu_release() frees the parked slots.
+// next call with the same shape takes them back.  At most kMaxParked slots and kMaxParkedBytes
+// of device + pinned memory stay parked (oldest out first); sqz_gpu_release() frees them all.
 static std::mutex g_park_mu;
 static std::vector<Slot> g_parked;
 constexpr size_t kMaxParked = 4;
+constexpr size_t kMaxParkedBytes = (size_t)3 << 30;
 
-static int slot_take(Slot& s, int device, size_t chunk, uint32_t max_len, uint32_t max_dist, bool tokens) {
+static int slot_take(Slot& s, int device, size_t chunk, uint32_t max_len, uint32_t max_dist, int mode) {
     // round the capacity up to a power of two (>= 1 MiB) so that calls of similar size share slots
     size_t cap = (size_t)1 << 20;
     while (cap < chunk) { cap <<= 1; }
@@ -858,7 +1010,7 @@ static int slot_take(Slot& s, int device, size_t chunk, uint32_t max_len, uint32
         std::lock_guard<std::mutex> lk(g_park_mu);
         for (size_t k = 0; k < g_parked.size(); k++) {
             const Slot& c = g_parked[k];
-            if (c.device == device && c.cap_tokens == tokens && c.cap_chunk >= chunk &&
+            if (c.device == device && c.cap_mode == mode && c.cap_chunk >= chunk &&
                 c.cap_chunk <= 4 * chunk && c.cap_len >= max_len && c.cap_dist >= max_dist) {
                 s = c;
                 g_parked.erase(g_parked.begin() + (long)k);
@@ -867,7 +1019,7 @@ static int slot_take(Slot& s, int device, size_t chunk, uint32_t max_len, uint32
             }
         }
     }
-    int r = slot_alloc(s, device, chunk, max_len, max_dist, tokens);
+    int r = slot_alloc(s, device, chunk, max_len, max_dist, mode);
     if (r != 0) { slot_free(s); }
     return r;
 }
@@ -875,14 +1027,20 @@ static int slot_take(Slot& s, int device, size_t chunk, uint32_t max_len, uint32
 static void slot_give_back(Slot& s) {
     if (s.stream == nullptr) { s = Slot(); return; }
     cudaStreamSynchronize(s.stream);
-    Slot victim;
+    std::vector<Slot> victims;
     {
         std::lock_guard<std::mutex> lk(g_park_mu);
         g_parked.push_back(s);
-        if (g_parked.size() > kMaxParked) { victim = g_parked.front(); g_parked.erase(g_parked.begin()); }
+        size_t total = 0;
+        for (const Slot& c : g_parked) { total += c.device_bytes + c.pinned_bytes; }
+        while (!g_parked.empty() && (g_parked.size() > kMaxParked || total > kMaxParkedBytes)) {
+            total -= g_parked.front().device_bytes + g_parked.front().pinned_bytes;
+            victims.push_back(g_parked.front());
+            g_parked.erase(g_parked.begin());
+        }
     }
     s = Slot();
-    if (victim.stream != nullptr) { cudaSetDevice(victim.device); slot_free(victim); }
+    for (Slot& v : victims) { cudaSetDevice(v.device); slot_free(v); }
 }
 
 extern "C" void sqz_gpu_release(void) {
@@ -891,10 +1049,9 @@ extern "C" void sqz_gpu_release(void) {
         std::lock_guard<std::mutex> lk(g_park_mu);
         all.swap(g_parked);
     }
-    int cur = 0;
-    cudaGetDevice(&cur);
+    DeviceScope keep;
     for (Slot& c : all) { cudaSetDevice(c.device); slot_free(c); }
-    cudaSetDevice(cur);
+    pool_release_all();
 }
 
 // device < 0 = the calling thread's current device
@@ -926,9 +1083,9 @@ static int stream_launch_next(sqz_gpu_stream* st, uint16_t* len_out, uint16_t* d
     CU(cudaMemcpyAsync(s.d_data, st->data + first - back, back + n + ahead,
                        cudaMemcpyHostToDevice, s.stream));
     const uint8_t* d_shard = s.d_data + back;
-    if (int r = sqz_gpu_match_table_device(d_shard, back, n, ahead, st->min_len, st->max_len,
-                                           st->max_dist, s.d_table, s.stream)) { return r; }
-    if (st->want_tokens) {
+    if (int r = sqz_gpu_match_table_device_ws(d_shard, back, n, ahead, st->min_len, st->max_len,
+                                              st->max_dist, s.d_table, s.d_mwork, s.stream)) { return r; }
+    if (st->mode != kModeTable) {
         const uint32_t* d_entry = nullptr;
         if (st->prev_result != nullptr) {
             CU(cudaStreamWaitEvent(s.stream, st->prev_parsed, 0));
@@ -937,14 +1094,17 @@ static int stream_launch_next(sqz_gpu_stream* st, uint16_t* len_out, uint16_t* d
         if (int r = parse_launch(d_shard, s.d_table, n, d_entry, 0, st->min_len, st->max_len,
                                  s.d_tokens, n, s.d_work, s.d_result, s.stream, st->symbols)) { return r; }
         CU(cudaMemcpyAsync(s.h_result, s.d_result, 16, cudaMemcpyDeviceToHost, s.stream));
-        if (st->prev_parsed == nullptr) {
-            CU(cudaEventCreateWithFlags(&st->prev_parsed, cudaEventDisableTiming));
-        }
-        CU(cudaEventRecord(st->prev_parsed, s.stream));
+        CU(cudaEventRecord(s.parsed, s.stream));
+        st->prev_parsed = s.parsed;
         st->prev_result = s.d_result;
-        // the tokens follow right away, all n slots of them (the count is only known on the device):
-        // the copy engine is idle anyway and the consumer finds them in pinned memory when it asks
-        CU(cudaMemcpyAsync(s.h_tokens, s.d_tokens, n * 4, cudaMemcpyDeviceToHost, s.stream));
+        if (st->mode == kModeTokensPinned) {
+            // the tokens follow right away, exactly as many as there are: the consumer finds them
+            // in pinned memory when it asks
+            const unsigned grid = (unsigned)std::min<size_t>((n / 4 + 255) / 256 + 1, (size_t)sm_count() * 4);
+            tokens_to_host<<<grid, 256, 0, s.stream>>>(s.d_tokens, s.d_result, s.h_tokens);
+            LAUNCHED("tokens_to_host");
+        }
+        // kModeTokensDirect: the caller copies count x 4 bytes to their final place once it knows the count
     } else {
         if (int r = sqz_gpu_unpack_table_device(s.d_table, n, s.d_len, s.d_dist, s.stream)) { return r; }
         CU(cudaMemcpyAsync(len_out + first, s.d_len, n * 2, cudaMemcpyDeviceToHost, s.stream));
@@ -959,14 +1119,14 @@ static int stream_launch_next(sqz_gpu_stream* st, uint16_t* len_out, uint16_t* d
 
 // Token mode feeds a host consumer chunk by chunk: smaller chunks overlap better.
 // Table mode only streams: larger chunks waste less on the last wave of tiles.
-static size_t default_chunk(size_t bytes, bool tokens) {
-    const size_t kDefault = tokens ? (size_t)32 << 20 : (size_t)128 << 20;
+static size_t default_chunk(size_t bytes, bool consumer) {
+    const size_t kDefault = consumer ? (size_t)32 << 20 : (size_t)128 << 20;
     return std::max<size_t>(std::min(bytes, kDefault), 1);
 }
 
 static int stream_open(sqz_gpu_stream** out, int device, const uint8_t* data, size_t bytes,
                        uint32_t window, uint32_t min_len, uint32_t max_len, uint32_t max_dist,
-                       size_t chunk, bool tokens) {
+                       size_t chunk, int mode) {
     *out = nullptr;
     if (int r = check_rules(min_len, max_len, max_dist)) { return r; }
     if (window == 0 || (window & (window - 1)) != 0 || max_dist > window) {
@@ -980,13 +1140,13 @@ static int stream_open(sqz_gpu_stream** out, int device, const uint8_t* data, si
     st->data = data;
     st->bytes = bytes;
     st->min_len = min_len; st->max_len = max_len; st->max_dist = max_dist;
-    st->chunk = chunk ? chunk : default_chunk(bytes, tokens);
-    st->want_tokens = tokens;
+    st->chunk = chunk ? chunk : default_chunk(bytes, mode == kModeTokensPinned);
+    st->mode = mode;
     // token streams with the default chunking start with short chunks: 2, 4, 8, 16 MiB, then 32 MiB
-    if (tokens && chunk == 0 && st->chunk > ((size_t)2 << 20)) { st->ramp = (size_t)2 << 20; }
+    if (mode == kModeTokensPinned && chunk == 0 && st->chunk > ((size_t)2 << 20)) { st->ramp = (size_t)2 << 20; }
     const int slots = bytes > (st->ramp ? st->ramp : st->chunk) ? 2 : 1;
     for (int k = 0; k < slots && bytes > 0; k++) {
-        if (int r = slot_take(st->slot[k], device, st->chunk, max_len, max_dist, tokens)) {
+        if (int r = slot_take(st->slot[k], device, st->chunk, max_len, max_dist, mode)) {
             sqz_gpu_stream_close(st);
             return r;
         }
@@ -1004,8 +1164,9 @@ extern "C" int sqz_gpu_stream_open(sqz_gpu_stream** st, int device, const uint8_
     if (flags & SQZ_GPU_STREAM_SYMBOLS) {
         if (int r = check_symbol_rules(min_len, max_len, max_dist)) { return r; }
     }
+    DeviceScope keep;
     if (int r = stream_open(st, device, data, bytes, window, min_len, max_len, max_dist,
-                            chunk_bytes, true)) { return r; }
+                            chunk_bytes, kModeTokensPinned)) { return r; }
     (*st)->symbols = (flags & SQZ_GPU_STREAM_SYMBOLS) != 0;
     if (bytes > 0) {
         if (int r = stream_launch_next(*st, nullptr, nullptr)) {
@@ -1022,6 +1183,7 @@ extern "C" int sqz_gpu_stream_next(sqz_gpu_stream* st, const uint32_t** tokens, 
     *tokens = nullptr;
     *count = 0;
     if (st->delivered >= st->bytes) { return 0; }
+    DeviceScope keep;
     CU(cudaSetDevice(st->device));
     // keep the device busy: the slot the caller has just finished reading is free now
     if (st->launched < st->bytes) {
@@ -1041,35 +1203,63 @@ extern "C" int sqz_gpu_stream_next(sqz_gpu_stream* st, const uint32_t** tokens, 
 
 extern "C" void sqz_gpu_stream_close(sqz_gpu_stream* st) {
     if (st == nullptr) { return; }
+    DeviceScope keep;
     cudaSetDevice(st->device);
     slot_give_back(st->slot[0]);
     slot_give_back(st->slot[1]);
-    if (st->prev_parsed) { cudaEventDestroy(st->prev_parsed); }
     delete st;
 }
 
+// One-shot token call: the chunks' tokens go straight from device memory to their final place in
+// the caller's buffer, count x 4 bytes each (a pinned destination takes them by DMA while the next
+// chunk is searched; a pageable one through the driver's staging).  Nothing consumes the chunks
+// on the way, so the larger streaming chunk is used.
 extern "C" int sqz_gpu_tokens(const uint8_t* data, size_t bytes, uint32_t window,
                               uint32_t min_len, uint32_t max_len, uint32_t max_dist,
                               uint32_t* tokens_out, size_t tokens_cap, size_t* n_tokens) {
     if (n_tokens == nullptr) { return fail(EINVAL, "null n_tokens"); }
     *n_tokens = 0;
     sqz_gpu_stream* st = nullptr;
-    // one-shot call: nothing consumes the chunks on the way, so use the larger streaming chunk
-    if (int r = sqz_gpu_stream_open(&st, -1, data, bytes, window, min_len, max_len, max_dist,
-                                    default_chunk(bytes, false), 0)) {
+    DeviceScope keep;
+    if (int r = stream_open(&st, -1, data, bytes, window, min_len, max_len, max_dist, 0, kModeTokensDirect)) {
         return r;
     }
     size_t total = 0;
     int rc = 0;
-    for (;;) {
-        const uint32_t* t = nullptr;
-        size_t c = 0;
-        rc = sqz_gpu_stream_next(st, &t, &c);
-        if (rc != 0 || c == 0) { break; }
-        if (total < tokens_cap && tokens_out != nullptr) {
-            memcpy(tokens_out + total, t, std::min(c, tokens_cap - total) * 4);
+    if (bytes > 0) { rc = stream_launch_next(st, nullptr, nullptr); }
+    while (rc == 0 && st->delivered < st->bytes) {
+        Slot& s = st->slot[st->read_slot];
+        // the other slot is free (its copy was queued before its `done`): keep the device busy
+        if (st->launched < st->bytes) {
+            Slot& o = st->slot[st->next_slot];
+            if (o.busy) {
+                cudaError_t ce = cudaEventSynchronize(o.done);
+                if (ce != cudaSuccess) { rc = fail(cuda_code(ce), "cudaEventSynchronize", ce); break; }
+                o.busy = false;
+            }
+            rc = stream_launch_next(st, nullptr, nullptr);
+            if (rc != 0) { break; }
         }
+        cudaError_t ce = cudaEventSynchronize(s.parsed);
+        if (ce != cudaSuccess) { rc = fail(cuda_code(ce), "cudaEventSynchronize", ce); break; }
+        const size_t c = (size_t)s.h_result[0];
+        if (c > s.n) { rc = fail(EIO, "parse produced more tokens than positions"); break; }
+        if (tokens_out != nullptr && total < tokens_cap) {
+            ce = cudaMemcpyAsync(tokens_out + total, s.d_tokens, std::min(c, tokens_cap - total) * 4,
+                                 cudaMemcpyDeviceToHost, s.stream);
+            if (ce != cudaSuccess) { rc = fail(cuda_code(ce), "cudaMemcpyAsync", ce); break; }
+        }
+        ce = cudaEventRecord(s.done, s.stream);      // the slot is free again once the copy has landed
+        if (ce != cudaSuccess) { rc = fail(cuda_code(ce), "cudaEventRecord", ce); break; }
         total += c;
+        st->delivered = s.first + s.n;
+        st->read_slot ^= 1;
+    }
+    for (int k = 0; k < 2; k++) {
+        if (st->slot[k].stream != nullptr) {
+            cudaError_t ce = cudaStreamSynchronize(st->slot[k].stream);
+            if (ce != cudaSuccess && rc == 0) { rc = fail(cuda_code(ce), "cudaStreamSynchronize", ce); }
+        }
     }
     sqz_gpu_stream_close(st);
     *n_tokens = total;
@@ -1084,7 +1274,8 @@ extern "C" int sqz_gpu_match_table(const uint8_t* data, size_t bytes, uint32_t w
         return fail(EINVAL, "null output");
     }
     sqz_gpu_stream* st = nullptr;
-    if (int r = stream_open(&st, -1, data, bytes, window, min_len, max_len, max_dist, 0, false)) {
+    DeviceScope keep;
+    if (int r = stream_open(&st, -1, data, bytes, window, min_len, max_len, max_dist, 0, kModeTable)) {
         return r;
     }
     int rc = 0;
@@ -1105,6 +1296,236 @@ extern "C" int sqz_gpu_match_table(const uint8_t* data, size_t bytes, uint32_t w
     }
     sqz_gpu_stream_close(st);
     return rc;
+}
+
+// ---------------------------------------------------------------------------
+// several devices, one call.  The input is cut into contiguous shards,
+// one per device, each uploaded with its look-back and look-ahead halo, so the match tables need
+// no exchange at all.  The greedy parse has one scalar dependency per seam -- where the previous
+// shard's last token ends (squeeze.h:377-394: i += len) -- which is resolved without a
+// collective: every device composes its shard's exit map (overshoot for every possible entry,
+// 1 KiB), the host chains the maps (one lookup per seam), every device then emits its tokens from
+// its true entry, and the token arrays are concatenated in shard order by plain copies sized by
+// their counts: device -> host when tokens_out is host memory, peer-to-peer (cudaMemcpyPeerAsync
+// over NVLink) when it is device memory.
+// ---------------------------------------------------------------------------
+struct MultiPart {
+    int device = 0;
+    size_t first = 0, n = 0, back = 0, ahead = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t mapped = nullptr, parsed = nullptr;
+    uint8_t* d_data = nullptr;
+    uint32_t* d_table = nullptr;
+    uint32_t* d_tokens = nullptr;
+    void* d_work = nullptr;
+    void* d_mwork = nullptr;
+    uint16_t* d_map = nullptr;
+    uint64_t* d_result = nullptr;
+    uint16_t* h_map = nullptr;        // pinned: exit map
+    uint64_t* h_result = nullptr;     // pinned: count, overshoot
+};
+
+static void multi_free(MultiPart& p) {
+    cudaSetDevice(p.device);
+    if (p.stream) { cudaStreamSynchronize(p.stream); }
+    cudaFree(p.d_data); cudaFree(p.d_table); cudaFree(p.d_tokens); cudaFree(p.d_work);
+    cudaFree(p.d_mwork); cudaFree(p.d_map); cudaFree(p.d_result);
+    cudaFreeHost(p.h_map); cudaFreeHost(p.h_result);
+    if (p.mapped) { cudaEventDestroy(p.mapped); }
+    if (p.parsed) { cudaEventDestroy(p.parsed); }
+    if (p.stream) { cudaStreamDestroy(p.stream); }
+    p = MultiPart();
+}
+
+static int multi_alloc(MultiPart& p) {
+    CU(cudaSetDevice(p.device));
+    CU(cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&p.mapped, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&p.parsed, cudaEventDisableTiming));
+    CU(cudaMalloc(&p.d_data, p.back + p.n + p.ahead + 64));
+    CU(cudaMalloc(&p.d_table, std::max<size_t>(p.n, 1) * 4));
+    CU(cudaMalloc(&p.d_tokens, std::max<size_t>(p.n, 1) * 4 + 16));
+    CU(cudaMalloc(&p.d_work, parse::workspace(std::max<size_t>(p.n, 1))));
+    CU(cudaMalloc(&p.d_mwork, sqz_gpu_match_workspace(p.n)));
+    CU(cudaMalloc(&p.d_map, parse::kMapStride * 2));
+    CU(cudaMalloc(&p.d_result, 16));
+    CU(cudaHostAlloc(&p.h_map, parse::kMapStride * 2, cudaHostAllocDefault));
+    CU(cudaHostAlloc(&p.h_result, 16, cudaHostAllocDefault));
+    return 0;
+}
+
+static int multi_run(std::vector<MultiPart>& parts, const uint8_t* data, uint32_t min_len, uint32_t max_len,
+                     uint32_t max_dist, uint32_t* tokens_out, size_t tokens_cap, bool out_on_device,
+                     int out_device, size_t* n_tokens, size_t* shard_tokens) {
+    // phase A on every device at once: upload, match table, composed exit map
+    for (MultiPart& p : parts) {
+        if (p.n == 0) { continue; }
+        if (int r = multi_alloc(p)) { return r; }
+        CU(cudaMemcpyAsync(p.d_data, data + p.first - p.back, p.back + p.n + p.ahead, cudaMemcpyHostToDevice, p.stream));
+        const uint8_t* d_shard = p.d_data + p.back;
+        if (int r = sqz_gpu_match_table_device_ws(d_shard, p.back, p.n, p.ahead, min_len, max_len, max_dist,
+                                                  p.d_table, p.d_mwork, p.stream)) { return r; }
+        if (int r = sqz_gpu_parse_exit_map_device(p.d_table, p.n, min_len, max_len, p.d_work, p.d_map, p.stream)) { return r; }
+        CU(cudaMemcpyAsync(p.h_map, p.d_map, (size_t)max_len * 2, cudaMemcpyDeviceToHost, p.stream));
+        CU(cudaEventRecord(p.mapped, p.stream));
+    }
+    // seams: shard g+1 is entered where shard g's last token ends
+    uint32_t entry = 0;
+    for (MultiPart& p : parts) {
+        if (p.n == 0) { continue; }
+        CU(cudaSetDevice(p.device));
+        CU(cudaEventSynchronize(p.mapped));
+        const uint8_t* d_shard = p.d_data + p.back;
+        if (entry >= max_len) { return fail(EIO, "seam entry out of range"); }
+        const uint32_t next_entry = p.h_map[entry];
+        if (int r = parse_launch(d_shard, p.d_table, p.n, nullptr, entry, min_len, max_len, p.d_tokens, p.n,
+                                 p.d_work, p.d_result, p.stream)) { return r; }
+        CU(cudaMemcpyAsync(p.h_result, p.d_result, 16, cudaMemcpyDeviceToHost, p.stream));
+        CU(cudaEventRecord(p.parsed, p.stream));
+        entry = next_entry;
+    }
+    // concatenation in shard order, every copy sized by its shard's count
+    size_t total = 0;
+    for (size_t g = 0; g < parts.size(); g++) {
+        MultiPart& p = parts[g];
+        size_t c = 0;
+        if (p.n != 0) {
+            CU(cudaSetDevice(p.device));
+            CU(cudaEventSynchronize(p.parsed));
+            c = (size_t)p.h_result[0];
+            if (c > p.n) { return fail(EIO, "parse produced more tokens than positions"); }
+            if (tokens_out != nullptr && total < tokens_cap) {
+                const size_t take = std::min(c, tokens_cap - total);
+                if (out_on_device) {
+                    CU(cudaMemcpyPeerAsync(tokens_out + total, out_device, p.d_tokens, p.device, take * 4, p.stream));
+                } else {
+                    CU(cudaMemcpyAsync(tokens_out + total, p.d_tokens, take * 4, cudaMemcpyDeviceToHost, p.stream));
+                }
+            }
+        }
+        if (shard_tokens != nullptr) { shard_tokens[g] = c; }
+        total += c;
+    }
+    for (MultiPart& p : parts) {
+        if (p.n == 0) { continue; }
+        CU(cudaSetDevice(p.device));
+        CU(cudaStreamSynchronize(p.stream));
+    }
+    *n_tokens = total;
+    if (entry != 0) { return fail(EIO, "the parse does not end at the end of the input"); }
+    return total > tokens_cap ? fail(E2BIG, "token buffer too small") : 0;
+}
+
+extern "C" int sqz_gpu_tokens_multi(const int* devices, int n_devices, const uint8_t* data, size_t bytes,
+                                    uint32_t window, uint32_t min_len, uint32_t max_len, uint32_t max_dist,
+                                    uint32_t* tokens_out, size_t tokens_cap, size_t* n_tokens,
+                                    size_t* shard_tokens) {
+    if (n_tokens == nullptr) { return fail(EINVAL, "null n_tokens"); }
+    *n_tokens = 0;
+    if (devices == nullptr || n_devices < 1 || n_devices > kMaxDevices) { return fail(EINVAL, "bad device list"); }
+    if (int r = check_rules(min_len, max_len, max_dist)) { return r; }
+    if (window == 0 || (window & (window - 1)) != 0 || max_dist > window) {
+        return fail(EINVAL, "window must be a power of two and max_dist <= window");
+    }
+    if (data == nullptr && bytes != 0) { return fail(EINVAL, "null input"); }
+    int count = 0;
+    cudaError_t ce = cudaGetDeviceCount(&count);
+    if (ce != cudaSuccess || count == 0) {
+        return fail(ENODEV, "no CUDA device: the match search has no CPU fallback", ce);
+    }
+    for (int g = 0; g < n_devices; g++) {
+        // (a device may be listed more than once: its shards then share it, each on its own stream)
+        if (devices[g] < 0 || devices[g] >= count) { return fail(ENODEV, "no such CUDA device"); }
+    }
+    DeviceScope keep;
+    // where do the tokens go: host memory, or device memory (then peer copies gather them there)
+    bool out_on_device = false;
+    int out_device = devices[0];
+    if (tokens_out != nullptr) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, tokens_out) == cudaSuccess && at.type == cudaMemoryTypeDevice) {
+            out_on_device = true;
+            out_device = at.device;
+        }
+        cudaGetLastError();
+    }
+    if (out_on_device) {
+        for (int g = 0; g < n_devices; g++) {
+            if (devices[g] == out_device) { continue; }
+            int can = 0;
+            CU(cudaDeviceCanAccessPeer(&can, devices[g], out_device));
+            if (can) {
+                CU(cudaSetDevice(devices[g]));
+                ce = cudaDeviceEnablePeerAccess(out_device, 0);
+                if (ce != cudaSuccess && ce != cudaErrorPeerAccessAlreadyEnabled) { return fail(cuda_code(ce), "cudaDeviceEnablePeerAccess", ce); }
+                cudaGetLastError();
+            }   // without peer access cudaMemcpyPeerAsync still works, staged through the host
+        }
+    }
+    std::vector<MultiPart> parts((size_t)n_devices);
+    const size_t base = bytes / (size_t)n_devices, extra = bytes % (size_t)n_devices;
+    size_t first = 0;
+    for (int g = 0; g < n_devices; g++) {
+        MultiPart& p = parts[(size_t)g];
+        p.device = devices[g];
+        p.first = first;
+        p.n = base + ((size_t)g < extra ? 1 : 0);
+        p.back = std::min<size_t>(first, max_dist);
+        p.ahead = std::min<size_t>(bytes - (first + p.n), max_len);
+        first += p.n;
+    }
+    const int rc = multi_run(parts, data, min_len, max_len, max_dist, tokens_out, tokens_cap, out_on_device,
+                             out_device, n_tokens, shard_tokens);
+    for (MultiPart& p : parts) { if (p.stream != nullptr || p.d_data != nullptr) { multi_free(p); } }
+    return rc;
+}
+
+// ---------------------------------------------------------------------------
+// one process per device (torchrun-style jobs): the same gather needs the destination buffer of
+// one process mapped into the others.  Plain CUDA IPC, no collective library.
+// ---------------------------------------------------------------------------
+extern "C" int sqz_gpu_device_alloc(void** d_ptr, size_t bytes) {
+    if (d_ptr == nullptr) { return fail(EINVAL, "null argument"); }
+    *d_ptr = nullptr;
+    CU(cudaMalloc(d_ptr, bytes ? bytes : 1));
+    return 0;
+}
+
+extern "C" void sqz_gpu_device_free(void* d_ptr) {
+    if (d_ptr != nullptr) { cudaFree(d_ptr); }
+}
+
+extern "C" int sqz_gpu_ipc_export(const void* d_ptr, uint8_t handle[SQZ_GPU_IPC_HANDLE_BYTES]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == SQZ_GPU_IPC_HANDLE_BYTES, "IPC handle size");
+    if (d_ptr == nullptr || handle == nullptr) { return fail(EINVAL, "null argument"); }
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, const_cast<void*>(d_ptr)));
+    memcpy(handle, &h, sizeof(h));
+    return 0;
+}
+
+extern "C" int sqz_gpu_ipc_open(const uint8_t handle[SQZ_GPU_IPC_HANDLE_BYTES], void** d_ptr) {
+    if (d_ptr == nullptr || handle == nullptr) { return fail(EINVAL, "null argument"); }
+    *d_ptr = nullptr;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    CU(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+extern "C" int sqz_gpu_ipc_close(void* d_ptr) {
+    if (d_ptr == nullptr) { return 0; }
+    CU(cudaIpcCloseMemHandle(d_ptr));
+    return 0;
+}
+
+// copy `count` tokens of this process's device into a (possibly IPC-mapped, possibly remote)
+// device buffer at token offset `at`: the per-shard step of the gather
+extern "C" int sqz_gpu_put_tokens(uint32_t* d_dst, size_t at, const uint32_t* d_tokens, size_t count, void* stream) {
+    if (count == 0) { return 0; }
+    if (d_dst == nullptr || d_tokens == nullptr) { return fail(EINVAL, "null argument"); }
+    CU(cudaMemcpyAsync(d_dst + at, d_tokens, count * 4, cudaMemcpyDefault, (cudaStream_t)stream));
+    return 0;
 }
 
 // ---------------------------------------------------------------------------
@@ -1145,7 +1566,7 @@ extern "C" int sqz_gpu_expand_tokens_device(const uint32_t* d_tokens, size_t n_t
     expand::place_tokens<<<(unsigned)blocks, 256, 0, s>>>(d_tokens, n_tokens, block_off, d_out, hop,
                                                         (uint64_t)bytes, d_bad);
     LAUNCHED("expand_place_tokens");
-    const unsigned grid = 148 * 8;
+    const unsigned grid = (unsigned)sm_count() * 8;
     for (int round = 0; round < 40; round++) {       // a chain halves its hop count every round
         CU(cudaMemsetAsync(d_changed, 0, 4, s));
         expand::double_hops<<<grid, 256, 0, s>>>(hop, (uint64_t)bytes, d_changed);

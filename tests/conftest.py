@@ -32,10 +32,10 @@ def golden():
 
 @pytest.fixture(scope="session")
 def inputs():
-    """name -> uint8 array: the reference tests' synthetic vectors + its six data files."""
+    """name -> uint8 array: the reference tests' synthetic vectors, its six data files and csrc.cat."""
     from sqz_b200 import corpus
     d = {k: np.frombuffer(v, dtype=np.uint8) for k, v in corpus.kat_inputs().items()}
-    d.update(corpus.fixtures())
+    d.update(corpus.all_files())
     return d
 
 

@@ -12,6 +12,7 @@ Writes
                    checked against the reference on the same input.
 """
 import hashlib
+import io
 import json
 import os
 import sys
@@ -22,7 +23,13 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
-REF_TEST = "/root/reference/test"
+REF = "/root/reference"
+REF_TEST = REF + "/test"
+# csrc.cat stands in for the missing test/sqlite3.c
+CSRC_CAT = ["src/sqz.c", "shl/sqz/sqz.h", "test.c", "bst.c", "shl.c", "inc/rt/rt.h", "inc/rt/rt_generics.h",
+            "inc/rt/rt_generics_test.h", "inc/rt/ustd.h", "inc/rt/fileio.h", "inc/sqz/sqz.h",
+            "attic/map_experiment/bitstream.h", "attic/map_experiment/file.h", "attic/map_experiment/huffman.h",
+            "attic/map_experiment/map.h", "attic/map_experiment/squeeze.h", "attic/map_experiment/test.c"]
 
 from oracle import Oracle, Reference, build  # noqa: E402
 from sqz_b200 import corpus  # noqa: E402
@@ -39,6 +46,11 @@ def pack():
     with tarfile.open(os.path.join(HERE, "fixtures.tar.xz"), "w:xz", preset=9) as tf:
         for n in corpus.ORDER:
             tf.add(os.path.join(REF_TEST, n), arcname=n, filter=reset)
+        cat = b"".join(open(os.path.join(REF, f), "rb").read() for f in CSRC_CAT)
+        assert len(cat) == 179548, len(cat)
+        ti = reset(tarfile.TarInfo("csrc.cat"))
+        ti.size = len(cat)
+        tf.addfile(ti, io.BytesIO(cat))
 
 
 def blob_sha1(b: bytes) -> str:
@@ -50,7 +62,7 @@ def main():
     pack()
     o, r = Oracle.get(), Reference.get()
     inputs = {k: np.frombuffer(v, dtype=np.uint8) for k, v in corpus.kat_inputs().items()}
-    inputs.update(corpus.fixtures())
+    inputs.update(corpus.all_files())
     out = {"_about": "made by tests/golden/make_golden.py from oracle/_ref (unmodified reference) "
                      "and oracle/sqz_oracle.c; FNV-1a-64 digests, hex",
            "inputs": {}}

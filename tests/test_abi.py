@@ -54,7 +54,7 @@ def test_struct_layout_matches_the_header(tmp_path):
 
 def test_version_and_device_probe():
     L = _lib.load()
-    assert L.sqz_gpu_abi_version() == 2
+    assert L.sqz_gpu_abi_version() == 3
     assert L.sqz_gpu_device_count() >= 0
     assert L.sqz_gpu_parse_workspace(1 << 20) > 0
     assert L.sqz_gpu_select_kernel(7) != 0 and L.sqz_gpu_select_kernel(0) == 0

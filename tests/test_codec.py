@@ -342,7 +342,8 @@ def test_tokens_the_decoder_would_reject_are_einval(bad):
     assert e.value.errno == errno.EINVAL
 
 
-@pytest.mark.parametrize("bad", [256, 285, 511, 257 | 30 << 14, 0xFFFFFFFF])
+# 284 | 31 << 9 is bucket 27 with extra bits 31 = length 258, which the decoders reject (squeeze.h:529-545)
+@pytest.mark.parametrize("bad", [256, 285, 511, 257 | 30 << 14, 284 | 31 << 9, 0xFFFFFFFF])
 def test_words_that_are_not_symbol_words_are_einval(bad):
     with pytest.raises(sq.SqzError) as e:
         sq.encode_symbols(np.array([65, 66, 67, bad], np.uint32), 300, 15)
@@ -381,3 +382,30 @@ def test_compress_without_a_device_is_enodev():
     with pytest.raises(sq.SqzError) as e:
         sq.match_table(b"abcabcabc")
     assert e.value.errno == errno.ENODEV
+
+
+@pytest.mark.parametrize("names", [("hello", "abc40"), ("laozi.txt", "hello"), ("zeros4096", "laozi.txt"), ("lorem3", "lorem3")])
+def test_bitstream_position_after_decode_is_the_references(names, inputs, oracle):
+    """After sqz_decompress the bitstream stands where the reference's word-at-a-time reader would
+    (bitstream.h:65-95): `read` at the end of the stream's last word, whatever the decoder read ahead.
+    Two streams stored back to back decode one after the other from the same sqz_bitstream."""
+    L = _lib.load()
+    parts = [inputs[n] for n in names]
+    comps = [sq.encode_tokens(oracle_tokens(oracle, d, 15), d.size, 15) for d in parts]
+    buf = np.frombuffer(b"".join(comps) + bytes(64), np.uint8).copy()
+    bs = _bs(buf)
+    bs.bytes = buf.size
+    for d, comp in zip(parts, comps):
+        start = int(bs.read)
+        n, wb = C.c_uint64(), C.c_uint8()
+        L.sqz_read_header(C.byref(bs), C.byref(n), C.byref(wb))
+        assert bs.error == 0 and n.value == d.size and wb.value == 15
+        out = np.zeros(max(d.size, 1), np.uint8)
+        s = _lib.State()
+        L.sqz_init(C.byref(s))
+        L.sqz_decompress(C.byref(s), C.byref(bs), out.ctypes.data_as(_lib.u8p), d.size)
+        assert s.error == 0 and out[: d.size].tobytes() == d.tobytes()
+        assert int(bs.read) == start + len(comp), (names, int(bs.read), start, len(comp))
+        assert 0 <= bs.bits < 64
+        bs.bits = 0                     # the padding of the last word belongs to the stream just read
+        bs.b64 = 0

@@ -8,7 +8,8 @@ from conftest import fnv
 
 pytestmark = pytest.mark.gpu
 
-FILES = ["laozi.txt", "confucius.txt", "x64.elf", "arm64.elf", "mandrill.bmp", "mandrill.png"]
+# the reference's six test/ files + csrc.cat, the stand-in for BASELINE config 2's sqlite3.c
+FILES = ["laozi.txt", "confucius.txt", "x64.elf", "arm64.elf", "mandrill.bmp", "mandrill.png", "csrc.cat"]
 KATS = ["zeros4096", "pat1234x1024", "hello", "abc40", "lorem3", "empty", "one", "two", "aaa", "aaaa"]
 
 
@@ -50,7 +51,7 @@ def test_tokens_and_bitstream_golden(name, wb, inputs, golden, oracle):
     assert sq.decompress(comp) == d.tobytes()
 
 
-@pytest.mark.parametrize("name", ["hello", "laozi.txt", "arm64.elf"])
+@pytest.mark.parametrize("name", ["hello", "laozi.txt", "arm64.elf", "csrc.cat"])
 def test_reference_decoder_accepts_our_stream(name, inputs, reference):
     d = inputs[name]
     comp = sq.compress(d, 15)
@@ -59,3 +60,20 @@ def test_reference_decoder_accepts_our_stream(name, inputs, reference):
     # file mode = the same 64-bit words in host byte order
     a = np.frombuffer(comp, np.uint8).reshape(-1, 8)[:, ::-1].reshape(-1)
     assert a.tobytes() == comp_f
+
+
+def test_config_2_far_max_len_repeats(inputs, golden, oracle, reference):
+    """BASELINE config 2 (csrc.cat for sqlite3.c): 17 % of the positions reach max_len at a mean
+    distance of ~30,600 -- the reference's far early-out, squeeze.h:353.  Full table against the
+    brute-force oracle, element by element; token stream and bytes against the unmodified reference."""
+    d = inputs["csrc.cat"]
+    ln, ds = sq.match_table(d, 1 << 15)
+    oln, ods = oracle.match_table(d, 1 << 15)              # oracle A: the restated loop itself
+    bad = np.nonzero((ln != oln) | (ds != ods))[0]
+    assert bad.size == 0, (bad[:5], ln[bad[:5]], oln[bad[:5]], ds[bad[:5]], ods[bad[:5]])
+    far = (ln == 257) & (ds > 30000)
+    assert far.sum() > 0.15 * d.size                       # the case this input is here for
+    comp = sq.compress(d, 15)
+    assert comp == reference.compress(d, 15)
+    t = sq.tokens(d, 1 << 15)
+    assert (t == reference.tokens(comp)).all()

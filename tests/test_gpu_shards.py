@@ -103,7 +103,11 @@ def test_seam_hand_off_between_shards(world, oracle):
         words.append(sym.cpu().numpy().view(np.uint32))
     cat = np.concatenate(parts)
     assert cat.size == whole.size and (cat == whole).all()
-    # symbol words from the GPU == the host statement of squeeze.h:290-315 on the same tokens
+    # symbol words from the GPU, entropy-coded, == the bytes the reference's own encoder
+    # (squeeze_encode_len/pos/literal, squeeze.h:278-315) makes of the same token stream
+    from oracle import Reference
+    if Reference.available():
+        assert sq.encode_symbols(np.concatenate(words), total, 15) == Reference.get().encode_tokens(whole, total, 15)
     assert (np.concatenate(words) == sq.symbols_of_tokens(whole)).all()
 
 
@@ -124,6 +128,10 @@ def test_symbol_words_cover_every_bucket():
     sym, over = device.parse(dev, 0, t, data.size, 0, symbols=True)
     assert over == 0
     got = sym.cpu().numpy().view(np.uint32)
+    # pinned to the reference: the GPU's words through the coder == the reference's encoder on the tokens
+    from oracle import Reference
+    if Reference.available():
+        assert sq.encode_symbols(got, data.size, 15) == Reference.get().encode_tokens(whole, data.size, 15)
     want = sq.symbols_of_tokens(whole)
     assert got.size == want.size and (got == want).all()
     lens = set((whole[whole > 0xFFFF] >> 16).tolist())
@@ -264,3 +272,138 @@ def test_randomised_inputs_and_rules(seed, oracle, kernel):
     t = sq.tokens(d, window, mn, mx, md)
     ot, end = oracle.tokens_from_table(d, oln, ods, mn)
     assert end == n and t.size == ot.size and (t == ot).all()
+
+
+def _far_repeat_input(rng, n):
+    """Blocks of 4-12 KiB repeated at distances of 30,000-32,767 with a few defects, runs of 32
+    spaces and of one byte value in between: the far max_len early-out (squeeze.h:353) next to
+    thousands of near candidates that tie on their first bytes."""
+    out = []
+    size = 0
+    words = [b"    " * 8, b"\t\t", b"static ", b"const ", b"uint32_t ", b"return ", b";\n", b"if (", b") {\n", b"}\n"]
+    def filler(k):
+        parts, got = [], 0
+        while got < k:
+            w = words[int(rng.integers(0, len(words)))] if rng.random() < 0.7 else bytes(rng.integers(97, 123, int(rng.integers(1, 9)), dtype=np.uint8))
+            parts.append(w); got += len(w)
+        return np.frombuffer(b"".join(parts)[:k], np.uint8)
+    while size < n:
+        block = filler(int(rng.integers(4096, 12288)))
+        gap = int(rng.integers(30000, 32768)) - block.size
+        mid = filler(max(gap, 1)).copy()
+        if rng.random() < 0.5:
+            at = int(rng.integers(0, max(mid.size - 600, 1)))
+            mid[at:at + int(rng.integers(33, 600))] = 32 if rng.random() < 0.5 else 0
+        again = block.copy()
+        for at in rng.integers(0, block.size, int(rng.integers(0, 4))).tolist():
+            again[at] ^= 1
+        out += [block, mid, again]
+        size += 2 * block.size + mid.size
+    return np.concatenate(out)[:n].copy()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_far_repeats_fuzz(seed, oracle, kernel):
+    """Full table == oracle B on far-repeat inputs, == the brute-force loop on sampled positions."""
+    rng = np.random.default_rng(7000 + seed)
+    n = int(rng.choice([90000, 200000, 400000]))
+    d = _far_repeat_input(rng, n)
+    ln, ds = sq.match_table(d, 1 << 15)
+    oln, ods = oracle.match_table(d, 1 << 15, fast=True)
+    bad = np.nonzero((ln != oln) | (ds != ods))[0]
+    assert bad.size == 0, (seed, n, bad[:5], ln[bad[:5]], oln[bad[:5]], ds[bad[:5]], ods[bad[:5]])
+    assert ((ln == 257) & (ds >= 30000)).sum() > n // 20
+    for i in rng.integers(0, n, 300).tolist():
+        assert oracle.best(d, i, 1 << 15) == (int(ln[i]), int(ds[i])), i
+    t = sq.tokens(d)
+    ot, end = oracle.tokens_from_table(d, oln, ods)
+    assert end == n and t.size == ot.size and (t == ot).all()
+
+
+@pytest.mark.parametrize("mx,md", [(257, 32767), (64, 32767), (40, 5000), (300, 40000), (512, 65535)])
+def test_capped_inheritance_other_caps(mx, md, oracle):
+    """The far-repeat shortcut of phase 2 depends on max_len (its slack shrinks to max_len - 32)."""
+    rng = np.random.default_rng(mx * 7 + md)
+    d = _far_repeat_input(rng, 150000)
+    window = 1 << 16 if md > 32767 else 1 << 15
+    ln, ds = sq.match_table(d, window, 3, mx, md)
+    oln, ods = oracle.match_table(d, window, fast=True, min_len=3, max_len=mx, max_dist=md)
+    bad = np.nonzero((ln != oln) | (ds != ods))[0]
+    assert bad.size == 0, (mx, md, bad[:5], ln[bad[:5]], oln[bad[:5]], ds[bad[:5]], ods[bad[:5]])
+
+
+def test_symbol_mode_rejects_length_258():
+    """max_len 258 has a bucket but no decoder accepts it (squeeze.h:529-545): EINVAL at open time."""
+    import ctypes as C, errno
+    from sqz_b200 import _lib
+    L = _lib.load()
+    d = np.zeros(1000, np.uint8)
+    st = C.c_void_p()
+    rc = L.sqz_gpu_stream_open(C.byref(st), 0, d.ctypes.data_as(_lib.u8p), d.size, 1 << 15, 3, 258, 32767, 0, 1)
+    assert rc == errno.EINVAL
+    rc = L.sqz_gpu_stream_open(C.byref(st), 0, d.ctypes.data_as(_lib.u8p), d.size, 1 << 15, 3, 257, 32767, 0, 1)
+    assert rc == 0
+    L.sqz_gpu_stream_close(st)
+
+
+def test_calls_keep_the_current_device():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two devices")
+    torch.cuda.set_device(0)
+    sq.tokens_multi(corpus.fixtures()["laozi.txt"], [1])
+    assert torch.cuda.current_device() == 0
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+def test_tokens_multi_equals_single_device(world, inputs, oracle):
+    """sqz_gpu_tokens_multi: the input cut into `world` shards, every shard on a device (all on
+    device 0 when the box has fewer), seams chained, tokens concatenated == one parse of the whole."""
+    n_dev = torch.cuda.device_count()
+    devices = [g % n_dev for g in range(world)]           # fewer devices than shards: they share
+    for name in ["hello", "laozi.txt", "csrc.cat", "x64.elf"]:
+        d = inputs[name]
+        want = sq.tokens(d)
+        got, per = sq.tokens_multi(d, devices, return_shard_counts=True)
+        assert got.size == want.size and (got == want).all(), (name, world)
+        assert sum(per) == want.size and len(per) == world
+    d = corpus.synthetic(3 << 20, 3276897 - (1 << 20))
+    want = oracle.tokens_from_table(d, *oracle.match_table(d, 1 << 15, fast=True))[0]
+    got = sq.tokens_multi(d, devices)
+    assert got.size == want.size and (got == want).all()
+
+
+def test_tokens_multi_gathers_on_a_device():
+    """tokens_out in device memory: the shards' tokens are concatenated there by peer copies."""
+    import ctypes as C
+    from sqz_b200 import _lib
+    L = _lib.load()
+    n_dev = torch.cuda.device_count()
+    devices = list(range(min(n_dev, 4)))
+    d = corpus.synthetic(2 << 20, 12345)
+    want = sq.tokens(d)
+    out = torch.zeros(d.size, dtype=torch.int32, device="cuda:0")
+    n = C.c_size_t()
+    devs = (C.c_int * len(devices))(*devices)
+    rc = L.sqz_gpu_tokens_multi(devs, len(devices), d.ctypes.data_as(_lib.u8p), d.size, 1 << 15, 3, 257, 32767,
+                                out.data_ptr(), out.numel(), C.byref(n), None)
+    assert rc == 0, L.sqz_gpu_last_error()
+    got = out[: n.value].cpu().numpy().view(np.uint32)
+    assert got.size == want.size and (got == want).all()
+
+
+def test_tokens_multi_bad_arguments():
+    import ctypes as C, errno
+    from sqz_b200 import _lib
+    L = _lib.load()
+    d = np.zeros(100, np.uint8)
+    out = np.zeros(100, np.uint32)
+    n = C.c_size_t()
+    for devs in ([], [99], [0, -1]):
+        arr = (C.c_int * max(len(devs), 1))(*devs)
+        rc = L.sqz_gpu_tokens_multi(arr, len(devs), d.ctypes.data_as(_lib.u8p), d.size, 1 << 15, 3, 257, 32767,
+                                    out.ctypes.data, out.size, C.byref(n), None)
+        assert rc in (errno.EINVAL, errno.ENODEV), devs
+    arr = (C.c_int * 1)(0)
+    rc = L.sqz_gpu_tokens_multi(arr, 1, d.ctypes.data_as(_lib.u8p), d.size, 1 << 15, 3, 257, 32767,
+                                out.ctypes.data, 1, C.byref(n), None)
+    assert rc == errno.E2BIG and n.value == 2                # a literal and one (99, 1) match
