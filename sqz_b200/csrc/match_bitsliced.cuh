@@ -151,7 +151,7 @@ __device__ __forceinline__ int pick_second_window(const uint32_t* __restrict__ W
     return 0xFFFF - (int)(mine & 0xFFFFu);
 }
 
-__device__ __noinline__ void finish_position(const uint8_t* __restrict__ S, int xi, int x_end,
+__device__ __forceinline__ void finish_position(const uint8_t* __restrict__ S, int xi, int x_end,
                                              uint32_t d_from, uint32_t reach, uint32_t room, uint32_t min_len,
                                              uint32_t& best, uint32_t& bdist, int lane,
                                              unsigned long long* dbg = nullptr, uint32_t* runner_up = nullptr) {
@@ -250,17 +250,24 @@ __device__ __noinline__ void finish_position(const uint8_t* __restrict__ S, int 
 // A position leaves phase 1: its table word keeps what was found so far, marked open, with the
 // distance below which everything is settled.  No value comes back (RED, not a load + store); a
 // fresh best may still have a nearer equal inside the current group, so phase 2 starts it over.
-__device__ __forceinline__ void hand_over(uint32_t* slot, bool fresh, uint32_t resume_tag) {
-    if (fresh) { *slot = kOpenBit; }
+__device__ __forceinline__ void hand_over(uint32_t* slot, bool fresh, uint32_t resume_tag, uint32_t slice_tag) {
+    if (fresh) { *slot = kOpenBit | slice_tag; }
     else       { atomicOr(slot, kOpenBit | resume_tag); }
 }
 
+// Small shards (fewer tiles than the device has room for) split the distance range as well:
+// blockIdx.y = slice, a slice scans slice_words word distances (a multiple of 32, i.e. of 1024
+// distances -- the unit of the resume tag) into a table of its own (slice 0 into the final table,
+// slice k into slice_tables + (k-1) * slice_stride), and combine_slices folds them: nearest slice first, strictly longer wins, as
+// if one scan had walked them in order.  A slice knows nothing of what nearer slices found, so it
+// lets more candidates through, but a warp walks 1/S of the distances: what bounds a small input
+// is the latency of one warp's walk, not throughput.  slice_words = 0: one scan over everything.
 template <int kMinLen, bool kEdge>
 __global__ void __launch_bounds__(kThreads, 3)
 match_table(const uint8_t* __restrict__ shard, long long back, long long n, long long ahead,
             uint32_t max_len, uint32_t max_dist, uint32_t* __restrict__ table,
-            uint32_t* __restrict__ open_mask, int tile_first,
-            unsigned long long* __restrict__ tile_cycles) {
+            uint32_t* __restrict__ slice_tables, uint32_t* __restrict__ open_mask, int tile_first,
+            int slice_words, long long slice_stride, unsigned long long* __restrict__ tile_cycles) {
 #ifdef SQZ_DEBUG_COUNTERS
     const long long t_begin = clock64();
 #endif
@@ -271,6 +278,8 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
     uint32_t* VL = reinterpret_cast<uint32_t*>(smem_raw + geo.region_bytes + kTilePos + 32);
 
     const int tile = tile_first + (int)blockIdx.x;
+    const int slice = (int)blockIdx.y;
+    if (slice > 0) { table = slice_tables + (long long)(slice - 1) * slice_stride; }   // slice 0 writes the final table
     const long long tile_pos0 = (long long)tile * kTilePos;              // shard-relative
     const long long plane_pos0 = tile_pos0 - (long long)geo.back_blocks * 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -361,7 +370,14 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
     // farthest distance any position of this tile can use
     const long long tile_last = min(tile_pos0 + kTilePos - 1, n - 1);
     const uint32_t reach = (uint32_t)min((long long)max_dist, tile_last + back);
-    const int m_end = (int)((reach + 31) / 32);
+    int m_end = (int)((reach + 31) / 32);
+    int m_begin = 1;
+    if (slice_words > 0) {
+        m_begin = 1 + slice * slice_words;
+        m_end = min(m_end, m_begin + slice_words - 1);
+    }
+    // a fresh position handed over starts over in phase 2 -- from the first distance of this slice
+    const uint32_t slice_tag = (uint32_t)min(31, (32 * (m_begin - 1) + 1) >> 10) << kResumeShift;
 
     // Distances are visited in groups of 128: for each bit offset sh the four distances
     // d_t = 32*(m0+t) - sh, t = 0..3, are evaluated together, because block q at d_t reads the
@@ -382,7 +398,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
 #define SQZ_COUNT(x) ((void)0)
 #endif
 
-    for (int m0 = 1; m0 <= m_end; m0 += kQ) {
+    for (int m0 = m_begin; m0 <= m_end; m0 += kQ) {
         // raw candidate words j = 0..2*kQ-1 <-> plane block blk0 - m0 - (kQ-1) + j
         uint32_t cr[2 * kQ][8];
         uint32_t vr[2 * kQ];
@@ -473,7 +489,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                                 // at least 32 equal bytes: longer than the window, phase 2 finishes it.
                                 // A fresh best may still have a nearer equal: let phase 2 start over.
                                 best_len[k] = kHandOver;
-                                hand_over(slot, (fresh[q] & bit) != 0, resume_tag);
+                                hand_over(slot, (fresh[q] & bit) != 0, resume_tag, slice_tag);
                                 closed_m[q] |= bit;
                                 SQZ_COUNT(c_hand);
                                 continue;
@@ -495,7 +511,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                                 // position that keeps attracting them is cheaper to finish in phase 2
                                 if (state >= (kTieLimit << 5)) {
                                     best_len[k] = kHandOver;
-                                    hand_over(slot, (fresh[q] & bit) != 0, resume_tag);
+                                    hand_over(slot, (fresh[q] & bit) != 0, resume_tag, slice_tag);
                                     closed_m[q] |= bit;
                                 } else {
                                     best_len[k] = (uint8_t)(state + 32u);
@@ -522,7 +538,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
     for (int q = 0; q < kQ; q++) {
         if (lane == 31 && q == kQ - 1) { continue; }               // look-ahead block: the next warp owns it
         const long long p0 = tile_pos0 + (long long)(own0 + q) * 32;
-        if (p0 < n) {
+        if (p0 < n && open_mask != nullptr) {                      // (sliced launches: combine_slices writes the list)
             const uint32_t past_end = p0 + 32 > n ? (0xFFFFFFFFu << (int)(n - p0)) : 0u;
             open_mask[p0 >> 5] = closed_m[q] & ~past_end;
         }
@@ -539,6 +555,36 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
 #else
     (void)tile_cycles;
 #endif
+}
+
+// Fold the tables of a sliced launch into slice 0's (the final table) and write the work list.
+// Slices are taken nearest first.  A position some slice left open stops the fold there: what
+// that slice and the nearer ones have settled is the state phase 2 resumes from, at the open
+// slice's resume distance (everything farther is searched again, exactly).
+__global__ void __launch_bounds__(256)
+combine_slices(uint32_t* __restrict__ table, const uint32_t* __restrict__ slice_tables, long long n,
+               long long slice_stride, int slices, uint32_t* __restrict__ open_mask) {
+    const long long padded = (n + 31) & ~31LL;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < padded; p += (long long)gridDim.x * blockDim.x) {
+        uint32_t best = 0;
+        bool open = false;
+        if (p < n) {
+            for (int sl = 0; sl < slices; sl++) {
+                const uint32_t w = sl == 0 ? table[p] : slice_tables[(long long)(sl - 1) * slice_stride + p];
+                if (w & kOpenBit) {
+                    const uint32_t part = w & kStateMask;
+                    if ((part >> 16) > (best >> 16)) { best = part; }
+                    best |= kOpenBit | (w & (31u << kResumeShift));
+                    open = true;
+                    break;
+                }
+                if ((w >> 16) > (best >> 16)) { best = w; }
+            }
+            table[p] = best;
+        }
+        const uint32_t mask = __ballot_sync(0xFFFFFFFFu, open);
+        if ((threadIdx.x & 31) == 0) { open_mask[p >> 5] = mask; }
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -566,123 +612,173 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
 //
 // counters[0] is the segment cursor.
 // ---------------------------------------------------------------------------
-constexpr int kSegment = 1024;            // positions per work item of phase 2 (large shards)
+constexpr int kChunk = 4096;              // positions per CTA work item of phase 2 (large shards)
 constexpr uint32_t kSlack = 64;           // capped inheritance looks for nearer runs >= max_len - kSlack
+constexpr int kFinishCtasPerSm = 6;       // resident CTAs the staged window allows (37 KB each at max_dist 32767)
 
-// A warp closes its segment's positions one after the other, so the slowest segment bounds the
-// latency of a small shard (x64.elf, 0.9 MB: 17 ms with 1024-position segments).  Small shards
-// get shorter segments, two per resident warp; each segment boundary costs at most one search
-// that inheritance would have saved.
-inline int finish_segment(long long n, int resident_warps) {
-    long long seg = n / (2LL * resident_warps);
-    seg = (seg + 31) / 32 * 32;
-    return (int)(seg < 64 ? 64 : (seg > kSegment ? kSegment : seg));
+// Phase 2 works on chunks: a CTA stages the chunk's bytes and their whole look-back window in
+// shared memory once (max_dist + chunk + max_len bytes), then its four warps close the chunk's
+// listed positions, one sub-segment (a quarter of the chunk or less) per warp at a time, from the
+// top down.  A search step is a shared-memory load away instead of an L2 round trip, which is what
+// bounds a small shard: a warp closes its positions one after the other, so the slowest warp sets
+// the time.  Small shards get smaller chunks, enough of them for two waves of CTAs.
+struct FinishShape { int chunk, sub, smem_bytes; };
+
+inline FinishShape finish_shape(long long n, uint32_t max_len, uint32_t max_dist, int sms) {
+    long long chunk = n / (2LL * kFinishCtasPerSm * sms);
+    chunk = chunk / 128 * 128;
+    chunk = chunk < 128 ? 128 : (chunk > kChunk ? kChunk : chunk);
+    FinishShape f;
+    f.chunk = (int)chunk;
+    f.sub = f.chunk >= 2048 ? 512 : f.chunk / 4;
+    f.smem_bytes = (int)(((long long)max_dist + chunk + max_len + 8 + 16 + 15) & ~15LL) + 16;
+    return f;
 }
 
 __global__ void __launch_bounds__(kThreads)
 finish_marked(const uint8_t* __restrict__ shard, long long back, long long n, long long ahead,
               uint32_t min_len, uint32_t max_len, uint32_t max_dist, uint32_t* __restrict__ table,
               const uint32_t* __restrict__ open_mask, unsigned int* __restrict__ counters,
-              unsigned long long* __restrict__ dbg, int segment) {
+              unsigned long long* __restrict__ dbg, int chunk, int sub) {
+    extern __shared__ __align__(16) uint8_t img[];     // the chunk's bytes and window, 16-byte aligned like the source
+    __shared__ unsigned int s_chunk, s_sub;
     const int lane = threadIdx.x & 31;
-    const long long segments = (n + segment - 1) / segment;
+    const long long chunks = (n + chunk - 1) / chunk;
     const long long mask_words = (n + 31) >> 5;
-    const int seg_words = segment >> 5;                // segment is a multiple of 32, at most 1024
+    const int sub_words = sub >> 5;                    // sub is a multiple of 32, at most 1024
     // runs a nearer candidate must reach to matter for capped inheritance: never below 32, the
     // longest run phase 1 can have settled without handing the position over
     const uint32_t slack = max_len > 32 + kSlack ? kSlack : (max_len > 32 ? max_len - 32 : 0u);
+    const uint32_t img_s = (uint32_t)__cvta_generic_to_shared(img);
+    const uintptr_t valid_lo = reinterpret_cast<uintptr_t>(shard) - (uintptr_t)back;
+    const uintptr_t valid_hi = reinterpret_cast<uintptr_t>(shard) + (uintptr_t)(n + ahead);
     for (;;) {
-        unsigned int seg = 0;
-        if (lane == 0) { seg = atomicAdd(counters, 1u); }
-        seg = __shfl_sync(0xFFFFFFFFu, seg, 0);
-        if ((long long)seg >= segments) { break; }
-        const long long s0 = (long long)seg * segment;
-        const long long w0 = s0 >> 5;
-        const uint32_t my_words = (lane < seg_words && w0 + lane < mask_words) ? open_mask[w0 + lane] : 0u;
-        uint32_t listed = __ballot_sync(0xFFFFFFFFu, my_words != 0);
-        long long known_pos = -1;                      // position closed last by this warp ...
-        uint32_t known_word = 0;                       // ... and its final word
-        uint32_t cert = 0;                             // positions below known_pos that may inherit its capped result
-        while (listed != 0) {
-            const int wi = 31 - __clz((int)listed);    // highest block first
-            listed &= ~(1u << wi);
-            uint32_t marks = __shfl_sync(0xFFFFFFFFu, my_words, wi);
-            const long long base = s0 + 32LL * wi;
-            while (marks != 0) {
-                const int src = 31 - __clz((int)marks);             // highest position first
-                marks &= ~(1u << src);
-                const long long p = base + src;
-                SQZ_CHECK(p < n, "phase 2: listed position outside the shard");
-                const uint32_t raw = table[p];
-                SQZ_CHECK((raw & kOpenBit) != 0, "phase 2: listed position is not open");
-                const uint32_t word = raw & kStateMask;
-                const uint32_t resume = ((raw >> kResumeShift) & 31u) << 10;   // phase 1 settled every nearer distance
-                uint32_t best = word >> 16, bdist = word & 0xFFFFu;
-                const uint32_t room = (uint32_t)min((long long)max_len, n + ahead - p);
-                const uint32_t far = (uint32_t)min((long long)max_dist, p + back);
-                // the neighbour above: closed by this warp a moment ago, or read from the table
-                uint32_t nb = 0;
-                if (p + 1 < n) { nb = (p + 1 == known_pos) ? known_word : table[p + 1]; }
-                const uint32_t nlen = (nb >> 16) & 0x7FFFu, ndist = nb & 0xFFFFu;
-                bool done = false;
-                const bool usable = (nb & kOpenBit) == 0 && nlen >= min_len && ndist >= 1 && ndist <= far;
-                // local byte image for a search: starts at the farthest candidate, rounded down to a word
-                const uint8_t* lo = shard + p - (long long)far;
-                const int mis = (int)(reinterpret_cast<uintptr_t>(lo) & 3);
-                const long long left = n + ahead - p;
-                const int x_end = mis + (int)far + (int)min(left, (long long)max_len + 8);
-                uint32_t cert_next = 0;
-                if (usable && nlen + 1 <= room && nlen < max_len) {
-                    SQZ_CHECK(p - (long long)ndist >= -back && p < n + ahead, "phase 2: inheritance byte outside the data");
-                    if (shard[p] == shard[p - (long long)ndist]) {
-                        best = nlen + 1;
-                        bdist = ndist;
-                        done = true;
+        __syncthreads();                               // everyone is done with the previous chunk's image
+        if (threadIdx.x == 0) { s_chunk = atomicAdd(counters, 1u); s_sub = 0; }
+        __syncthreads();
+        const long long c = s_chunk;
+        if (c >= chunks) { break; }
+        const long long c0 = c * chunk;
+        const long long c1 = min(c0 + chunk, n);
+        // anything listed in this chunk?  (chunk / 32 <= 128 mask words, one per thread)
+        const long long mw = (c0 >> 5) + threadIdx.x;
+        const int listed_here = (threadIdx.x < (chunk >> 5) && mw < mask_words && open_mask[mw] != 0) ? 1 : 0;
+        if (!__syncthreads_or(listed_here)) { continue; }
+        // ---- stage [lo, hi) of the shard: 16-byte cp.async pieces, the ragged ends byte by byte ----
+        const long long lo = c0 - min((long long)max_dist, c0 + back);
+        const long long hi = min(c1 + (long long)max_len + 8, n + ahead);
+        const uint8_t* src0 = shard + lo;
+        const int mis = (int)(reinterpret_cast<uintptr_t>(src0) & 15);
+        const uint8_t* base = src0 - mis;              // img[k] = base[k]; position x sits at img[x - lo + mis]
+        const int pieces = (int)((mis + (hi - lo) + 15) >> 4) + 1;      // + one zeroed piece for word reads past the end
+        for (int k = threadIdx.x; k < pieces; k += kThreads) {
+            const uint8_t* g = base + 16 * k;
+            const uintptr_t ga = reinterpret_cast<uintptr_t>(g);
+            if (ga >= valid_lo && ga + 16 <= valid_hi) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(img_s + 16u * (uint32_t)k), "l"(g) : "memory");
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    img[16 * k + j] = (ga + j >= valid_lo && ga + j < valid_hi) ? __ldg(g + j) : (uint8_t)0;
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncthreads();
+        const long long off = (long long)mis - lo;     // img[x + off] = byte at shard-relative position x (lo <= x < hi)
+        // ---- the warps take sub-segments of the chunk until none is left ----
+        for (;;) {
+            unsigned int k = 0;
+            if (lane == 0) { k = atomicAdd(&s_sub, 1u); }
+            k = __shfl_sync(0xFFFFFFFFu, k, 0);
+            const long long s0 = c0 + (long long)k * sub;
+            if (s0 >= c1) { break; }
+            const long long w0 = s0 >> 5;
+            const uint32_t my_words = (lane < sub_words && w0 + lane < mask_words) ? open_mask[w0 + lane] : 0u;
+            uint32_t listed = __ballot_sync(0xFFFFFFFFu, my_words != 0);
+            long long known_pos = -1;                      // position closed last by this warp ...
+            uint32_t known_word = 0;                       // ... and its final word
+            uint32_t cert = 0;                             // positions below known_pos that may inherit its capped result
+            while (listed != 0) {
+                const int wi = 31 - __clz((int)listed);    // highest block first
+                listed &= ~(1u << wi);
+                uint32_t marks = __shfl_sync(0xFFFFFFFFu, my_words, wi);
+                const long long blk = s0 + 32LL * wi;
+                while (marks != 0) {
+                    const int src = 31 - __clz((int)marks);             // highest position first
+                    marks &= ~(1u << src);
+                    const long long p = blk + src;
+                    SQZ_CHECK(p < c1, "phase 2: listed position outside the chunk");
+                    const uint32_t raw = table[p];
+                    SQZ_CHECK((raw & kOpenBit) != 0, "phase 2: listed position is not open");
+                    const uint32_t word = raw & kStateMask;
+                    const uint32_t resume = ((raw >> kResumeShift) & 31u) << 10;   // phase 1 settled every nearer distance
+                    uint32_t best = word >> 16, bdist = word & 0xFFFFu;
+                    const uint32_t room = (uint32_t)min((long long)max_len, n + ahead - p);
+                    const uint32_t far = (uint32_t)min((long long)max_dist, p + back);
+                    // the neighbour above: closed by this warp a moment ago, or read from the table
+                    uint32_t nb = 0;
+                    if (p + 1 < n) { nb = (p + 1 == known_pos) ? known_word : table[p + 1]; }
+                    const uint32_t nlen = (nb >> 16) & 0x7FFFu, ndist = nb & 0xFFFFu;
+                    const bool usable = (nb & kOpenBit) == 0 && nlen >= min_len && ndist >= 1 && ndist <= far;
+                    const bool byte_same = usable && img[p + off] == img[p + off - (long long)ndist];
+                    // 0 = closed without a search, 1 = full search, 2 = capped inheritance's search among nearer candidates
+                    int mode = 1;
+                    uint32_t cert_next = 0;
+                    if (usable && nlen + 1 <= room && nlen < max_len) {
+                        if (byte_same) { best = nlen + 1; bdist = ndist; mode = 0; }
+                    } else if (byte_same && nlen == max_len && room == max_len) {
+                        if (ndist == 1) {
+                            // inside a run of one byte value: nothing is nearer than 1
+                            best = max_len; bdist = 1; mode = 0;
+                        } else if (cert > 0 && p + 1 == known_pos) {
+                            // the search a few positions above saw no nearer run long enough to matter here
+                            best = max_len; bdist = ndist; cert_next = cert - 1; mode = 0;
+                        } else if (slack > 0) {
+                            mode = 2;
+                        }
                     }
-                } else if (usable && nlen == max_len && room == max_len && shard[p] == shard[p - (long long)ndist]) {
-                    if (ndist == 1) {
-                        // inside a run of one byte value: nothing is nearer than 1
-                        best = max_len;
-                        bdist = 1;
-                        done = true;
-                    } else if (cert > 0 && p + 1 == known_pos) {
-                        // the search a few positions above saw no nearer run long enough to matter here
-                        best = max_len;
-                        bdist = ndist;
-                        cert_next = cert - 1;
-                        done = true;
-                    } else if (slack > 0) {
-                        uint32_t b2 = max_len - slack - 1, d2 = 0, runner_up = b2;
-                        SQZ_CHECK(p - (long long)far >= -back && p + (long long)room <= n + ahead, "phase 2: search window outside the data");
-                        finish_position(lo - mis, mis + (int)far, x_end, resume, ndist - 1, room, min_len, b2, d2, lane, dbg, &runner_up);
-                        best = max_len;
-                        bdist = b2 == max_len ? d2 : ndist;
-                        cert_next = max_len - 1 - (b2 == max_len ? runner_up : b2);
-                        done = true;
-                        if (dbg != nullptr && lane == 0) { atomicAdd(dbg + 22, 1ull); }
+                    if (mode == 1 && dbg != nullptr && lane == 0) {
+                        // why a search: 16 neighbour open, 17 neighbour without a match, 18 neighbour at max_len (byte differs),
+                        // 19 byte differs, 20 no neighbour in this shard, 21 other
+                        int why = 21;
+                        if (p + 1 >= n) { why = 20; }
+                        else if (nb & kOpenBit) { why = 16; }
+                        else if (nlen < min_len) { why = 17; }
+                        else if (nlen >= max_len) { why = 18; }
+                        else if (usable && nlen + 1 <= room) { why = 19; }
+                        atomicAdd(dbg + why, 1ull);
                     }
+                    if (mode != 0) {
+                        // byte image of the search: starts at the farthest candidate, rounded down to a word
+                        const long long first = p - (long long)far;
+                        SQZ_CHECK(first >= lo && p + (long long)room <= hi, "phase 2: search window outside the staged image");
+                        const int mis4 = (int)((mis + (first - lo)) & 3);
+                        const long long left = n + ahead - p;
+                        const int x_end = mis4 + (int)far + (int)min(left, (long long)max_len + 8);
+                        uint32_t b2 = mode == 2 ? max_len - slack - 1 : best;
+                        uint32_t d2 = mode == 2 ? 0u : bdist;
+                        uint32_t runner_up = b2;
+                        finish_position(img + (first + off - mis4), mis4 + (int)far, x_end, resume, mode == 2 ? ndist - 1 : far,
+                                        room, min_len, b2, d2, lane, dbg, &runner_up);
+                        if (mode == 2) {
+                            best = max_len;
+                            bdist = b2 == max_len ? d2 : ndist;
+                            cert_next = max_len - 1 - (b2 == max_len ? runner_up : b2);
+                            if (dbg != nullptr && lane == 0) { atomicAdd(dbg + 22, 1ull); }
+                        } else {
+                            best = b2;
+                            bdist = d2;
+                        }
+                    } else if (dbg != nullptr && lane == 0) {
+                        atomicAdd(dbg + 5, 1ull);
+                    }
+                    cert = cert_next;
+                    known_pos = p;
+                    known_word = best >= min_len ? ((best << 16) | bdist) : 0u;
+                    if (lane == 0) { table[p] = known_word; }
                 }
-                if (!done && dbg != nullptr && lane == 0) {
-                    // why not: 16 neighbour open, 17 neighbour without a match, 18 neighbour at max_len (byte differs),
-                    // 19 byte differs, 20 no neighbour in this shard, 21 other
-                    int why = 21;
-                    if (p + 1 >= n) { why = 20; }
-                    else if (nb & kOpenBit) { why = 16; }
-                    else if (nlen < min_len) { why = 17; }
-                    else if (nlen >= max_len) { why = 18; }
-                    else if (usable && nlen + 1 <= room) { why = 19; }
-                    atomicAdd(dbg + why, 1ull);
-                }
-                if (!done) {
-                    SQZ_CHECK(p - (long long)far >= -back && p + (long long)room <= n + ahead, "phase 2: search window outside the data");
-                    finish_position(lo - mis, mis + (int)far, x_end, resume, far, room, min_len, best, bdist, lane, dbg);
-                } else if (dbg != nullptr && lane == 0) {
-                    atomicAdd(dbg + 5, 1ull);
-                }
-                cert = cert_next;
-                known_pos = p;
-                known_word = best >= min_len ? ((best << 16) | bdist) : 0u;
-                if (lane == 0) { table[p] = known_word; }
             }
         }
     }

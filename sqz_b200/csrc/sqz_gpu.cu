@@ -556,6 +556,9 @@ static int device_state(DeviceState** out) {
             e = cudaFuncSetAttribute(v1::match_table, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)v1::smem_bytes(sqz_gpu_max_len_limit, sqz_gpu_max_dist_limit));
         }
+        if (e == cudaSuccess) {
+            e = allow_smem(v2::finish_marked, v2::finish_shape(1LL << 30, sqz_gpu_max_len_limit, sqz_gpu_max_dist_limit, 148).smem_bytes);
+        }
         if (e == cudaSuccess) { e = cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev); }
         if (e == cudaSuccess) { e = cudaStreamCreateWithFlags(&d.side, cudaStreamNonBlocking); }
         if (e == cudaSuccess) { e = cudaStreamCreateWithFlags(&d.side2, cudaStreamNonBlocking); }
@@ -585,8 +588,36 @@ struct ScopedEvent {
 // ---------------------------------------------------------------------------
 constexpr size_t kCursorBytes = 256;
 
+// Distance slices of a small shard (match_bitsliced.cuh): as many as it takes to give the device
+// about four waves of CTAs, a power of two, at most 32; none once the tiles alone fill it.
+// Fixed numbers (444 resident CTAs: 148 SMs x 3), so that the workspace size depends on n only.
+struct SlicePlan { int slices; int slice_words; size_t stride; };
+
+static SlicePlan slice_plan(size_t n, uint32_t max_dist) {
+    const size_t tiles = (n + v2::kTilePos - 1) / v2::kTilePos;
+    const size_t target = 4 * 444;
+    SlicePlan sp{1, 0, 0};
+    if (tiles == 0 || tiles >= target) { return sp; }
+    size_t want = (target + tiles - 1) / tiles;
+    int slices = 1;
+    while ((size_t)slices < want && slices < 32) { slices <<= 1; }
+    const int words = (int)((max_dist + 31) / 32);                 // word distances of a full scan
+    int per = (words + slices - 1) / slices;
+    per = (per + 31) / 32 * 32;                                    // whole units of the resume tag (1024 distances)
+    slices = (words + per - 1) / per;
+    if (slices <= 1) { return sp; }
+    sp.slices = slices;
+    sp.slice_words = per;
+    sp.stride = (n + 63) / 64 * 64;
+    return sp;
+}
+
+static size_t mask_bytes(size_t n) { return (((n + 31) / 32 + 8) * 4 + 255) / 256 * 256; }
+
 extern "C" size_t sqz_gpu_match_workspace(size_t n) {
-    return kCursorBytes + (((n + 31) / 32 + 8) * 4 + 255) / 256 * 256;
+    const SlicePlan sp = slice_plan(n, sqz_gpu_max_dist_limit);
+    // slices 1.. of a sliced launch get tables of their own (slice 0 writes the caller's)
+    return kCursorBytes + mask_bytes(n) + (sp.slices > 1 ? (size_t)(sp.slices - 1) * sp.stride * 4 : 0);
 }
 
 struct PoolBuffer { void* ptr; size_t bytes; cudaEvent_t passed; int device; };
@@ -688,6 +719,10 @@ static int launch_v2(const uint8_t* d_shard, size_t back, size_t n, size_t ahead
     CU(cudaMemsetAsync(d_counters, 0, 16, s));
     const int smem_main = v2::geometry(max_len, max_dist, false).smem_bytes;
     const int smem_edge = v2::geometry(max_len, max_dist, true).smem_bytes;
+    // small shards: the distance range is split across CTAs as well, the slices' tables sit behind
+    // the work list and are folded into d_table afterwards
+    const SlicePlan sp = slice_plan(n, max_dist);
+    uint32_t* d_slices = sp.slices > 1 ? reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(d_work) + kCursorBytes + mask_bytes(n)) : nullptr;
     // The few edge tiles run concurrently with the interior tiles: leading and trailing edge
     // tiles each on a side stream of the device, forked from and joined back into `s`.
     const bool lead = t_lo > 0, trail = tiles > t_hi;
@@ -696,34 +731,45 @@ static int launch_v2(const uint8_t* d_shard, size_t back, size_t n, size_t ahead
         CU(fork.create());
         CU(cudaEventRecord(fork.e, s));
     }
+    auto launch = [&](auto kernel, long long first, long long count, int smem, cudaStream_t on) -> cudaError_t {
+        kernel<<<dim3((unsigned)count, (unsigned)sp.slices), v2::kThreads, smem, on>>>(
+            d_shard, (long long)back, (long long)n, (long long)ahead, max_len, max_dist, d_table, d_slices,
+            sp.slices > 1 ? nullptr : d_open, (int)first, sp.slice_words, (long long)sp.stride, g_tile_cycles);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return cudaGetLastError();
+    };
+    cudaError_t le = cudaSuccess;
     if (lead) {
         CU(cudaStreamWaitEvent(dv->side, fork.e, 0));
-        v2::match_table<kMinLen, true><<<(unsigned)t_lo, v2::kThreads, smem_edge, dv->side>>>(
-            d_shard, (long long)back, (long long)n, (long long)ahead, max_len, max_dist, d_table, d_open, 0, g_tile_cycles);
-        LAUNCHED("match_table_v2_edge");
+        le = launch(v2::match_table<kMinLen, true>, 0, t_lo, smem_edge, dv->side);
+        if (le != cudaSuccess) { return fail(cuda_code(le), "match_table_v2_edge", le); }
         CU(join1.create());
         CU(cudaEventRecord(join1.e, dv->side));
     }
     if (trail) {
         CU(cudaStreamWaitEvent(dv->side2, fork.e, 0));
-        v2::match_table<kMinLen, true><<<(unsigned)(tiles - t_hi), v2::kThreads, smem_edge, dv->side2>>>(
-            d_shard, (long long)back, (long long)n, (long long)ahead, max_len, max_dist, d_table, d_open, (int)t_hi, g_tile_cycles);
-        LAUNCHED("match_table_v2_edge");
+        le = launch(v2::match_table<kMinLen, true>, t_hi, tiles - t_hi, smem_edge, dv->side2);
+        if (le != cudaSuccess) { return fail(cuda_code(le), "match_table_v2_edge", le); }
         CU(join2.create());
         CU(cudaEventRecord(join2.e, dv->side2));
     }
     if (t_hi > t_lo) {
-        v2::match_table<kMinLen, false><<<(unsigned)(t_hi - t_lo), v2::kThreads, smem_main, s>>>(
-            d_shard, (long long)back, (long long)n, (long long)ahead, max_len, max_dist, d_table, d_open, (int)t_lo, g_tile_cycles);
-        LAUNCHED("match_table_v2");
+        le = launch(v2::match_table<kMinLen, false>, t_lo, t_hi - t_lo, smem_main, s);
+        if (le != cudaSuccess) { return fail(cuda_code(le), "match_table_v2", le); }
     }
     if (join1.e != nullptr) { CU(cudaStreamWaitEvent(s, join1.e, 0)); }
     if (join2.e != nullptr) { CU(cudaStreamWaitEvent(s, join2.e, 0)); }
-    const int finish_ctas = dv->sms * 16;
-    v2::finish_marked<<<finish_ctas, v2::kThreads, 0, s>>>(d_shard, (long long)back, (long long)n, (long long)ahead,
-                                                           (uint32_t)kMinLen, max_len, max_dist, d_table, d_open, d_counters,
-                                                           g_tile_cycles ? g_tile_cycles + (1 << 20) : nullptr,
-                                                           v2::finish_segment((long long)n, finish_ctas * v2::kWarps));
+    if (sp.slices > 1) {
+        const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)dv->sms * 8);
+        v2::combine_slices<<<grid, 256, 0, s>>>(d_table, d_slices, (long long)n, (long long)sp.stride, sp.slices, d_open);
+        LAUNCHED("combine_slices");
+    }
+    const v2::FinishShape fs = v2::finish_shape((long long)n, max_len, max_dist, dv->sms);
+    const long long chunks = ((long long)n + fs.chunk - 1) / fs.chunk;
+    const unsigned finish_ctas = (unsigned)std::min<long long>(chunks, (long long)dv->sms * v2::kFinishCtasPerSm);
+    v2::finish_marked<<<finish_ctas, v2::kThreads, fs.smem_bytes, s>>>(
+        d_shard, (long long)back, (long long)n, (long long)ahead, (uint32_t)kMinLen, max_len, max_dist, d_table, d_open,
+        d_counters, g_tile_cycles ? g_tile_cycles + (1 << 20) : nullptr, fs.chunk, fs.sub);
     LAUNCHED("match_finish_marked");
     return 0;
 }
