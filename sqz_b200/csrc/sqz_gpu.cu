@@ -1089,6 +1089,8 @@ static void slot_give_back(Slot& s) {
     for (Slot& v : victims) { cudaSetDevice(v.device); slot_free(v); }
 }
 
+static void multi_release_all();
+
 extern "C" void sqz_gpu_release(void) {
     std::vector<Slot> all;
     {
@@ -1098,6 +1100,7 @@ extern "C" void sqz_gpu_release(void) {
     DeviceScope keep;
     for (Slot& c : all) { cudaSetDevice(c.device); slot_free(c); }
     pool_release_all();
+    multi_release_all();
 }
 
 // device < 0 = the calling thread's current device
@@ -1369,6 +1372,7 @@ struct MultiPart {
     uint64_t* d_result = nullptr;
     uint16_t* h_map = nullptr;        // pinned: exit map
     uint64_t* h_result = nullptr;     // pinned: count, overshoot
+    size_t cap_n = 0, cap_data = 0;   // what the buffers hold (parts are recycled between calls)
 };
 
 static void multi_free(MultiPart& p) {
@@ -1383,21 +1387,70 @@ static void multi_free(MultiPart& p) {
     p = MultiPart();
 }
 
+// Like the slots of the single-device pipeline, the per-device buffers of a multi-device call are
+// kept for the next call of a similar size (allocating ten gigabytes takes longer than searching a
+// small input); at most kMultiParked of them, and only parts below kMultiParkBytes of device memory.
+static std::vector<MultiPart> g_multi_parked;      // guarded by g_park_mu
+constexpr size_t kMultiParked = 8;
+constexpr size_t kMultiParkBytes = (size_t)12 << 30;
+
+static size_t multi_bytes(const MultiPart& p) { return p.cap_data + p.cap_n * 8 + parse::workspace(p.cap_n) + sqz_gpu_match_workspace(p.cap_n); }
+
 static int multi_alloc(MultiPart& p) {
+    const size_t need_data = p.back + p.n + p.ahead + 64;
+    {
+        std::lock_guard<std::mutex> lk(g_park_mu);
+        for (size_t k = 0; k < g_multi_parked.size(); k++) {
+            const MultiPart& c = g_multi_parked[k];
+            if (c.device == p.device && c.cap_n >= p.n && c.cap_n <= 2 * p.n + ((size_t)1 << 20) && c.cap_data >= need_data) {
+                MultiPart t = c;
+                g_multi_parked.erase(g_multi_parked.begin() + (long)k);
+                t.first = p.first; t.n = p.n; t.back = p.back; t.ahead = p.ahead;
+                p = t;
+                CU(cudaSetDevice(p.device));
+                return 0;
+            }
+        }
+    }
     CU(cudaSetDevice(p.device));
+    p.cap_n = (std::max<size_t>(p.n, 1) + ((size_t)1 << 20) - 1) >> 20 << 20;
+    p.cap_data = p.cap_n + (size_t)sqz_gpu_max_dist_limit + sqz_gpu_max_len_limit + 64;
     CU(cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&p.mapped, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&p.parsed, cudaEventDisableTiming));
-    CU(cudaMalloc(&p.d_data, p.back + p.n + p.ahead + 64));
-    CU(cudaMalloc(&p.d_table, std::max<size_t>(p.n, 1) * 4));
-    CU(cudaMalloc(&p.d_tokens, std::max<size_t>(p.n, 1) * 4 + 16));
-    CU(cudaMalloc(&p.d_work, parse::workspace(std::max<size_t>(p.n, 1))));
-    CU(cudaMalloc(&p.d_mwork, sqz_gpu_match_workspace(p.n)));
+    CU(cudaMalloc(&p.d_data, p.cap_data));
+    CU(cudaMalloc(&p.d_table, p.cap_n * 4));
+    CU(cudaMalloc(&p.d_tokens, p.cap_n * 4 + 16));
+    CU(cudaMalloc(&p.d_work, parse::workspace(p.cap_n)));
+    CU(cudaMalloc(&p.d_mwork, sqz_gpu_match_workspace(p.cap_n)));
     CU(cudaMalloc(&p.d_map, parse::kMapStride * 2));
     CU(cudaMalloc(&p.d_result, 16));
     CU(cudaHostAlloc(&p.h_map, parse::kMapStride * 2, cudaHostAllocDefault));
     CU(cudaHostAlloc(&p.h_result, 16, cudaHostAllocDefault));
     return 0;
+}
+
+static void multi_give_back(MultiPart& p) {
+    if (p.stream == nullptr || p.cap_n == 0 || multi_bytes(p) > kMultiParkBytes) { multi_free(p); return; }
+    cudaSetDevice(p.device);
+    cudaStreamSynchronize(p.stream);
+    MultiPart victim;
+    {
+        std::lock_guard<std::mutex> lk(g_park_mu);
+        g_multi_parked.push_back(p);
+        if (g_multi_parked.size() > kMultiParked) { victim = g_multi_parked.front(); g_multi_parked.erase(g_multi_parked.begin()); }
+    }
+    p = MultiPart();
+    if (victim.stream != nullptr) { multi_free(victim); }
+}
+
+static void multi_release_all() {
+    std::vector<MultiPart> all;
+    {
+        std::lock_guard<std::mutex> lk(g_park_mu);
+        all.swap(g_multi_parked);
+    }
+    for (MultiPart& p : all) { multi_free(p); }
 }
 
 static int multi_run(std::vector<MultiPart>& parts, const uint8_t* data, uint32_t min_len, uint32_t max_len,
@@ -1522,7 +1575,10 @@ extern "C" int sqz_gpu_tokens_multi(const int* devices, int n_devices, const uin
     }
     const int rc = multi_run(parts, data, min_len, max_len, max_dist, tokens_out, tokens_cap, out_on_device,
                              out_device, n_tokens, shard_tokens);
-    for (MultiPart& p : parts) { if (p.stream != nullptr || p.d_data != nullptr) { multi_free(p); } }
+    for (MultiPart& p : parts) {
+        if (rc == 0 && p.stream != nullptr) { multi_give_back(p); }
+        else if (p.stream != nullptr || p.d_data != nullptr) { multi_free(p); }
+    }
     return rc;
 }
 
