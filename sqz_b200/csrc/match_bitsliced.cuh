@@ -80,6 +80,10 @@ constexpr uint32_t kTieMask = SQZ_TIE_MASK;   // a rejected survivor is counted 
 #define SQZ_TIE_LIMIT 6
 #endif
 constexpr uint32_t kTieLimit = SQZ_TIE_LIMIT; // rejected survivors a position may collect before the next one hands it over (<= 6)
+#ifndef SQZ_SLICED_TIE_LIMIT
+#define SQZ_SLICED_TIE_LIMIT 6
+#endif
+constexpr uint32_t kSlicedTieLimit = SQZ_SLICED_TIE_LIMIT;   // the same in a sliced launch (8 = never hand over on rejects)
 constexpr int kStageBlocks = 448;         // staging piece: 448 x 32 B + alignment slack fits in best_len
 constexpr uint8_t kHandOver = 0xFF;       // best_len mark: finish this position in phase 2
 constexpr uint32_t kOpenBit = 0x80000000u; // table word mark: position is finished by the phase 2 kernel
@@ -376,6 +380,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
         m_begin = 1 + slice * slice_words;
         m_end = min(m_end, m_begin + slice_words - 1);
     }
+    const uint32_t tie_limit = slice_words > 0 ? kSlicedTieLimit : kTieLimit;
     // a fresh position handed over starts over in phase 2 -- from the first distance of this slice
     const uint32_t slice_tag = (uint32_t)min(31, (32 * (m_begin - 1) + 1) >> 10) << kResumeShift;
 
@@ -509,11 +514,11 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                             } else if ((SQZ_COUNT(c_reject), (d & kTieMask) == 0)) {
                                 // a candidate that only ties or falls short: count a sample of them; a
                                 // position that keeps attracting them is cheaper to finish in phase 2
-                                if (state >= (kTieLimit << 5)) {
+                                if (state >= (tie_limit << 5)) {
                                     best_len[k] = kHandOver;
                                     hand_over(slot, (fresh[q] & bit) != 0, resume_tag, slice_tag);
                                     closed_m[q] |= bit;
-                                } else {
+                                } else if (state < (7u << 5)) {
                                     best_len[k] = (uint8_t)(state + 32u);
                                 }
                             }

@@ -593,12 +593,13 @@ constexpr size_t kCursorBytes = 256;
 // Fixed numbers (444 resident CTAs: 148 SMs x 3), so that the workspace size depends on n only.
 struct SlicePlan { int slices; int slice_words; size_t stride; };
 
+constexpr size_t kSliceTarget = 2 * 444;        // CTAs a sliced launch aims for
+
 static SlicePlan slice_plan(size_t n, uint32_t max_dist) {
     const size_t tiles = (n + v2::kTilePos - 1) / v2::kTilePos;
-    const size_t target = 4 * 444;
     SlicePlan sp{1, 0, 0};
-    if (tiles == 0 || tiles >= target) { return sp; }
-    size_t want = (target + tiles - 1) / tiles;
+    if (tiles == 0 || 2 * tiles > kSliceTarget) { return sp; }     // a wave of tiles or more: no slices
+    size_t want = (kSliceTarget + tiles - 1) / tiles;
     int slices = 1;
     while ((size_t)slices < want && slices < 32) { slices <<= 1; }
     const int words = (int)((max_dist + 31) / 32);                 // word distances of a full scan
@@ -614,10 +615,18 @@ static SlicePlan slice_plan(size_t n, uint32_t max_dist) {
 
 static size_t mask_bytes(size_t n) { return (((n + 31) / 32 + 8) * 4 + 255) / 256 * 256; }
 
+static size_t slice_bytes(const SlicePlan& sp) { return sp.slices > 1 ? (size_t)(sp.slices - 1) * sp.stride * 4 : 0; }
+
+// A workspace sized for n serves every shard of at most n positions (the pipeline's slots are
+// sized once and see chunks of many sizes): the slice tables are what a smaller shard may need
+// more of, so their part is the largest any n' <= n asks for.
 extern "C" size_t sqz_gpu_match_workspace(size_t n) {
-    const SlicePlan sp = slice_plan(n, sqz_gpu_max_dist_limit);
-    // slices 1.. of a sliced launch get tables of their own (slice 0 writes the caller's)
-    return kCursorBytes + mask_bytes(n) + (sp.slices > 1 ? (size_t)(sp.slices - 1) * sp.stride * 4 : 0);
+    size_t tables = slice_bytes(slice_plan(n, sqz_gpu_max_dist_limit));
+    const size_t tiles = std::min<size_t>((n + v2::kTilePos - 1) / v2::kTilePos, kSliceTarget);
+    for (size_t t = 1; t <= tiles; t++) {
+        tables = std::max(tables, slice_bytes(slice_plan(std::min(n, t * (size_t)v2::kTilePos), sqz_gpu_max_dist_limit)));
+    }
+    return kCursorBytes + mask_bytes(n) + tables;
 }
 
 struct PoolBuffer { void* ptr; size_t bytes; cudaEvent_t passed; int device; };

@@ -7,7 +7,7 @@ L = _lib.load()
 fx = corpus.fixtures()
 kinds = {"text": np.concatenate([fx["confucius.txt"], fx["laozi.txt"]]), "elf": np.concatenate([fx["x64.elf"], fx["arm64.elf"]]),
          "image": np.concatenate([fx["mandrill.bmp"], fx["mandrill.png"]])}
-size = 16 << 20
+size = int(sys.argv[1]) if len(sys.argv) > 1 else 16 << 20
 cyc = torch.zeros((1 << 20) + 64, dtype=torch.int64, device="cuda")
 L.sqz_gpu_debug_tile_cycles(cyc.data_ptr())
 for name, base in kinds.items():
