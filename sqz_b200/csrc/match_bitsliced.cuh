@@ -98,7 +98,7 @@ struct Geometry {            // identical for all CTAs of a launch
     int smem_bytes;
 };
 
-__host__ __device__ inline Geometry geometry(uint32_t max_len, uint32_t max_dist, bool edge) {
+__host__ __device__ inline Geometry geometry(uint32_t max_len, uint32_t max_dist, bool edge, bool seeded = false) {
     Geometry g;
     g.back_blocks = (int)((max_dist + 31) / 32) + 2 * kQ;   // a group of kQ word distances + its window
     g.ahead_blocks = kQ + 2;
@@ -106,7 +106,11 @@ __host__ __device__ inline Geometry geometry(uint32_t max_len, uint32_t max_dist
     (void)max_len;
     g.region_bytes = g.plane_blocks * 32;                                  // 8 planes x 4 B per block
     int bytes = g.region_bytes + kTilePos + 32;                            // + one state byte per position
+#ifdef SQZ_FRESH_T
+    bytes += kTilePos / 2;                                                 // + which of a group's four distances holds a fresh best
+#endif
     if (edge) { bytes += g.plane_blocks * 4; }                             // validity plane
+    if (seeded) { bytes += (kTileBlocks + 1) * (kGated + 1) * 4; }         // starting masks of a seeded slice
     g.smem_bytes = (bytes + 15) & ~15;
     return g;
 }
@@ -266,23 +270,39 @@ __device__ __forceinline__ void hand_over(uint32_t* slot, bool fresh, uint32_t r
 // if one scan had walked them in order.  A slice knows nothing of what nearer slices found, so it
 // lets more candidates through, but a warp walks 1/S of the distances: what bounds a small input
 // is the latency of one warp's walk, not throughput.  slice_words = 0: one scan over everything.
+// To keep the far slices from treating every three-byte coincidence as an improvement (measured:
+// 28 instead of 2.7 scalar-path candidates per position on ELF data), the nearest slice runs first
+// and the others are seeded with its table (init_table): a position starts with the nearest
+// slice's best as the run to beat -- strictly, the nearest slice is nearer -- and a position the
+// nearest slice handed over is closed in every other slice, because phase 2 will walk on from
+// there through all farther distances anyway.
 template <int kMinLen, bool kEdge>
 __global__ void __launch_bounds__(kThreads, 3)
 match_table(const uint8_t* __restrict__ shard, long long back, long long n, long long ahead,
             uint32_t max_len, uint32_t max_dist, uint32_t* __restrict__ table,
             uint32_t* __restrict__ slice_tables, uint32_t* __restrict__ open_mask, int tile_first,
-            int slice_words, long long slice_stride, unsigned long long* __restrict__ tile_cycles) {
+            int slice_words, long long slice_stride, int slice_base, const uint32_t* __restrict__ init_table,
+            unsigned long long* __restrict__ tile_cycles) {
 #ifdef SQZ_DEBUG_COUNTERS
     const long long t_begin = clock64();
 #endif
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    const Geometry geo = geometry(max_len, max_dist, kEdge);
+    const Geometry geo = geometry(max_len, max_dist, kEdge, init_table != nullptr);
     const uint4* PL = reinterpret_cast<const uint4*>(smem_raw);           // [plane_blocks][2]
     uint8_t* best_len = smem_raw + geo.region_bytes;                      // [kTilePos + 32]
+#ifdef SQZ_FRESH_T
+    // A fresh best (set inside the current group of 128 distances) loses to an equal run at a
+    // nearer distance.  Inside a group a later candidate is nearer exactly when its t is smaller
+    // (d = 32 (m0 + t) - sh, sh descends), so two bits per position replace a read of the table word.
+    uint8_t* fresh_t = smem_raw + geo.region_bytes + kTilePos + 32;       // [kTilePos / 2] nibbles
+    uint32_t* VL = reinterpret_cast<uint32_t*>(smem_raw + geo.region_bytes + kTilePos + 32 + kTilePos / 2);
+#else
     uint32_t* VL = reinterpret_cast<uint32_t*>(smem_raw + geo.region_bytes + kTilePos + 32);
+#endif
 
+    uint32_t* seed = VL + (kEdge ? geo.plane_blocks : 0);                  // [(kTileBlocks + 1)][kGated + 1], seeded slices only
     const int tile = tile_first + (int)blockIdx.x;
-    const int slice = (int)blockIdx.y;
+    const int slice = slice_base + (int)blockIdx.y;
     if (slice > 0) { table = slice_tables + (long long)(slice - 1) * slice_stride; }   // slice 0 writes the final table
     const long long tile_pos0 = (long long)tile * kTilePos;              // shard-relative
     const long long plane_pos0 = tile_pos0 - (long long)geo.back_blocks * 32;
@@ -343,6 +363,25 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
             const long long p = tile_pos0 + k;
             if (p < n) { table[p] = 0; }
         }
+        if (init_table != nullptr) {
+            // seeded slice: the nearest slice's result is the run to beat (state byte and need masks);
+            // what it handed over is closed here
+            for (int blk = warp; blk <= kTileBlocks; blk += kWarps) {
+                const int k = blk * 32 + lane;
+                const long long p = tile_pos0 + k;
+                const uint32_t w = (blk < kTileBlocks && p < n) ? init_table[p] : 0u;
+                const bool open = (w & kOpenBit) != 0;
+                const uint32_t have = open ? 0u : min((w >> 16) & 0x3FFu, 31u);
+                if (blk < kTileBlocks) { best_len[k] = open ? kHandOver : (uint8_t)have; }
+#pragma unroll
+                for (int g = 0; g < kGated; g++) {
+                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, have > (uint32_t)(kMinLen + g));
+                    if (lane == g) { seed[blk * (kGated + 1) + g] = m; }
+                }
+                const uint32_t c = __ballot_sync(0xFFFFFFFFu, open);
+                if (lane == kGated) { seed[blk * (kGated + 1) + kGated] = c; }
+            }
+        }
     }
     __syncthreads();
 
@@ -368,6 +407,11 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
         closed_m[q] = closed;
 #pragma unroll
         for (int k = 0; k < kGated; k++) { G[k][q] = 0; }
+        if (init_table != nullptr) {
+#pragma unroll
+            for (int k = 0; k < kGated; k++) { G[k][q] = seed[(own0 + q) * (kGated + 1) + k]; }
+            closed_m[q] |= seed[(own0 + q) * (kGated + 1) + kGated];
+        }
         vq[q] = kEdge ? VL[blk0 + q] : 0xFFFFFFFFu;
     }
 
@@ -501,12 +545,25 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                             }
                             const uint32_t run = (uint32_t)(__ffs((int)win) - 1);
                             bool better = run > have;
+#ifdef SQZ_FRESH_T
+                            if (run == have && (fresh[q] & bit)) {
+                                better = (uint32_t)t < ((uint32_t)(fresh_t[k >> 1] >> ((k & 1) * 4)) & 3u);
+                                SQZ_COUNT(c_tie_fresh);
+                            }
+#else
                             if (run == have && (fresh[q] & bit)) { better = d < (*slot & 0xFFFFu); SQZ_COUNT(c_tie_fresh); }
+#endif
                             if (better) {
                                 SQZ_COUNT(c_better);
                                 best_len[k] = (uint8_t)run;
                                 *slot = (run << 16) | d;
                                 fresh[q] |= bit;
+#ifdef SQZ_FRESH_T
+                                {
+                                    const int sh4 = (k & 1) * 4;
+                                    fresh_t[k >> 1] = (uint8_t)((fresh_t[k >> 1] & ~(0xF << sh4)) | (t << sh4));
+                                }
+#endif
 #pragma unroll
                                 for (int g = 0; g < kGated; g++) {
                                     if (run > (uint32_t)(kMinLen + g)) { G[g][q] |= bit; }
@@ -635,7 +692,10 @@ inline FinishShape finish_shape(long long n, uint32_t max_len, uint32_t max_dist
     chunk = chunk < 128 ? 128 : (chunk > kChunk ? kChunk : chunk);
     FinishShape f;
     f.chunk = (int)chunk;
-    f.sub = f.chunk >= 2048 ? 512 : f.chunk / 4;
+    // large shards: 512-position pieces (a boundary can cost a search inheritance would have saved);
+    // small shards: 32-position pieces, the dense spots of an ELF table then spread over all warps
+    f.sub = f.chunk >= 2048 ? 512 : 32;
+    f.chunk = f.chunk / f.sub * f.sub;                 // whole pieces
     f.smem_bytes = (int)(((long long)max_dist + chunk + max_len + 8 + 16 + 15) & ~15LL) + 16;
     return f;
 }
@@ -700,7 +760,8 @@ finish_marked(const uint8_t* __restrict__ shard, long long back, long long n, lo
             const long long s0 = c0 + (long long)k * sub;
             if (s0 >= c1) { break; }
             const long long w0 = s0 >> 5;
-            const uint32_t my_words = (lane < sub_words && w0 + lane < mask_words) ? open_mask[w0 + lane] : 0u;
+            const long long w_end = min(mask_words, (c1 + 31) >> 5);        // the chunk's words only
+            const uint32_t my_words = (lane < sub_words && w0 + lane < w_end) ? open_mask[w0 + lane] : 0u;
             uint32_t listed = __ballot_sync(0xFFFFFFFFu, my_words != 0);
             long long known_pos = -1;                      // position closed last by this warp ...
             uint32_t known_word = 0;                       // ... and its final word

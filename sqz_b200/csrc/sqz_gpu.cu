@@ -547,7 +547,7 @@ static int device_state(DeviceState** out) {
     if (dev < 0 || dev >= kMaxDevices) { return fail(ENODEV, "device index out of range"); }
     DeviceState& d = g_dev[dev];
     std::call_once(d.once, [&d, dev] {
-        const int big = v2::geometry(sqz_gpu_max_len_limit, sqz_gpu_max_dist_limit, true).smem_bytes;
+        const int big = v2::geometry(sqz_gpu_max_len_limit, sqz_gpu_max_dist_limit, true, true).smem_bytes;
         cudaError_t e = allow_smem(v2::match_table<3, false>, big);
         if (e == cudaSuccess) { e = allow_smem(v2::match_table<3, true>, big); }
         if (e == cudaSuccess) { e = allow_smem(v2::match_table<2, false>, big); }
@@ -740,30 +740,39 @@ static int launch_v2(const uint8_t* d_shard, size_t back, size_t n, size_t ahead
         CU(fork.create());
         CU(cudaEventRecord(fork.e, s));
     }
-    auto launch = [&](auto kernel, long long first, long long count, int smem, cudaStream_t on) -> cudaError_t {
-        kernel<<<dim3((unsigned)count, (unsigned)sp.slices), v2::kThreads, smem, on>>>(
+    // sliced: the nearest slice first (into d_table), then the others seeded with its result
+    const int smem_main_seeded = v2::geometry(max_len, max_dist, false, true).smem_bytes;
+    const int smem_edge_seeded = v2::geometry(max_len, max_dist, true, true).smem_bytes;
+    auto launch = [&](auto kernel, long long first, long long count, bool edge, cudaStream_t on) -> cudaError_t {
+        kernel<<<dim3((unsigned)count, 1), v2::kThreads, edge ? smem_edge : smem_main, on>>>(
             d_shard, (long long)back, (long long)n, (long long)ahead, max_len, max_dist, d_table, d_slices,
-            sp.slices > 1 ? nullptr : d_open, (int)first, sp.slice_words, (long long)sp.stride, g_tile_cycles);
+            sp.slices > 1 ? nullptr : d_open, (int)first, sp.slice_words, (long long)sp.stride, 0, nullptr, g_tile_cycles);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess || sp.slices <= 1) { return e; }
+        kernel<<<dim3((unsigned)count, (unsigned)(sp.slices - 1)), v2::kThreads, edge ? smem_edge_seeded : smem_main_seeded, on>>>(
+            d_shard, (long long)back, (long long)n, (long long)ahead, max_len, max_dist, d_table, d_slices,
+            nullptr, (int)first, sp.slice_words, (long long)sp.stride, 1, d_table, g_tile_cycles);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         return cudaGetLastError();
     };
     cudaError_t le = cudaSuccess;
     if (lead) {
         CU(cudaStreamWaitEvent(dv->side, fork.e, 0));
-        le = launch(v2::match_table<kMinLen, true>, 0, t_lo, smem_edge, dv->side);
+        le = launch(v2::match_table<kMinLen, true>, 0, t_lo, true, dv->side);
         if (le != cudaSuccess) { return fail(cuda_code(le), "match_table_v2_edge", le); }
         CU(join1.create());
         CU(cudaEventRecord(join1.e, dv->side));
     }
     if (trail) {
         CU(cudaStreamWaitEvent(dv->side2, fork.e, 0));
-        le = launch(v2::match_table<kMinLen, true>, t_hi, tiles - t_hi, smem_edge, dv->side2);
+        le = launch(v2::match_table<kMinLen, true>, t_hi, tiles - t_hi, true, dv->side2);
         if (le != cudaSuccess) { return fail(cuda_code(le), "match_table_v2_edge", le); }
         CU(join2.create());
         CU(cudaEventRecord(join2.e, dv->side2));
     }
     if (t_hi > t_lo) {
-        le = launch(v2::match_table<kMinLen, false>, t_lo, t_hi - t_lo, smem_main, s);
+        le = launch(v2::match_table<kMinLen, false>, t_lo, t_hi - t_lo, false, s);
         if (le != cudaSuccess) { return fail(cuda_code(le), "match_table_v2", le); }
     }
     if (join1.e != nullptr) { CU(cudaStreamWaitEvent(s, join1.e, 0)); }

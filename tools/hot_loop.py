@@ -1,0 +1,70 @@
+"""Instruction counts of the match kernel's hot loop, read from the SASS of the built library.
+
+The loop over the 32 bit offsets of a group of 128 distances (`for sh` in match_bitsliced.cuh) is
+the smallest backward branch around the four SHFL.DOWN of the look-ahead exchange.  Its fast path
+is the straight line from the loop head to the branch that skips the scalar path, plus the tail
+from that branch's target to the backward branch.  Per iteration a warp covers 127 owned blocks x
+32 positions x 4 distances = 16,256 candidate-compares.
+
+    python tools/hot_loop.py [libsqz_b200.so] [--json]
+"""
+import json, os, re, subprocess, sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def sass(lib, mangled_part):
+    out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
+    keep, on = [], False
+    for line in out.splitlines():
+        if "Function :" in line:
+            on = mangled_part in line
+        elif on:
+            m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", line)
+            if m:
+                keep.append((int(m.group(1), 16), m.group(2).strip()))
+    return keep
+
+
+def hot_loop(lib=None, kernel="match_tableILi3ELb0E"):
+    lib = lib or os.path.join(ROOT, "sqz_b200", "lib", "libsqz_b200.so")
+    ins = sass(lib, kernel)
+    shfl = [a for a, t in ins if t.startswith("SHFL.DOWN")]
+    assert len(shfl) >= 4, "look-ahead exchange not found"
+    first, last = shfl[0], shfl[-1]
+    loops = []
+    for a, t in ins:
+        m = re.search(r"BRA(?:\.U)?\s+(?:!?U?P\d+,\s*)?0x([0-9a-f]+)", t)
+        if m and a > last and int(m.group(1), 16) <= first:
+            loops.append((a - int(m.group(1), 16), int(m.group(1), 16), a))
+    size, head, back = min(loops)
+    # the branch over the scalar path: first forward branch after the exchange that lands inside the loop
+    skip_at = skip_to = None
+    for a, t in ins:
+        m = re.search(r"BRA\s+0x([0-9a-f]+)", t)
+        if m and last < a < back and head < int(m.group(1), 16) <= back and int(m.group(1), 16) > a:
+            skip_at, skip_to = a, int(m.group(1), 16)
+            break
+    assert skip_at is not None, "branch over the scalar path not found"
+    fast = [t for a, t in ins if head <= a <= skip_at or skip_to <= a <= back]
+    def op(t):
+        t = re.sub(r"^@!?U?P\d+\s+", "", t)
+        return t.split()[0].split(".")[0]
+    hist = {}
+    for t in fast:
+        hist[op(t)] = hist.get(op(t), 0) + 1
+    alu = hist.get("LOP3", 0) + hist.get("SHF", 0)
+    return {"kernel": "v2::match_table<3,false>", "loop_head": hex(head), "skip_branch": hex(skip_at), "skip_target": hex(skip_to),
+            "back_branch": hex(back), "fast_path_instructions": len(fast), "alu_instr_per_warp_iteration": alu,
+            "lop3": hist.get("LOP3", 0), "shf": hist.get("SHF", 0), "histogram": dict(sorted(hist.items(), key=lambda kv: -kv[1])),
+            "scalar_path_instructions": sum(1 for a, t in ins if skip_at < a < skip_to),
+            "cc_per_warp_iteration": 127 * 32 * 4}
+
+
+if __name__ == "__main__":
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    r = hot_loop(args[0] if args else None)
+    print(json.dumps(r, indent=1) if "--json" in sys.argv else
+          "hot loop %s..%s: %d instructions on the fast path (%d LOP3 + %d SHF = %d ALU-pipe), scalar path %d instructions, %d CC per warp iteration"
+          % (r["loop_head"], r["back_branch"], r["fast_path_instructions"], r["lop3"], r["shf"], r["alu_instr_per_warp_iteration"],
+             r["scalar_path_instructions"], r["cc_per_warp_iteration"]))
