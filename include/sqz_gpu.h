@@ -191,8 +191,10 @@ int  sqz_gpu_put_tokens(uint32_t* d_dst, size_t at, const uint32_t* d_tokens, si
  * do not describe exactly `bytes` bytes or a match reaches before the start. */
 int sqz_gpu_expand_tokens(const uint32_t* tokens, size_t n_tokens, uint8_t* out, size_t bytes);
 /* device pointers; d_work holds sqz_gpu_expand_workspace(n_tokens, bytes) bytes.
- * Returns after the kernels are queued on `stream`, except that it waits for
- * the (few) rounds of pointer doubling to learn when the chains are done.     */
+ * Waits for the stream twice: once for the scan of the token lengths (a stream
+ * that does not describe `bytes` bytes is refused before anything is placed),
+ * once at the end for the verdict on the distances.  The rounds of pointer
+ * doubling in between end themselves on the device.                           */
 size_t sqz_gpu_expand_workspace(size_t n_tokens, size_t bytes);
 int sqz_gpu_expand_tokens_device(const uint32_t* d_tokens, size_t n_tokens, uint8_t* d_out,
                                  size_t bytes, void* d_work, void* stream);

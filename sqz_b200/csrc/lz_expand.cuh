@@ -142,9 +142,18 @@ place_tokens(const uint32_t* __restrict__ tokens, size_t n_tokens, const uint64_
     }
 }
 
-// one round of pointer doubling; *changed is set when some hop has not reached its literal yet
+// One round of pointer doubling.  All rounds a chain can need (32: hops are 31-bit) are queued at
+// once, without a host round trip in between: round r raises flag[r % 3] when some hop has not
+// reached its literal yet, and a round whose predecessor raised nothing returns at once -- every
+// block reads the same flag, written by a kernel that has finished.  The third flag is the one
+// the next round will raise; this round clears it.
 __global__ void __launch_bounds__(256)
-double_hops(uint32_t* __restrict__ hop, uint64_t bytes, int* __restrict__ changed) {
+double_hops(uint32_t* __restrict__ hop, uint64_t bytes, int* __restrict__ flag, int round) {
+    if (round > 0 && flag[(round + 2) % 3] == 0) {          // the previous round found every chain landed
+        if (blockIdx.x == 0 && threadIdx.x == 0) { flag[(round + 1) % 3] = 0; flag[round % 3] = 0; }
+        return;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { flag[(round + 1) % 3] = 0; }
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     bool any = false;
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < bytes; j += stride) {
@@ -160,7 +169,7 @@ double_hops(uint32_t* __restrict__ hop, uint64_t bytes, int* __restrict__ change
             any = true;                                       // still on its way
         }
     }
-    if (__syncthreads_or(any) && threadIdx.x == 0) { *changed = 1; }
+    if (__syncthreads_or(any) && threadIdx.x == 0) { flag[round % 3] = 1; }
 }
 
 __global__ void __launch_bounds__(256)

@@ -64,10 +64,15 @@ namespace v2 {
 
 constexpr int kWarps = 4;                 // warps per CTA
 constexpr int kThreads = kWarps * 32;
-constexpr int kQ = 4;                     // blocks of 32 positions per thread
-constexpr int kWarpOwned = 32 * kQ - 1;   // blocks a warp owns; its last block is look-ahead only
-constexpr int kTileBlocks = kWarps * kWarpOwned;      // owned blocks per CTA
-constexpr int kTilePos = kTileBlocks * 32;            // positions per CTA
+// Blocks of 32 positions per thread (kQ, a template parameter of the phase 1 kernel).  4 is the
+// throughput shape: four distances share their shifted words, 31 candidate-compares per instruction.
+// 1 is the latency shape for small shards: a quarter of the positions and of the scalar-path work
+// per warp, four times as many warps, at 1.4 times the instructions per candidate-compare.
+__host__ __device__ constexpr int warp_owned(int q) { return 32 * q - 1; }          // blocks a warp owns; its last block is look-ahead only
+__host__ __device__ constexpr int tile_blocks(int q) { return kWarps * warp_owned(q); }   // owned blocks per CTA
+__host__ __device__ constexpr int tile_pos(int q) { return tile_blocks(q) * 32; }         // positions per CTA
+// staging piece: its bytes + alignment slack fit in the state bytes of the tile
+__host__ __device__ constexpr int stage_blocks(int q) { return tile_blocks(q) - 4 < 448 ? tile_blocks(q) - 4 : 448; }
 #ifndef SQZ_GATED
 #define SQZ_GATED 3
 #endif
@@ -84,7 +89,6 @@ constexpr uint32_t kTieLimit = SQZ_TIE_LIMIT; // rejected survivors a position m
 #define SQZ_SLICED_TIE_LIMIT 6
 #endif
 constexpr uint32_t kSlicedTieLimit = SQZ_SLICED_TIE_LIMIT;   // the same in a sliced launch (8 = never hand over on rejects)
-constexpr int kStageBlocks = 448;         // staging piece: 448 x 32 B + alignment slack fits in best_len
 constexpr uint8_t kHandOver = 0xFF;       // best_len mark: finish this position in phase 2
 constexpr uint32_t kOpenBit = 0x80000000u; // table word mark: position is finished by the phase 2 kernel
 constexpr int kResumeShift = 26;          // bits 26..30 of an open word: distance/1024 below which all is settled
@@ -98,17 +102,15 @@ struct Geometry {            // identical for all CTAs of a launch
     int smem_bytes;
 };
 
-__host__ __device__ inline Geometry geometry(uint32_t max_len, uint32_t max_dist, bool edge, bool seeded = false) {
+__host__ __device__ inline Geometry geometry(uint32_t max_len, uint32_t max_dist, bool edge, bool seeded, int q) {
+    const int kTileBlocks = tile_blocks(q), kTilePos = tile_pos(q);
     Geometry g;
-    g.back_blocks = (int)((max_dist + 31) / 32) + 2 * kQ;   // a group of kQ word distances + its window
-    g.ahead_blocks = kQ + 2;
+    g.back_blocks = (int)((max_dist + 31) / 32) + 2 * q;    // a group of q word distances + its window
+    g.ahead_blocks = q + 2;
     g.plane_blocks = g.back_blocks + kTileBlocks + g.ahead_blocks;
     (void)max_len;
     g.region_bytes = g.plane_blocks * 32;                                  // 8 planes x 4 B per block
     int bytes = g.region_bytes + kTilePos + 32;                            // + one state byte per position
-#ifdef SQZ_FRESH_T
-    bytes += kTilePos / 2;                                                 // + which of a group's four distances holds a fresh best
-#endif
     if (edge) { bytes += g.plane_blocks * 4; }                             // validity plane
     if (seeded) { bytes += (kTileBlocks + 1) * (kGated + 1) * 4; }         // starting masks of a seeded slice
     g.smem_bytes = (bytes + 15) & ~15;
@@ -276,8 +278,8 @@ __device__ __forceinline__ void hand_over(uint32_t* slot, bool fresh, uint32_t r
 // slice's best as the run to beat -- strictly, the nearest slice is nearer -- and a position the
 // nearest slice handed over is closed in every other slice, because phase 2 will walk on from
 // there through all farther distances anyway.
-template <int kMinLen, bool kEdge>
-__global__ void __launch_bounds__(kThreads, 3)
+template <int kMinLen, bool kEdge, int kQ>
+__global__ void __launch_bounds__(kThreads, kQ == 4 ? 3 : 5)
 match_table(const uint8_t* __restrict__ shard, long long back, long long n, long long ahead,
             uint32_t max_len, uint32_t max_dist, uint32_t* __restrict__ table,
             uint32_t* __restrict__ slice_tables, uint32_t* __restrict__ open_mask, int tile_first,
@@ -287,18 +289,12 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
     const long long t_begin = clock64();
 #endif
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    const Geometry geo = geometry(max_len, max_dist, kEdge, init_table != nullptr);
+    constexpr int kWarpOwned = warp_owned(kQ), kTileBlocks = tile_blocks(kQ), kTilePos = tile_pos(kQ);
+    constexpr int kStageBlocks = stage_blocks(kQ);
+    const Geometry geo = geometry(max_len, max_dist, kEdge, init_table != nullptr, kQ);
     const uint4* PL = reinterpret_cast<const uint4*>(smem_raw);           // [plane_blocks][2]
     uint8_t* best_len = smem_raw + geo.region_bytes;                      // [kTilePos + 32]
-#ifdef SQZ_FRESH_T
-    // A fresh best (set inside the current group of 128 distances) loses to an equal run at a
-    // nearer distance.  Inside a group a later candidate is nearer exactly when its t is smaller
-    // (d = 32 (m0 + t) - sh, sh descends), so two bits per position replace a read of the table word.
-    uint8_t* fresh_t = smem_raw + geo.region_bytes + kTilePos + 32;       // [kTilePos / 2] nibbles
-    uint32_t* VL = reinterpret_cast<uint32_t*>(smem_raw + geo.region_bytes + kTilePos + 32 + kTilePos / 2);
-#else
     uint32_t* VL = reinterpret_cast<uint32_t*>(smem_raw + geo.region_bytes + kTilePos + 32);
-#endif
 
     uint32_t* seed = VL + (kEdge ? geo.plane_blocks : 0);                  // [(kTileBlocks + 1)][kGated + 1], seeded slices only
     const int tile = tile_first + (int)blockIdx.x;
@@ -545,25 +541,12 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                             }
                             const uint32_t run = (uint32_t)(__ffs((int)win) - 1);
                             bool better = run > have;
-#ifdef SQZ_FRESH_T
-                            if (run == have && (fresh[q] & bit)) {
-                                better = (uint32_t)t < ((uint32_t)(fresh_t[k >> 1] >> ((k & 1) * 4)) & 3u);
-                                SQZ_COUNT(c_tie_fresh);
-                            }
-#else
                             if (run == have && (fresh[q] & bit)) { better = d < (*slot & 0xFFFFu); SQZ_COUNT(c_tie_fresh); }
-#endif
                             if (better) {
                                 SQZ_COUNT(c_better);
                                 best_len[k] = (uint8_t)run;
                                 *slot = (run << 16) | d;
                                 fresh[q] |= bit;
-#ifdef SQZ_FRESH_T
-                                {
-                                    const int sh4 = (k & 1) * 4;
-                                    fresh_t[k >> 1] = (uint8_t)((fresh_t[k >> 1] & ~(0xF << sh4)) | (t << sh4));
-                                }
-#endif
 #pragma unroll
                                 for (int g = 0; g < kGated; g++) {
                                     if (run > (uint32_t)(kMinLen + g)) { G[g][q] |= bit; }

@@ -547,11 +547,16 @@ static int device_state(DeviceState** out) {
     if (dev < 0 || dev >= kMaxDevices) { return fail(ENODEV, "device index out of range"); }
     DeviceState& d = g_dev[dev];
     std::call_once(d.once, [&d, dev] {
-        const int big = v2::geometry(sqz_gpu_max_len_limit, sqz_gpu_max_dist_limit, true, true).smem_bytes;
-        cudaError_t e = allow_smem(v2::match_table<3, false>, big);
-        if (e == cudaSuccess) { e = allow_smem(v2::match_table<3, true>, big); }
-        if (e == cudaSuccess) { e = allow_smem(v2::match_table<2, false>, big); }
-        if (e == cudaSuccess) { e = allow_smem(v2::match_table<2, true>, big); }
+        const int big4 = v2::geometry(sqz_gpu_max_len_limit, sqz_gpu_max_dist_limit, true, true, 4).smem_bytes;
+        const int big1 = v2::geometry(sqz_gpu_max_len_limit, sqz_gpu_max_dist_limit, true, true, 1).smem_bytes;
+        cudaError_t e = allow_smem(v2::match_table<3, false, 4>, big4);
+        if (e == cudaSuccess) { e = allow_smem(v2::match_table<3, true, 4>, big4); }
+        if (e == cudaSuccess) { e = allow_smem(v2::match_table<2, false, 4>, big4); }
+        if (e == cudaSuccess) { e = allow_smem(v2::match_table<2, true, 4>, big4); }
+        if (e == cudaSuccess) { e = allow_smem(v2::match_table<3, false, 1>, big1); }
+        if (e == cudaSuccess) { e = allow_smem(v2::match_table<3, true, 1>, big1); }
+        if (e == cudaSuccess) { e = allow_smem(v2::match_table<2, false, 1>, big1); }
+        if (e == cudaSuccess) { e = allow_smem(v2::match_table<2, true, 1>, big1); }
         if (e == cudaSuccess) {
             e = cudaFuncSetAttribute(v1::match_table, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)v1::smem_bytes(sqz_gpu_max_len_limit, sqz_gpu_max_dist_limit));
@@ -591,15 +596,30 @@ constexpr size_t kCursorBytes = 256;
 // Distance slices of a small shard (match_bitsliced.cuh): as many as it takes to give the device
 // about four waves of CTAs, a power of two, at most 32; none once the tiles alone fill it.
 // Fixed numbers (444 resident CTAs: 148 SMs x 3), so that the workspace size depends on n only.
-struct SlicePlan { int slices; int slice_words; size_t stride; };
+struct SlicePlan { int q; int slices; int slice_words; size_t stride; };
 
-constexpr size_t kSliceTarget = 2 * 444;        // CTAs a sliced launch aims for
+// How a shard is cut (match_bitsliced.cuh).  From a wave of throughput tiles on (444 resident CTAs of
+// 16,256 positions: 148 SMs x 3) it is tiles only, four blocks per thread.  Below that the latency
+// shape takes over -- one block per thread, 3,968 positions per CTA, five CTAs per SM -- and the
+// distance range is split into as many slices as it takes to give the device about two waves of
+// CTAs (a power of two, at most 32).  Fixed numbers, so that the workspace size depends on n only.
+constexpr size_t kWaveQ4 = 148 * 3, kWaveQ1 = 148 * 5;
 
 static SlicePlan slice_plan(size_t n, uint32_t max_dist) {
-    const size_t tiles = (n + v2::kTilePos - 1) / v2::kTilePos;
-    SlicePlan sp{1, 0, 0};
-    if (tiles == 0 || 2 * tiles > kSliceTarget) { return sp; }     // a wave of tiles or more: no slices
-    size_t want = (kSliceTarget + tiles - 1) / tiles;
+    SlicePlan sp{4, 1, 0, 0};
+    const size_t tiles4 = (n + v2::tile_pos(4) - 1) / v2::tile_pos(4);
+    int force_q = 0, force_s = 0;
+#ifdef SQZ_TUNING
+    if (const char* e = getenv("SQZ_Q")) { force_q = atoi(e); }
+    if (const char* e = getenv("SQZ_SLICES")) { force_s = atoi(e); }
+#endif
+    if (n == 0 || (force_q == 0 && tiles4 > kWaveQ4) || force_q == 4) {
+        if (force_s <= 1) { return sp; }
+    } else {
+        sp.q = 1;
+    }
+    const size_t tiles = (n + v2::tile_pos(sp.q) - 1) / v2::tile_pos(sp.q);
+    const size_t want = force_s > 0 ? (size_t)force_s : (2 * (sp.q == 1 ? kWaveQ1 : kWaveQ4) + tiles - 1) / tiles;
     int slices = 1;
     while ((size_t)slices < want && slices < 32) { slices <<= 1; }
     const int words = (int)((max_dist + 31) / 32);                 // word distances of a full scan
@@ -622,10 +642,14 @@ static size_t slice_bytes(const SlicePlan& sp) { return sp.slices > 1 ? (size_t)
 // more of, so their part is the largest any n' <= n asks for.
 extern "C" size_t sqz_gpu_match_workspace(size_t n) {
     size_t tables = slice_bytes(slice_plan(n, sqz_gpu_max_dist_limit));
-    const size_t tiles = std::min<size_t>((n + v2::kTilePos - 1) / v2::kTilePos, kSliceTarget);
+    const size_t tp = v2::tile_pos(1);
+    const size_t tiles = std::min<size_t>((n + tp - 1) / tp, 2 * kWaveQ1 + 1);
     for (size_t t = 1; t <= tiles; t++) {
-        tables = std::max(tables, slice_bytes(slice_plan(std::min(n, t * (size_t)v2::kTilePos), sqz_gpu_max_dist_limit)));
+        tables = std::max(tables, slice_bytes(slice_plan(std::min(n, t * tp), sqz_gpu_max_dist_limit)));
     }
+#ifdef SQZ_TUNING
+    tables = std::max(tables, (size_t)31 * ((std::min<size_t>(n, (size_t)64 << 20) + 63) / 64 * 64) * 4);   // whatever SQZ_SLICES asks for
+#endif
     return kCursorBytes + mask_bytes(n) + tables;
 }
 
@@ -706,15 +730,15 @@ static int launch_v1(const uint8_t* d_shard, size_t back, size_t n, size_t ahead
     return 0;
 }
 
-template <int kMinLen>
-static int launch_v2(const uint8_t* d_shard, size_t back, size_t n, size_t ahead, uint32_t max_len,
-                     uint32_t max_dist, uint32_t* d_table, void* d_work, cudaStream_t s) {
+template <int kMinLen, int kQ>
+static int launch_tiles(const SlicePlan& sp, const uint8_t* d_shard, size_t back, size_t n, size_t ahead, uint32_t max_len,
+                        uint32_t max_dist, uint32_t* d_table, void* d_work, cudaStream_t s) {
     DeviceState* dv = nullptr;
     if (int r = device_state(&dv)) { return r; }
     // Tiles whose every position sees the full max_dist window and max_len of
     // look-ahead run the plain variant; the rest (start of the first shard, end
     // of the last one, a partial last tile) run the variant with a validity plane.
-    const long long tp = v2::kTilePos;
+    const long long tp = v2::tile_pos(kQ);
     const long long tiles = ((long long)n + tp - 1) / tp;
     if (tiles > 0x7FFFFFFFll) { return fail(EINVAL, "shard too large for one launch"); }
     long long t_lo = back >= max_dist ? 0 : ((long long)max_dist - (long long)back + tp - 1) / tp;
@@ -726,11 +750,10 @@ static int launch_v2(const uint8_t* d_shard, size_t back, size_t n, size_t ahead
     unsigned int* d_counters = static_cast<unsigned int*>(d_work);
     uint32_t* d_open = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(d_work) + kCursorBytes);
     CU(cudaMemsetAsync(d_counters, 0, 16, s));
-    const int smem_main = v2::geometry(max_len, max_dist, false).smem_bytes;
-    const int smem_edge = v2::geometry(max_len, max_dist, true).smem_bytes;
+    const int smem_main = v2::geometry(max_len, max_dist, false, false, kQ).smem_bytes;
+    const int smem_edge = v2::geometry(max_len, max_dist, true, false, kQ).smem_bytes;
     // small shards: the distance range is split across CTAs as well, the slices' tables sit behind
     // the work list and are folded into d_table afterwards
-    const SlicePlan sp = slice_plan(n, max_dist);
     uint32_t* d_slices = sp.slices > 1 ? reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(d_work) + kCursorBytes + mask_bytes(n)) : nullptr;
     // The few edge tiles run concurrently with the interior tiles: leading and trailing edge
     // tiles each on a side stream of the device, forked from and joined back into `s`.
@@ -741,8 +764,8 @@ static int launch_v2(const uint8_t* d_shard, size_t back, size_t n, size_t ahead
         CU(cudaEventRecord(fork.e, s));
     }
     // sliced: the nearest slice first (into d_table), then the others seeded with its result
-    const int smem_main_seeded = v2::geometry(max_len, max_dist, false, true).smem_bytes;
-    const int smem_edge_seeded = v2::geometry(max_len, max_dist, true, true).smem_bytes;
+    const int smem_main_seeded = v2::geometry(max_len, max_dist, false, true, kQ).smem_bytes;
+    const int smem_edge_seeded = v2::geometry(max_len, max_dist, true, true, kQ).smem_bytes;
     auto launch = [&](auto kernel, long long first, long long count, bool edge, cudaStream_t on) -> cudaError_t {
         kernel<<<dim3((unsigned)count, 1), v2::kThreads, edge ? smem_edge : smem_main, on>>>(
             d_shard, (long long)back, (long long)n, (long long)ahead, max_len, max_dist, d_table, d_slices,
@@ -759,20 +782,20 @@ static int launch_v2(const uint8_t* d_shard, size_t back, size_t n, size_t ahead
     cudaError_t le = cudaSuccess;
     if (lead) {
         CU(cudaStreamWaitEvent(dv->side, fork.e, 0));
-        le = launch(v2::match_table<kMinLen, true>, 0, t_lo, true, dv->side);
+        le = launch(v2::match_table<kMinLen, true, kQ>, 0, t_lo, true, dv->side);
         if (le != cudaSuccess) { return fail(cuda_code(le), "match_table_v2_edge", le); }
         CU(join1.create());
         CU(cudaEventRecord(join1.e, dv->side));
     }
     if (trail) {
         CU(cudaStreamWaitEvent(dv->side2, fork.e, 0));
-        le = launch(v2::match_table<kMinLen, true>, t_hi, tiles - t_hi, true, dv->side2);
+        le = launch(v2::match_table<kMinLen, true, kQ>, t_hi, tiles - t_hi, true, dv->side2);
         if (le != cudaSuccess) { return fail(cuda_code(le), "match_table_v2_edge", le); }
         CU(join2.create());
         CU(cudaEventRecord(join2.e, dv->side2));
     }
     if (t_hi > t_lo) {
-        le = launch(v2::match_table<kMinLen, false>, t_lo, t_hi - t_lo, false, s);
+        le = launch(v2::match_table<kMinLen, false, kQ>, t_lo, t_hi - t_lo, false, s);
         if (le != cudaSuccess) { return fail(cuda_code(le), "match_table_v2", le); }
     }
     if (join1.e != nullptr) { CU(cudaStreamWaitEvent(s, join1.e, 0)); }
@@ -790,6 +813,14 @@ static int launch_v2(const uint8_t* d_shard, size_t back, size_t n, size_t ahead
         d_counters, g_tile_cycles ? g_tile_cycles + (1 << 20) : nullptr, fs.chunk, fs.sub);
     LAUNCHED("match_finish_marked");
     return 0;
+}
+
+template <int kMinLen>
+static int launch_v2(const uint8_t* d_shard, size_t back, size_t n, size_t ahead, uint32_t max_len,
+                     uint32_t max_dist, uint32_t* d_table, void* d_work, cudaStream_t s) {
+    const SlicePlan sp = slice_plan(n, max_dist);
+    return sp.q == 1 ? launch_tiles<kMinLen, 1>(sp, d_shard, back, n, ahead, max_len, max_dist, d_table, d_work, s)
+                     : launch_tiles<kMinLen, 4>(sp, d_shard, back, n, ahead, max_len, max_dist, d_table, d_work, s);
 }
 
 extern "C" int sqz_gpu_match_table_device_ws(const uint8_t* d_shard, size_t back, size_t n,
@@ -1672,7 +1703,7 @@ extern "C" int sqz_gpu_expand_tokens_device(const uint32_t* d_tokens, size_t n_t
     uint8_t* flags = w + parse::align_up(blocks * 8 + 8);
     uint64_t* d_total = reinterpret_cast<uint64_t*>(flags);
     int* d_bad = reinterpret_cast<int*>(flags + 8);
-    int* d_changed = reinterpret_cast<int*>(flags + 16);
+    int* d_rounds = reinterpret_cast<int*>(flags + 16);          // three flags of the doubling rounds
     uint32_t* hop = reinterpret_cast<uint32_t*>(flags + 256);
     CU(cudaMemsetAsync(flags, 0, 256, s));
     expand::block_lengths<<<(unsigned)blocks, 256, 0, s>>>(d_tokens, n_tokens, block_off);
@@ -1687,17 +1718,19 @@ extern "C" int sqz_gpu_expand_tokens_device(const uint32_t* d_tokens, size_t n_t
                                                         (uint64_t)bytes, d_bad);
     LAUNCHED("expand_place_tokens");
     const unsigned grid = (unsigned)sm_count() * 8;
-    for (int round = 0; round < 40; round++) {       // a chain halves its hop count every round
-        CU(cudaMemsetAsync(d_changed, 0, 4, s));
-        expand::double_hops<<<grid, 256, 0, s>>>(hop, (uint64_t)bytes, d_changed);
+    // a chain halves its hop count every round: 32 rounds cover 31-bit hops; rounds after the last
+    // useful one return at once (the device decides, the host does not wait in between)
+    for (int round = 0; round < 32; round++) {
+        expand::double_hops<<<grid, 256, 0, s>>>(hop, (uint64_t)bytes, d_rounds, round);
         LAUNCHED("expand_double_hops");
-        CU(cudaMemcpyAsync(&h, flags, 24, cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
-        if (h.bad != 0) { return fail(EINVAL, "a match reaches before the start of the output"); }
-        if (h.changed == 0) { break; }
     }
     expand::fetch_bytes<<<grid, 256, 0, s>>>(hop, d_out, (uint64_t)bytes);
     LAUNCHED("expand_fetch_bytes");
+    // one wait for the whole copy phase: was a token out of range?  (The bytes of such a stream are
+    // garbage but in bounds: place_tokens cut every bad hop to 0.)
+    CU(cudaMemcpyAsync(&h, flags, 16, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (h.bad != 0) { return fail(EINVAL, "a match reaches before the start of the output"); }
     return 0;
 }
 

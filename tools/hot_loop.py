@@ -26,7 +26,7 @@ def sass(lib, mangled_part):
     return keep
 
 
-def hot_loop(lib=None, kernel="match_tableILi3ELb0E"):
+def hot_loop(lib=None, kernel="match_tableILi3ELb0ELi4E"):
     lib = lib or os.path.join(ROOT, "sqz_b200", "lib", "libsqz_b200.so")
     ins = sass(lib, kernel)
     shfl = [a for a, t in ins if t.startswith("SHFL.DOWN")]
