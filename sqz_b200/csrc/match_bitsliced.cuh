@@ -128,8 +128,8 @@ __device__ __forceinline__ uint32_t fsr(uint32_t lo, uint32_t hi, int s) {
 // `reach`; `room` = min(max_len, bytes left).  (best, bdist) enter with what
 // phase 1 found (all distances < max(bdist+1, d_from) are settled) and leave final.
 //
-// 32 lanes x 4 candidates per step: every lane takes one aligned word and tests
-// the four byte offsets in it against the 4 bytes a candidate has to match to
+// 32 lanes x 2 words x 4 candidates per step: every lane takes two aligned words and tests
+// the four byte offsets in each against the 4 bytes a candidate has to match to
 // win (the word ending at offset need-1; the first `need` bytes while
 // need < 4).  Hits are verified nearest first by all lanes together.
 // ---------------------------------------------------------------------------
@@ -186,65 +186,77 @@ __device__ __forceinline__ void finish_position(const uint8_t* __restrict__ S, i
         const int c_hi = a - (int)d0;                      // nearest candidate still open
         const int c_lo = a - (int)reach;                   // farthest candidate
         bool improved = false;
-        for (int wtop = c_hi >> 2; (wtop << 2) + 3 >= c_lo && !improved; wtop -= 32) {
-            const int w = wtop - lane;                     // lane 0 holds the nearest word
-            uint32_t hb = 0;
+        // one step = 64 words = 256 candidates: every lane takes the word 32 below its first one as well,
+        // so that the loop control, the vote and the range test are paid once per 256 candidates
+        for (int wtop = c_hi >> 2; (wtop << 2) + 3 >= c_lo && !improved; wtop -= 64) {
+            uint32_t hb0 = 0u, hb1 = 0u;                   // hits in the nearer word / in the farther word
             n_steps++;
-            // interior steps: all 128 candidates of the warp lie strictly inside (c_lo, c_hi]
-            const bool interior = (wtop << 2) + 3 <= c_hi && ((wtop - 31) << 2) >= c_lo;
-            if (interior || (w << 2) + 3 >= c_lo) {
-                SQZ_CHECK(w >= 0 && w <= w_last, "finish: candidate word outside the image");
-                const uint32_t low = W[w], hiw = word_at(W, w + 1, w_last);
-                const uint32_t t0 = (low ^ key) & mask;
-                const uint32_t t1 = (__byte_perm(low, hiw, 0x4321) ^ key) & mask;
-                const uint32_t t2 = (__byte_perm(low, hiw, 0x5432) ^ key) & mask;
-                const uint32_t t3 = (__byte_perm(low, hiw, 0x6543) ^ key) & mask;
-                hb = (t0 == 0 ? 1u : 0u) | (t1 == 0 ? 2u : 0u) | (t2 == 0 ? 4u : 0u) | (t3 == 0 ? 8u : 0u);
-                if (!interior) {
-                    const int kmax = min(3, c_hi - (w << 2));  // only the very first word is cut at the top
-                    const int kmin = max(0, c_lo - (w << 2));
-                    hb &= (2u << kmax) - 1u;
-                    hb &= ~((1u << kmin) - 1u);
-                }
-                if (hb != 0 && so >= 0) {
-                    const int w2 = w - back_words;         // >= 0: the window lies inside the match
-                    // words below the image start can only feed candidates that are cut off anyway
-                    SQZ_CHECK(w2 <= w_last, "finish: second window outside the image");
-                    const uint32_t x0 = w2 >= 0 ? W[w2] : 0u;
-                    const uint32_t x1 = w2 + 1 >= 0 ? word_at(W, w2 + 1, w_last) : 0u;
-                    const uint32_t x2 = w2 + 2 >= 0 ? word_at(W, w2 + 2, w_last) : 0u;
-                    const uint32_t lo2 = fsr(x0, x1, sh8), hi2 = fsr(x1, x2, sh8);
-                    const uint32_t u0 = lo2 ^ key2;
-                    const uint32_t u1 = __byte_perm(lo2, hi2, 0x4321) ^ key2;
-                    const uint32_t u2 = __byte_perm(lo2, hi2, 0x5432) ^ key2;
-                    const uint32_t u3 = __byte_perm(lo2, hi2, 0x6543) ^ key2;
-                    hb &= (u0 == 0 ? 1u : 0u) | (u1 == 0 ? 2u : 0u) | (u2 == 0 ? 4u : 0u) | (u3 == 0 ? 8u : 0u);
+            // interior steps: all 256 candidates of the warp lie strictly inside (c_lo, c_hi]
+            const bool interior = (wtop << 2) + 3 <= c_hi && ((wtop - 63) << 2) >= c_lo;
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                const int w = wtop - 32 * half - lane;     // lane 0 holds the nearest word of its half
+                if (interior || (w << 2) + 3 >= c_lo) {
+                    SQZ_CHECK(w >= 0 && w <= w_last, "finish: candidate word outside the image");
+                    const uint32_t low = W[w], hiw = word_at(W, w + 1, w_last);
+                    const uint32_t t0 = (low ^ key) & mask;
+                    const uint32_t t1 = (__byte_perm(low, hiw, 0x4321) ^ key) & mask;
+                    const uint32_t t2 = (__byte_perm(low, hiw, 0x5432) ^ key) & mask;
+                    const uint32_t t3 = (__byte_perm(low, hiw, 0x6543) ^ key) & mask;
+                    uint32_t hits = (t0 == 0 ? 1u : 0u) | (t1 == 0 ? 2u : 0u) | (t2 == 0 ? 4u : 0u) | (t3 == 0 ? 8u : 0u);
+                    if (!interior) {
+                        const int kmax = min(3, c_hi - (w << 2));  // only the very first word is cut at the top
+                        const int kmin = max(0, c_lo - (w << 2));
+                        hits &= kmax >= 0 ? (2u << kmax) - 1u : 0u;
+                        hits &= ~((1u << kmin) - 1u);
+                    }
+                    if (hits != 0 && so >= 0) {
+                        const int w2 = w - back_words;         // >= 0: the window lies inside the match
+                        // words below the image start can only feed candidates that are cut off anyway
+                        SQZ_CHECK(w2 <= w_last, "finish: second window outside the image");
+                        const uint32_t x0 = w2 >= 0 ? W[w2] : 0u;
+                        const uint32_t x1 = w2 + 1 >= 0 ? word_at(W, w2 + 1, w_last) : 0u;
+                        const uint32_t x2 = w2 + 2 >= 0 ? word_at(W, w2 + 2, w_last) : 0u;
+                        const uint32_t lo2 = fsr(x0, x1, sh8), hi2 = fsr(x1, x2, sh8);
+                        const uint32_t u0 = lo2 ^ key2;
+                        const uint32_t u1 = __byte_perm(lo2, hi2, 0x4321) ^ key2;
+                        const uint32_t u2 = __byte_perm(lo2, hi2, 0x5432) ^ key2;
+                        const uint32_t u3 = __byte_perm(lo2, hi2, 0x6543) ^ key2;
+                        hits &= (u0 == 0 ? 1u : 0u) | (u1 == 0 ? 2u : 0u) | (u2 == 0 ? 4u : 0u) | (u3 == 0 ? 8u : 0u);
+                    }
+                    if (half == 0) { hb0 = hits; } else { hb1 = hits; }
                 }
             }
-            for (;;) {
-                const uint32_t any = __ballot_sync(0xFFFFFFFFu, hb != 0);
-                if (any == 0) { break; }
-                const int src = __ffs((int)any) - 1;                       // lowest lane = nearest word
-                const int kk = 31 - __clz((int)(hb | 1u));                 // nearest candidate in my word
-                const int c = __shfl_sync(0xFFFFFFFFu, (w << 2) + kk, src);
-                const uint32_t hit_d = (uint32_t)(a - c);
-                // cooperative verify: common prefix of S[xi..] and S[xi-hit_d..], capped at room
-                uint32_t m = room;
-                n_verify++;
-                for (uint32_t base = 0; base < room; base += 32) {
-                    n_rounds++;
-                    const uint32_t k = base + (uint32_t)lane;
-                    SQZ_CHECK(k >= room || (xi - (int)hit_d + (int)k >= 0 && xi + (int)k < x_end), "finish: verify outside the image");
-                    const bool diff = k < room && S[xi + (int)k] != S[xi - (int)hit_d + (int)k];
-                    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, diff);
-                    if (bal != 0) { m = base + (uint32_t)(__ffs((int)bal) - 1); break; }
+            if (__ballot_sync(0xFFFFFFFFu, (hb0 | hb1) != 0) == 0) { continue; }
+#pragma unroll
+            for (int half = 0; half < 2; half++) {         // the nearer half first
+                const int w = wtop - 32 * half - lane;
+                uint32_t& mine = half == 0 ? hb0 : hb1;
+                while (!improved) {
+                    const uint32_t any = __ballot_sync(0xFFFFFFFFu, mine != 0);
+                    if (any == 0) { break; }
+                    const int src = __ffs((int)any) - 1;                       // lowest lane = nearest word
+                    const int kk = 31 - __clz((int)(mine | 1u));               // nearest candidate in my word
+                    const int c = __shfl_sync(0xFFFFFFFFu, (w << 2) + kk, src);
+                    const uint32_t hit_d = (uint32_t)(a - c);
+                    // cooperative verify: common prefix of S[xi..] and S[xi-hit_d..], capped at room
+                    uint32_t m = room;
+                    n_verify++;
+                    for (uint32_t base = 0; base < room; base += 32) {
+                        n_rounds++;
+                        const uint32_t k = base + (uint32_t)lane;
+                        SQZ_CHECK(k >= room || (xi - (int)hit_d + (int)k >= 0 && xi + (int)k < x_end), "finish: verify outside the image");
+                        const bool diff = k < room && S[xi + (int)k] != S[xi - (int)hit_d + (int)k];
+                        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, diff);
+                        if (bal != 0) { m = base + (uint32_t)(__ffs((int)bal) - 1); break; }
+                    }
+                    if (m >= need) {
+                        if (runner_up != nullptr) { *runner_up = best; }   // longest run among the nearer candidates
+                        best = m; bdist = hit_d; improved = true; n_improve++;
+                        break;
+                    }
+                    if (lane == src) { mine &= ~(1u << kk); }
                 }
-                if (m >= need) {
-                    if (runner_up != nullptr) { *runner_up = best; }   // longest run among the nearer candidates
-                    best = m; bdist = hit_d; improved = true; n_improve++;
-                    break;
-                }
-                if (lane == src) { hb &= ~(1u << kk); }
             }
         }
         if (!improved) { break; }
@@ -670,7 +682,9 @@ constexpr int kFinishCtasPerSm = 6;       // resident CTAs the staged window all
 struct FinishShape { int chunk, sub, smem_bytes; };
 
 inline FinishShape finish_shape(long long n, uint32_t max_len, uint32_t max_dist, int sms) {
-    long long chunk = n / (2LL * kFinishCtasPerSm * sms);
+    // eight chunks per resident CTA: where every position of a chunk needs a search (an ELF table),
+    // the chunk's CTA is what the whole shard waits for
+    long long chunk = n / (8LL * kFinishCtasPerSm * sms);
     chunk = chunk / 128 * 128;
     chunk = chunk < 128 ? 128 : (chunk > kChunk ? kChunk : chunk);
     FinishShape f;
@@ -683,7 +697,7 @@ inline FinishShape finish_shape(long long n, uint32_t max_len, uint32_t max_dist
     return f;
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, kFinishCtasPerSm)
 finish_marked(const uint8_t* __restrict__ shard, long long back, long long n, long long ahead,
               uint32_t min_len, uint32_t max_len, uint32_t max_dist, uint32_t* __restrict__ table,
               const uint32_t* __restrict__ open_mask, unsigned int* __restrict__ counters,

@@ -216,9 +216,19 @@ __global__ void unpack_table(const uint32_t* __restrict__ table, size_t n,
 // ---------------------------------------------------------------------------
 namespace parse {
 
-constexpr int kPB = 4096;        // positions per parse block
+constexpr int kPBLarge = 4096;   // positions per parse block
+constexpr int kPBSmall = 1024;   // ... of a small shard: the walks of a block are serial, shorter ones finish sooner
+constexpr size_t kSmallShard = (size_t)8 << 20;
 constexpr int kMapStride = 512;  // = sqz_gpu_max_len_limit entries per exit map
-constexpr int kGroup = 128;      // blocks per chain group
+constexpr int kGroupMax = 128;   // blocks per chain group (large shards; small ones use about sqrt(blocks))
+
+static int parse_block(size_t n) { return n <= kSmallShard ? kPBSmall : kPBLarge; }
+
+static int group_size(size_t blocks) {
+    int g = 8;
+    while (g < kGroupMax && (size_t)g * g < blocks) { g <<= 1; }
+    return g;
+}
 
 struct Work {                    // carved out of the caller's d_work
     uint16_t* exit_map;          // [blocks][kMapStride]
@@ -228,22 +238,30 @@ struct Work {                    // carved out of the caller's d_work
     uint32_t* count;             // [blocks]
     uint64_t* offset;            // [blocks]
     size_t blocks, groups;
+    int pb, group;               // positions per block, blocks per group
 };
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
-static size_t workspace(size_t n) {
-    const size_t blocks = (n + kPB - 1) / kPB + 1;
-    const size_t groups = (blocks + kGroup - 1) / kGroup + 1;
+static size_t workspace_for(size_t n, int pb) {
+    const size_t blocks = (n + pb - 1) / pb + 1;
+    const size_t groups = (blocks + 8 - 1) / 8 + 1;            // the smallest group size: an upper bound
     return align_up(blocks * kMapStride * 2) + align_up(groups * kMapStride * 2) +
            align_up((groups + 1) * 4) + align_up(blocks * 4) + align_up(blocks * 4) +
            align_up(blocks * 8) + 256;
 }
 
+// enough for every shard of at most n positions (small shards use smaller blocks)
+static size_t workspace(size_t n) {
+    return std::max(workspace_for(n, parse_block(n)), workspace_for(std::min(n, kSmallShard), kPBSmall));
+}
+
 static Work carve(void* d_work, size_t n) {
     Work w;
-    w.blocks = (n + kPB - 1) / kPB;
-    w.groups = (w.blocks + kGroup - 1) / kGroup;
+    w.pb = parse_block(n);
+    w.blocks = (n + w.pb - 1) / w.pb;
+    w.group = group_size(w.blocks);
+    w.groups = (w.blocks + w.group - 1) / w.group;
     const size_t blocks = w.blocks + 1, groups = w.groups + 1;
     uint8_t* p = (uint8_t*)d_work;
     p = (uint8_t*)(((uintptr_t)p + 255) & ~(uintptr_t)255);
@@ -261,6 +279,7 @@ __device__ __forceinline__ uint32_t step_of(uint32_t word, uint32_t min_len) {
     return len >= min_len ? len : 1u;
 }
 
+template <int kPB>
 __global__ void __launch_bounds__(256)
 parse_exit_map(const uint32_t* __restrict__ table, size_t n, uint32_t min_len,
                uint32_t max_len, uint16_t* __restrict__ exit_map) {
@@ -290,11 +309,11 @@ parse_exit_map(const uint32_t* __restrict__ table, size_t n, uint32_t min_len,
     }
 }
 
-__global__ void chain_groups(const uint16_t* __restrict__ exit_map, size_t blocks,
+__global__ void chain_groups(const uint16_t* __restrict__ exit_map, size_t blocks, int group,
                              uint32_t max_len, uint16_t* __restrict__ group_map) {
     const size_t g = blockIdx.x;
-    const size_t first = g * kGroup;
-    const size_t last = min(first + kGroup, blocks);
+    const size_t first = g * (size_t)group;
+    const size_t last = min(first + (size_t)group, blocks);
     for (uint32_t e = threadIdx.x; e < max_len; e += blockDim.x) {
         uint32_t x = e;
         for (size_t b = first; b < last; b++) { x = exit_map[b * kMapStride + x]; }
@@ -326,13 +345,13 @@ __global__ void chain_total(const uint16_t* __restrict__ group_map, size_t group
     }
 }
 
-__global__ void chain_expand(const uint16_t* __restrict__ exit_map, size_t blocks,
+__global__ void chain_expand(const uint16_t* __restrict__ exit_map, size_t blocks, int group,
                              size_t groups, const uint32_t* __restrict__ group_entry,
                              uint32_t* __restrict__ block_entry) {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= groups) { return; }
-    const size_t first = g * kGroup;
-    const size_t last = min(first + kGroup, blocks);
+    const size_t first = g * (size_t)group;
+    const size_t last = min(first + (size_t)group, blocks);
     uint32_t x = group_entry[g];
     for (size_t b = first; b < last; b++) {
         block_entry[b] = x;
@@ -413,7 +432,7 @@ __device__ __forceinline__ uint32_t symbols_of_match(uint32_t len, uint32_t dist
 // kEmit = false: count only (first pass, feeds the scan that places every block's tokens).
 constexpr int kParseWarps = 2;
 
-template <bool kEmit, bool kSymbols>
+template <bool kEmit, bool kSymbols, int kPB>
 __global__ void __launch_bounds__(32 * kParseWarps)
 parse_walk(const uint8_t* __restrict__ shard, const uint32_t* __restrict__ table, size_t n,
            size_t blocks, uint32_t min_len, const uint32_t* __restrict__ block_entry,
@@ -885,9 +904,13 @@ extern "C" size_t sqz_gpu_parse_workspace(size_t n) { return parse::workspace(n)
 
 static int parse_maps(const uint32_t* d_table, size_t n, uint32_t min_len, uint32_t max_len,
                       const parse::Work& w, cudaStream_t s) {
-    parse::parse_exit_map<<<(unsigned)w.blocks, 256, 0, s>>>(d_table, n, min_len, max_len, w.exit_map);
+    if (w.pb == parse::kPBSmall) {
+        parse::parse_exit_map<parse::kPBSmall><<<(unsigned)w.blocks, 256, 0, s>>>(d_table, n, min_len, max_len, w.exit_map);
+    } else {
+        parse::parse_exit_map<parse::kPBLarge><<<(unsigned)w.blocks, 256, 0, s>>>(d_table, n, min_len, max_len, w.exit_map);
+    }
     LAUNCHED("parse_exit_map");
-    parse::chain_groups<<<(unsigned)w.groups, 256, 0, s>>>(w.exit_map, w.blocks, max_len, w.group_map);
+    parse::chain_groups<<<(unsigned)w.groups, 256, 0, s>>>(w.exit_map, w.blocks, w.group, max_len, w.group_map);
     LAUNCHED("chain_groups");
     return 0;
 }
@@ -913,22 +936,26 @@ static int parse_launch(const uint8_t* d_shard, const uint32_t* d_table, size_t 
     parse::chain_top<<<1, 1, 0, s>>>(w.group_map, w.groups, d_entry, entry, w.group_entry, d_result);
     LAUNCHED("chain_top");
     parse::chain_expand<<<(unsigned)((w.groups + 127) / 128), 128, 0, s>>>(
-        w.exit_map, w.blocks, w.groups, w.group_entry, w.block_entry);
+        w.exit_map, w.blocks, w.group, w.groups, w.group_entry, w.block_entry);
     LAUNCHED("chain_expand");
     const unsigned wb = (unsigned)((w.blocks + parse::kParseWarps - 1) / parse::kParseWarps);
     const unsigned wt = 32 * parse::kParseWarps;
-    parse::parse_walk<false, false><<<wb, wt, 0, s>>>(d_shard, d_table, n, w.blocks, min_len, w.block_entry,
-                                                      w.count, nullptr, nullptr, 0);
+    const bool small = w.pb == parse::kPBSmall;
+    if (small) {
+        parse::parse_walk<false, false, parse::kPBSmall><<<wb, wt, 0, s>>>(d_shard, d_table, n, w.blocks, min_len, w.block_entry,
+                                                                           w.count, nullptr, nullptr, 0);
+    } else {
+        parse::parse_walk<false, false, parse::kPBLarge><<<wb, wt, 0, s>>>(d_shard, d_table, n, w.blocks, min_len, w.block_entry,
+                                                                           w.count, nullptr, nullptr, 0);
+    }
     LAUNCHED("parse_count");
     parse::scan_counts<<<1, 1024, 0, s>>>(w.count, w.blocks, w.offset, d_result);
     LAUNCHED("scan_counts");
-    if (symbols) {
-        parse::parse_walk<true, true><<<wb, wt, 0, s>>>(d_shard, d_table, n, w.blocks, min_len, w.block_entry,
-                                                        nullptr, w.offset, d_tokens, cap);
-    } else {
-        parse::parse_walk<true, false><<<wb, wt, 0, s>>>(d_shard, d_table, n, w.blocks, min_len, w.block_entry,
-                                                         nullptr, w.offset, d_tokens, cap);
-    }
+#define SQZ_EMIT(SYM, PB) parse::parse_walk<true, SYM, PB><<<wb, wt, 0, s>>>(d_shard, d_table, n, w.blocks, min_len, \
+                                                                             w.block_entry, nullptr, w.offset, d_tokens, cap)
+    if (symbols) { if (small) { SQZ_EMIT(true, parse::kPBSmall); } else { SQZ_EMIT(true, parse::kPBLarge); } }
+    else         { if (small) { SQZ_EMIT(false, parse::kPBSmall); } else { SQZ_EMIT(false, parse::kPBLarge); } }
+#undef SQZ_EMIT
     LAUNCHED("parse_emit");
     return 0;
 }

@@ -68,3 +68,18 @@ def test_product_never_links_the_oracle():
             if f.endswith((".py", ".c", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(root, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_workspaces_cover_every_smaller_shard():
+    """A workspace sized for n serves every shard of at most n positions (the pipeline sizes its slots
+    once and sees chunks of many sizes; small shards use more slice tables and smaller parse blocks)."""
+    import random
+    L = _lib.load()
+    rnd = random.Random(5)
+    ns = sorted(set([1, 31, 32, 3968, 3969, 16256, 10**6, 1 << 20, 4 << 20, 5900000, 7217663, 7217665, 8 << 20, (8 << 20) + 1,
+                     16 << 20, 32 << 20, 1 << 30] + [rnd.randrange(1, 40 << 20) for _ in range(200)]))
+    pm = pp = 0
+    for n in ns:
+        m, p = L.sqz_gpu_match_workspace(n), L.sqz_gpu_parse_workspace(n)
+        assert m >= pm and p >= pp, n
+        pm, pp = m, p
