@@ -76,7 +76,12 @@ __host__ __device__ constexpr int stage_blocks(int q) { return tile_blocks(q) - 
 #ifndef SQZ_GATED
 #define SQZ_GATED 3
 #endif
-constexpr int kGated = SQZ_GATED;         // need is tracked exactly up to min_len + kGated
+#ifndef SQZ_GATED_Q1
+#define SQZ_GATED_Q1 3
+#endif
+// need is tracked exactly up to min_len + gated(q): three levels measure best for the throughput
+// shape (each level costs 4-5 % of its loop)
+__host__ __device__ constexpr int gated(int q) { return q == 1 ? SQZ_GATED_Q1 : SQZ_GATED; }
 #ifndef SQZ_TIE_MASK
 #define SQZ_TIE_MASK 0
 #endif
@@ -112,7 +117,7 @@ __host__ __device__ inline Geometry geometry(uint32_t max_len, uint32_t max_dist
     g.region_bytes = g.plane_blocks * 32;                                  // 8 planes x 4 B per block
     int bytes = g.region_bytes + kTilePos + 32;                            // + one state byte per position
     if (edge) { bytes += g.plane_blocks * 4; }                             // validity plane
-    if (seeded) { bytes += (kTileBlocks + 1) * (kGated + 1) * 4; }         // starting masks of a seeded slice
+    if (seeded) { bytes += (kTileBlocks + 1) * (gated(q) + 1) * 4; }       // starting masks of a seeded slice
     g.smem_bytes = (bytes + 15) & ~15;
     return g;
 }
@@ -303,6 +308,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
     extern __shared__ __align__(16) uint8_t smem_raw[];
     constexpr int kWarpOwned = warp_owned(kQ), kTileBlocks = tile_blocks(kQ), kTilePos = tile_pos(kQ);
     constexpr int kStageBlocks = stage_blocks(kQ);
+    constexpr int kGated = gated(kQ);
     const Geometry geo = geometry(max_len, max_dist, kEdge, init_table != nullptr, kQ);
     const uint4* PL = reinterpret_cast<const uint4*>(smem_raw);           // [plane_blocks][2]
     uint8_t* best_len = smem_raw + geo.region_bytes;                      // [kTilePos + 32]
