@@ -671,7 +671,8 @@ combine_slices(uint32_t* __restrict__ table, const uint32_t* __restrict__ slice_
 //     full run either (it would be a run > m* at p) and inherit (max_len, d') on a byte compare.
 //     A block repeated at a large distance costs one search per ~kSlack positions instead of one
 //     per position (BASELINE config 2, csrc.cat: 17 % of the positions).  d' = 1 needs no search.
-//   search -- otherwise the exact warp-wide search (finish_position).
+//   search -- otherwise the exact warp-wide search (finish_position), bounded from above by the
+//     neighbour's run + 1 when the neighbour is finished and not cut at max_len.
 //
 // counters[0] is the segment cursor.
 // ---------------------------------------------------------------------------
@@ -829,8 +830,16 @@ finish_marked(const uint8_t* __restrict__ shard, long long back, long long n, lo
                         uint32_t b2 = mode == 2 ? max_len - slack - 1 : best;
                         uint32_t d2 = mode == 2 ? 0u : bdist;
                         uint32_t runner_up = b2;
+                        // A finished neighbour bounds this position from above: a candidate that gives p a run of L
+                        // gives p+1 a run of L-1, so L <= (best run at p+1) + 1 -- unless that one was cut at max_len.
+                        // The search ends at the nearest candidate that reaches the bound, and does not start at all
+                        // when phase 1 had found one already.
+                        uint32_t bound = room;
+                        if (p + 1 < n && (nb & kOpenBit) == 0 && nlen != max_len) {
+                            bound = min(room, (nlen >= min_len ? nlen : min_len - 1) + 1);
+                        }
                         finish_position(img + (first + off - mis4), mis4 + (int)far, x_end, resume, mode == 2 ? ndist - 1 : far,
-                                        room, min_len, b2, d2, lane, dbg, &runner_up);
+                                        bound, min_len, b2, d2, lane, dbg, &runner_up);
                         if (mode == 2) {
                             best = max_len;
                             bdist = b2 == max_len ? d2 : ndist;
