@@ -150,6 +150,13 @@ void sqz_encode_symbols_chunked(struct sqz* s, struct sqz_bitstream* bs,
  * reject); the reference for what the GPU emits.                             */
 void sqz_symbols_of_tokens(const uint32_t* tokens, uint64_t count, uint32_t* words);
 
+/* squeeze.decompress (squeeze.h:502-551).  On return the bitstream stands where
+ * the reference's bit-at-a-time reader would (bitstream.h:65-95): `read` at the
+ * end of the last word the stream used, the unused bits of that word in b64/bits.
+ * The decoder reads ahead; in memory mode a word it pulled too early is given
+ * back, so that data stored behind the stream can be read from the same
+ * sqz_bitstream.  A callback source cannot take a word back: there up to one
+ * 64-bit word more than the reference would have asked for has been consumed. */
 void sqz_decompress(struct sqz* s, struct sqz_bitstream* bs,
                     uint8_t* data, uint64_t bytes);
 
