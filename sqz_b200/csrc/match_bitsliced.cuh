@@ -625,13 +625,15 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
 // that slice and the nearer ones have settled is the state phase 2 resumes from, at the open
 // slice's resume distance (everything farther is searched again, exactly).
 __global__ void __launch_bounds__(256)
-combine_slices(uint32_t* __restrict__ table, const uint32_t* __restrict__ slice_tables, long long n,
+combine_slices(uint32_t* __restrict__ table, const uint32_t* __restrict__ slice_tables, long long first, long long end,
                long long slice_stride, int slices, uint32_t* __restrict__ open_mask) {
-    const long long padded = (n + 31) & ~31LL;
-    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < padded; p += (long long)gridDim.x * blockDim.x) {
+    // positions [first, end): first is a multiple of 32, and the positions from `end` to the next multiple of 32
+    // belong to nobody else (end is the end of the shard or a tile boundary)
+    const long long padded = (end + 31) & ~31LL;
+    for (long long p = first + (long long)blockIdx.x * blockDim.x + threadIdx.x; p < padded; p += (long long)gridDim.x * blockDim.x) {
         uint32_t best = 0;
         bool open = false;
-        if (p < n) {
+        if (p < end) {
             for (int sl = 0; sl < slices; sl++) {
                 const uint32_t w = sl == 0 ? table[p] : slice_tables[(long long)(sl - 1) * slice_stride + p];
                 if (w & kOpenBit) {

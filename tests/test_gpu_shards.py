@@ -407,3 +407,26 @@ def test_tokens_multi_bad_arguments():
     rc = L.sqz_gpu_tokens_multi(arr, 1, d.ctypes.data_as(_lib.u8p), d.size, 1 << 15, 3, 257, 32767,
                                 out.ctypes.data, 1, C.byref(n), None)
     assert rc == errno.E2BIG and n.value == 2                # a literal and one (99, 1) match
+
+
+@pytest.mark.parametrize("mib,offset", [(7.3, 0), (9, 1 << 20), (11.5, 3276897)])
+def test_shards_of_a_few_waves(mib, offset, oracle):
+    """Between one and a few waves of tiles the last, partial wave is cut into distance slices as well
+    (sqz_gpu.cu: launch_tiles): full table == oracle B, with and without a look-back halo."""
+    from sqz_b200 import device
+    n = int(mib * (1 << 20))
+    d = corpus.synthetic(n, offset)
+    oln, ods = oracle.match_table(d, 1 << 15, fast=True)
+    ln, ds = sq.match_table(d)
+    bad = np.nonzero((ln != oln) | (ds != ods))[0]
+    assert bad.size == 0, (mib, bad[:5], ln[bad[:5]], oln[bad[:5]], ds[bad[:5]], ods[bad[:5]])
+    # the same bytes as a shard in the middle of a larger buffer (halos on both sides, no edge tiles)
+    first, cnt = 40000, n - 50000
+    buf = torch.cat([torch.from_numpy(d).cuda(), torch.zeros(64, dtype=torch.uint8, device="cuda")])
+    t = device.match_table(buf, first, cnt, 32767, 257)
+    sl, sd = unpack(t)
+    bad = np.nonzero((sl != oln[first:first + cnt]) | (sd != ods[first:first + cnt]))[0]
+    assert bad.size == 0, (mib, bad[:5])
+    tk = sq.tokens(d)
+    ot, end = oracle.tokens_from_table(d, oln, ods)
+    assert end == n and tk.size == ot.size and (tk == ot).all()
