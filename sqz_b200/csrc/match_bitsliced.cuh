@@ -453,6 +453,8 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
     uint32_t fresh[kQ];
 #pragma unroll
     for (int q = 0; q < kQ; q++) { fresh[q] = 0; }
+    bool gate_on = true;                    // need masks in use (decided per warp and group, see the end of the loop)
+    uint32_t entered = 0;                   // iterations of the current group in which this thread met a candidate
     // debugging aid (tools/tile_cycles.py, -DSQZ_DEBUG_COUNTERS builds only): what the scalar path sees
 #ifdef SQZ_DEBUG_COUNTERS
     unsigned int c_surv = 0, c_better = 0, c_tie_fresh = 0, c_reject = 0, c_hand = 0, c_iter_slow = 0;
@@ -510,29 +512,56 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
             for (int t = 0; t < kQ; t++) { en[t] = __shfl_down_sync(0xFFFFFFFFu, e[0][t], 1); }
             uint32_t ib[kQ][kQ];
             uint32_t none = 0xFFFFFFFFu;
+            if (gate_on) {                                    // (the same for the whole warp)
 #pragma unroll
-            for (int q = 0; q < kQ; q++) {
-                uint32_t all_t = 0xFFFFFFFFu;
+                for (int q = 0; q < kQ; q++) {
+                    uint32_t all_t = 0xFFFFFFFFu;
 #pragma unroll
-                for (int t = 0; t < kQ; t++) {
-                    // a candidate fails at position p if any of the first need(p) bytes differs
-                    const uint32_t lo = e[q][t], hi = q + 1 < kQ ? e[q + 1][t] : en[t];
-                    uint32_t acc = lo | fsr(lo, hi, 1);
-                    if (kMinLen >= 3) { acc |= fsr(lo, hi, 2); }
+                    for (int t = 0; t < kQ; t++) {
+                        // a candidate fails at position p if any of the first need(p) bytes differs
+                        const uint32_t lo = e[q][t], hi = q + 1 < kQ ? e[q + 1][t] : en[t];
+                        uint32_t acc = lo | fsr(lo, hi, 1);
+                        if (kMinLen >= 3) { acc |= fsr(lo, hi, 2); }
 #pragma unroll
-                    for (int k = 0; k < kGated; k++) { acc |= fsr(lo, hi, kMinLen + k) & G[k][q]; }
-                    ib[q][t] = acc;
-                    all_t &= acc;
+                        for (int k = 0; k < kGated; k++) { acc |= fsr(lo, hi, kMinLen + k) & G[k][q]; }
+                        ib[q][t] = acc;
+                        all_t &= acc;
+                    }
+                    none &= all_t | closed_m[q];              // closed positions never count
                 }
-                none &= all_t | closed_m[q];                  // closed positions never count
+            } else {
+                // quiet data (an image): hardly any candidate matches even min_len bytes, so the need
+                // masks filter nothing; test min_len bytes only and let the scalar path judge the rest
+#pragma unroll
+                for (int q = 0; q < kQ; q++) {
+                    uint32_t all_t = 0xFFFFFFFFu;
+#pragma unroll
+                    for (int t = 0; t < kQ; t++) {
+                        const uint32_t lo = e[q][t], hi = q + 1 < kQ ? e[q + 1][t] : en[t];
+                        uint32_t acc = lo | fsr(lo, hi, 1);
+                        if (kMinLen >= 3) { acc |= fsr(lo, hi, 2); }
+                        ib[q][t] = acc;
+                        all_t &= acc;
+                    }
+                    none &= all_t | closed_m[q];
+                }
             }
             if (none != 0xFFFFFFFFu) {
                 // ---- scalar path: exact decision for the few surviving positions ----
+                entered++;
                 SQZ_COUNT(c_iter_slow);
 #pragma unroll
                 for (int t = 0; t < kQ; t++) {
                     const uint32_t d = (uint32_t)(32 * (m0 + t) - sh);
                     if (d > reach) { continue; }
+#ifdef SQZ_TSKIP
+                    if (kQ > 1) {                             // one test for the four blocks of this distance
+                        uint32_t live = 0;
+#pragma unroll
+                        for (int q = 0; q < kQ; q++) { live |= ~ib[q][t] & ~closed_m[q]; }
+                        if (live == 0) { continue; }
+                    }
+#endif
 #pragma unroll
                     for (int q = 0; q < kQ; q++) {
                         uint32_t todo = ~ib[q][t] & ~closed_m[q];       // closed since the masks were formed?
@@ -569,9 +598,11 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                                 for (int g = 0; g < kGated; g++) {
                                     if (run > (uint32_t)(kMinLen + g)) { G[g][q] |= bit; }
                                 }
-                            } else if ((SQZ_COUNT(c_reject), (d & kTieMask) == 0)) {
-                                // a candidate that only ties or falls short: count a sample of them; a
-                                // position that keeps attracting them is cheaper to finish in phase 2
+                            } else if ((SQZ_COUNT(c_reject), (d & kTieMask) == 0) &&
+                                       run >= min(have + ((fresh[q] & bit) ? 0u : 1u), (uint32_t)(kMinLen + kGated))) {
+                                // a candidate that only ties or falls short (and that the need masks would
+                                // have let through as well): count a sample of them; a position that keeps
+                                // attracting them is cheaper to finish in phase 2
                                 if (state >= (tie_limit << 5)) {
                                     best_len[k] = kHandOver;
                                     hand_over(slot, (fresh[q] & bit) != 0, resume_tag, slice_tag);
@@ -592,6 +623,18 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
             for (int g = kGated - 1; g > 0; g--) { G[g][q] |= G[g - 1][q] & fresh[q]; }
             G[0][q] |= fresh[q];
             fresh[q] = 0;
+        }
+        // The need masks are a filter, not part of the decision: the warp drops them while hardly any of
+        // its threads meets a candidate (one thread or none in the last 128 distances) and takes them
+        // up again when three or more did.
+        {
+            const int busy = __popc(__ballot_sync(0xFFFFFFFFu, entered != 0));
+#ifndef SQZ_GATE_ALWAYS
+            gate_on = busy >= 3 ? true : (busy <= 1 ? false : gate_on);
+#else
+            (void)busy;
+#endif
+            entered = 0;
         }
     }
     // Work list of phase 2: one bit per position handed over, one word per block of 32 positions.
@@ -700,7 +743,10 @@ inline FinishShape finish_shape(long long n, uint32_t max_len, uint32_t max_dist
     f.chunk = (int)chunk;
     // large shards: 512-position pieces (a boundary can cost a search inheritance would have saved);
     // small shards: 32-position pieces, the dense spots of an ELF table then spread over all warps
-    f.sub = f.chunk >= 2048 ? 512 : 32;
+#ifndef SQZ_FINISH_SUB
+#define SQZ_FINISH_SUB 512
+#endif
+    f.sub = f.chunk >= 2048 ? SQZ_FINISH_SUB : 32;
     f.chunk = f.chunk / f.sub * f.sub;                 // whole pieces
     f.smem_bytes = (int)(((long long)max_dist + chunk + max_len + 8 + 16 + 15) & ~15LL) + 16;
     return f;
