@@ -454,6 +454,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
 #pragma unroll
     for (int q = 0; q < kQ; q++) { fresh[q] = 0; }
     bool gate_on = true;                    // need masks in use (decided per warp and group, see the end of the loop)
+    int quiet_groups = 0;                   // consecutive groups without a candidate anywhere in the warp
     uint32_t entered = 0;                   // iterations of the current group in which this thread met a candidate
     // debugging aid (tools/tile_cycles.py, -DSQZ_DEBUG_COUNTERS builds only): what the scalar path sees
 #ifdef SQZ_DEBUG_COUNTERS
@@ -624,13 +625,15 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
             G[0][q] |= fresh[q];
             fresh[q] = 0;
         }
-        // The need masks are a filter, not part of the decision: the warp drops them while hardly any of
-        // its threads meets a candidate (one thread or none in the last 128 distances) and takes them
-        // up again when three or more did.
+        // The need masks are a filter, not part of the decision: the warp drops them after four groups
+        // (512 distances) in which none of its threads met a candidate, and takes them up again as soon as
+        // two threads do in one group.  The asymmetry is deliberate: without the masks, text makes every
+        // thread meet candidates in every iteration, so a wrong guess must not last.
         {
             const int busy = __popc(__ballot_sync(0xFFFFFFFFu, entered != 0));
 #ifndef SQZ_GATE_ALWAYS
-            gate_on = busy >= 3 ? true : (busy <= 1 ? false : gate_on);
+            if (busy >= 2) { quiet_groups = 0; } else if (busy == 0 && quiet_groups < 4) { quiet_groups++; }
+            gate_on = quiet_groups < 4;
 #else
             (void)busy;
 #endif

@@ -545,7 +545,7 @@ constexpr int kMaxDevices = 64;
 struct DeviceState {
     std::once_flag once;
     cudaError_t err = cudaSuccess;
-    cudaStream_t side = nullptr, side2 = nullptr, side3 = nullptr;
+    cudaStream_t side = nullptr, side2 = nullptr;
     int sms = 0;
 };
 static DeviceState g_dev[kMaxDevices];
@@ -586,11 +586,6 @@ static int device_state(DeviceState** out) {
         if (e == cudaSuccess) { e = cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev); }
         if (e == cudaSuccess) { e = cudaStreamCreateWithFlags(&d.side, cudaStreamNonBlocking); }
         if (e == cudaSuccess) { e = cudaStreamCreateWithFlags(&d.side2, cudaStreamNonBlocking); }
-        if (e == cudaSuccess) {
-            int least = 0, greatest = 0;
-            e = cudaDeviceGetStreamPriorityRange(&least, &greatest);
-            if (e == cudaSuccess) { e = cudaStreamCreateWithPriority(&d.side3, cudaStreamNonBlocking, greatest); }
-        }
         d.err = e;
     });
     if (d.err != cudaSuccess) { return fail(cuda_code(d.err), "per-device set-up", d.err); }
@@ -628,7 +623,6 @@ struct SlicePlan { int q; int slices; int slice_words; size_t stride; };
 // distance range is split into as many slices as it takes to give the device about two waves of
 // CTAs (a power of two, at most 32).  Fixed numbers, so that the workspace size depends on n only.
 constexpr size_t kWaveQ4 = 148 * 3, kWaveQ1 = 148 * 5;
-constexpr long long kTailTilesMax = 360;        // tiles of a sliced last wave (at most 0.8 waves), see launch_tiles
 
 static SlicePlan slice_plan(size_t n, uint32_t max_dist) {
     SlicePlan sp{4, 1, 0, 0};
@@ -671,9 +665,6 @@ extern "C" size_t sqz_gpu_match_workspace(size_t n) {
     const size_t tiles = std::min<size_t>((n + tp - 1) / tp, 2 * kWaveQ1 + 1);
     for (size_t t = 1; t <= tiles; t++) {
         tables = std::max(tables, slice_bytes(slice_plan(std::min(n, t * tp), sqz_gpu_max_dist_limit)));
-    }
-    if (n > kWaveQ4 * (size_t)v2::tile_pos(4)) {                       // the sliced last wave of a larger shard: three tables
-        tables = std::max(tables, (size_t)3 * (((size_t)kTailTilesMax * v2::tile_pos(4) + 63) / 64 * 64) * 4);
     }
 #ifdef SQZ_TUNING
     tables = std::max(tables, (size_t)31 * ((std::min<size_t>(n, (size_t)64 << 20) + 63) / 64 * 64) * 4);   // whatever SQZ_SLICES asks for
@@ -808,22 +799,6 @@ static int launch_tiles(const SlicePlan& sp, const uint8_t* d_shard, size_t back
         g_launches.fetch_add(1, std::memory_order_relaxed);
         return cudaGetLastError();
     };
-    // A shard of a few waves of tiles ends with a partial wave that takes as long as a full one.
-    // Those last tiles are cut into distance slices as well (four, seeded like a small shard's), on a
-    // side stream of higher priority, so that their short CTAs fill in beside the whole tiles.
-    long long tail_tiles = 0;
-    const int tail_slices = 4;
-    const int tail_words = (((int)((max_dist + 31) / 32) + tail_slices - 1) / tail_slices + 31) / 32 * 32;
-    if (kQ == 4 && sp.slices <= 1 && max_dist > 4096) {
-        const long long wave = (long long)dv->sms * 3, interior = t_hi - t_lo;
-        const long long rest = interior % wave;
-        if (interior > wave && rest > 0 && rest * 10 <= wave * 8 && rest <= kTailTilesMax) { tail_tiles = rest; }
-    }
-    const long long tail_first = t_hi - tail_tiles;
-    const long long tail_stride = (tail_tiles * tp + 63) / 64 * 64;
-    // the tail's slice tables are indexed by shard position like every table: shift the base
-    uint32_t* d_tail = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(d_work) + kCursorBytes + mask_bytes(n)) - tail_first * tp;
-    ScopedEvent join3;
     cudaError_t le = cudaSuccess;
     if (lead) {
         CU(cudaStreamWaitEvent(dv->side, fork.e, 0));
@@ -839,28 +814,12 @@ static int launch_tiles(const SlicePlan& sp, const uint8_t* d_shard, size_t back
         CU(join2.create());
         CU(cudaEventRecord(join2.e, dv->side2));
     }
-    if (tail_tiles > 0) {
-        if (fork.e == nullptr) {
-            CU(fork.create());
-            CU(cudaEventRecord(fork.e, s));
-        }
-        CU(cudaStreamWaitEvent(dv->side3, fork.e, 0));
-        le = launch(v2::match_table<kMinLen, false, kQ>, tail_first, tail_tiles, false, dv->side3, tail_slices, tail_words, tail_stride, d_tail);
-        if (le != cudaSuccess) { return fail(cuda_code(le), "match_table_v2_tail", le); }
-        const long long tail_lo = tail_first * tp, tail_hi = std::min((long long)n, t_hi * tp);
-        const unsigned grid = (unsigned)std::min<long long>((tail_hi - tail_lo + 255) / 256, (long long)dv->sms * 8);
-        v2::combine_slices<<<grid, 256, 0, dv->side3>>>(d_table, d_tail, tail_lo, tail_hi, tail_stride, tail_slices, d_open);
-        LAUNCHED("combine_slices");
-        CU(join3.create());
-        CU(cudaEventRecord(join3.e, dv->side3));
-    }
-    if (tail_first > t_lo) {
-        le = launch(v2::match_table<kMinLen, false, kQ>, t_lo, tail_first - t_lo, false, s, sp.slices, sp.slice_words, (long long)sp.stride, d_slices);
+    if (t_hi > t_lo) {
+        le = launch(v2::match_table<kMinLen, false, kQ>, t_lo, t_hi - t_lo, false, s, sp.slices, sp.slice_words, (long long)sp.stride, d_slices);
         if (le != cudaSuccess) { return fail(cuda_code(le), "match_table_v2", le); }
     }
     if (join1.e != nullptr) { CU(cudaStreamWaitEvent(s, join1.e, 0)); }
     if (join2.e != nullptr) { CU(cudaStreamWaitEvent(s, join2.e, 0)); }
-    if (join3.e != nullptr) { CU(cudaStreamWaitEvent(s, join3.e, 0)); }
     if (sp.slices > 1) {
         const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)dv->sms * 8);
         v2::combine_slices<<<grid, 256, 0, s>>>(d_table, d_slices, 0LL, (long long)n, (long long)sp.stride, sp.slices, d_open);
