@@ -309,6 +309,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
     constexpr int kWarpOwned = warp_owned(kQ), kTileBlocks = tile_blocks(kQ), kTilePos = tile_pos(kQ);
     constexpr int kStageBlocks = stage_blocks(kQ);
     constexpr int kGated = gated(kQ);
+    constexpr int kQuietGroups = 16 / kQ;          // groups of 32 kQ distances without a candidate before the need masks are dropped
     const Geometry geo = geometry(max_len, max_dist, kEdge, init_table != nullptr, kQ);
     const uint4* PL = reinterpret_cast<const uint4*>(smem_raw);           // [plane_blocks][2]
     uint8_t* best_len = smem_raw + geo.region_bytes;                      // [kTilePos + 32]
@@ -455,6 +456,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
     for (int q = 0; q < kQ; q++) { fresh[q] = 0; }
     bool gate_on = true;                    // need masks in use (decided per warp and group, see the end of the loop)
     int quiet_groups = 0;                   // consecutive groups without a candidate anywhere in the warp
+    int quiet_hits = 0;                     // iterations of the current group, masks off, in which some thread met one
     uint32_t entered = 0;                   // iterations of the current group in which this thread met a candidate
     // debugging aid (tools/tile_cycles.py, -DSQZ_DEBUG_COUNTERS builds only): what the scalar path sees
 #ifdef SQZ_DEBUG_COUNTERS
@@ -546,6 +548,9 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                     }
                     none &= all_t | closed_m[q];
                 }
+                // a wrong guess must not last: the third iteration of a group in which some thread meets a
+                // candidate brings the masks back at once
+                if (__any_sync(0xFFFFFFFFu, none != 0xFFFFFFFFu) && ++quiet_hits >= 3) { gate_on = true; quiet_groups = 0; }
             }
             if (none != 0xFFFFFFFFu) {
                 // ---- scalar path: exact decision for the few surviving positions ----
@@ -555,14 +560,12 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                 for (int t = 0; t < kQ; t++) {
                     const uint32_t d = (uint32_t)(32 * (m0 + t) - sh);
                     if (d > reach) { continue; }
-#ifdef SQZ_TSKIP
                     if (kQ > 1) {                             // one test for the four blocks of this distance
                         uint32_t live = 0;
 #pragma unroll
                         for (int q = 0; q < kQ; q++) { live |= ~ib[q][t] & ~closed_m[q]; }
                         if (live == 0) { continue; }
                     }
-#endif
 #pragma unroll
                     for (int q = 0; q < kQ; q++) {
                         uint32_t todo = ~ib[q][t] & ~closed_m[q];       // closed since the masks were formed?
@@ -599,11 +602,10 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                                 for (int g = 0; g < kGated; g++) {
                                     if (run > (uint32_t)(kMinLen + g)) { G[g][q] |= bit; }
                                 }
-                            } else if ((SQZ_COUNT(c_reject), (d & kTieMask) == 0) &&
-                                       run >= min(have + ((fresh[q] & bit) ? 0u : 1u), (uint32_t)(kMinLen + kGated))) {
-                                // a candidate that only ties or falls short (and that the need masks would
-                                // have let through as well): count a sample of them; a position that keeps
-                                // attracting them is cheaper to finish in phase 2
+                            } else if ((SQZ_COUNT(c_reject), (d & kTieMask) == 0) && gate_on) {
+                                // a candidate that only ties or falls short although the need masks let it
+                                // through: count a sample of them; a position that keeps attracting them is
+                                // cheaper to finish in phase 2  (without the masks everything gets here: not counted)
                                 if (state >= (tie_limit << 5)) {
                                     best_len[k] = kHandOver;
                                     hand_over(slot, (fresh[q] & bit) != 0, resume_tag, slice_tag);
@@ -625,15 +627,16 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
             G[0][q] |= fresh[q];
             fresh[q] = 0;
         }
-        // The need masks are a filter, not part of the decision: the warp drops them after four groups
-        // (512 distances) in which none of its threads met a candidate, and takes them up again as soon as
+        // The need masks are a filter, not part of the decision: the warp drops them after 512 distances
+        // (four groups of the throughput shape) in which none of its threads met a candidate, and takes them up again as soon as
         // two threads do in one group.  The asymmetry is deliberate: without the masks, text makes every
         // thread meet candidates in every iteration, so a wrong guess must not last.
         {
             const int busy = __popc(__ballot_sync(0xFFFFFFFFu, entered != 0));
 #ifndef SQZ_GATE_ALWAYS
-            if (busy >= 2) { quiet_groups = 0; } else if (busy == 0 && quiet_groups < 4) { quiet_groups++; }
-            gate_on = quiet_groups < 4;
+            if (busy >= 2) { quiet_groups = 0; } else if (busy == 0 && quiet_groups < kQuietGroups) { quiet_groups++; }
+            gate_on = quiet_groups < kQuietGroups;
+            quiet_hits = 0;
 #else
             (void)busy;
 #endif
