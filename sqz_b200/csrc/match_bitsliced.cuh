@@ -309,7 +309,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
     constexpr int kWarpOwned = warp_owned(kQ), kTileBlocks = tile_blocks(kQ), kTilePos = tile_pos(kQ);
     constexpr int kStageBlocks = stage_blocks(kQ);
     constexpr int kGated = gated(kQ);
-    constexpr int kQuietGroups = 16 / kQ;          // groups of 32 kQ distances without a candidate before the need masks are dropped
+    constexpr int kQuietGroups = 4;                // groups (of 128 distances) without a candidate before the need masks are dropped
     const Geometry geo = geometry(max_len, max_dist, kEdge, init_table != nullptr, kQ);
     const uint4* PL = reinterpret_cast<const uint4*>(smem_raw);           // [plane_blocks][2]
     uint8_t* best_len = smem_raw + geo.region_bytes;                      // [kTilePos + 32]
@@ -455,8 +455,10 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
 #pragma unroll
     for (int q = 0; q < kQ; q++) { fresh[q] = 0; }
     bool gate_on = true;                    // need masks in use (decided per warp and group, see the end of the loop)
-    int quiet_groups = 0;                   // consecutive groups without a candidate anywhere in the warp
-    int quiet_hits = 0;                     // iterations of the current group, masks off, in which some thread met one
+    // one word of warp-wide bookkeeping for that decision: bits 0-1 iterations of the current group, masks off,
+    // in which some thread met a candidate; bits 2-8 consecutive groups without one; bits 9-15 how many of those
+    // it takes to drop the masks (doubles after a wrong guess)
+    uint32_t quiet = (uint32_t)kQuietGroups << 9;
     uint32_t entered = 0;                   // iterations of the current group in which this thread met a candidate
     // debugging aid (tools/tile_cycles.py, -DSQZ_DEBUG_COUNTERS builds only): what the scalar path sees
 #ifdef SQZ_DEBUG_COUNTERS
@@ -550,7 +552,10 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                 }
                 // a wrong guess must not last: the third iteration of a group in which some thread meets a
                 // candidate brings the masks back at once
-                if (__any_sync(0xFFFFFFFFu, none != 0xFFFFFFFFu) && ++quiet_hits >= 3) { gate_on = true; quiet_groups = 0; }
+                if (__any_sync(0xFFFFFFFFu, none != 0xFFFFFFFFu) && (++quiet & 3u) == 3u) {
+                    gate_on = true;
+                    quiet = min(2u * (quiet >> 9), 64u) << 9; // no quiet groups, and the next attempt waits twice as long
+                }
             }
             if (none != 0xFFFFFFFFu) {
                 // ---- scalar path: exact decision for the few surviving positions ----
@@ -627,16 +632,20 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
             G[0][q] |= fresh[q];
             fresh[q] = 0;
         }
-        // The need masks are a filter, not part of the decision: the warp drops them after 512 distances
-        // (four groups of the throughput shape) in which none of its threads met a candidate, and takes them up again as soon as
+        // The need masks are a filter, not part of the decision: the warp drops them after four groups
+        // (512 distances) in which none of its threads met a candidate, and takes them up again as soon as
         // two threads do in one group.  The asymmetry is deliberate: without the masks, text makes every
         // thread meet candidates in every iteration, so a wrong guess must not last.
         {
             const int busy = __popc(__ballot_sync(0xFFFFFFFFu, entered != 0));
 #ifndef SQZ_GATE_ALWAYS
-            if (busy >= 2) { quiet_groups = 0; } else if (busy == 0 && quiet_groups < kQuietGroups) { quiet_groups++; }
-            gate_on = quiet_groups < kQuietGroups;
-            quiet_hits = 0;
+            if (kQ > 1) {       // (the latency shape keeps the masks: its loop is short, dropping them measured slower)
+                const uint32_t need = quiet >> 9;
+                uint32_t groups = (quiet >> 2) & 127u;
+                if (busy >= 2) { groups = 0; } else if (busy == 0 && groups < need) { groups++; }
+                gate_on = groups < need;
+                quiet = (need << 9) | (groups << 2);
+            }
 #else
             (void)busy;
 #endif
