@@ -82,6 +82,9 @@ __host__ __device__ constexpr int stage_blocks(int q) { return tile_blocks(q) - 
 // need is tracked exactly up to min_len + gated(q): three levels measure best for the throughput
 // shape (each level costs 4-5 % of its loop)
 __host__ __device__ constexpr int gated(int q) { return q == 1 ? SQZ_GATED_Q1 : SQZ_GATED; }
+#ifndef SQZ_T0_STRICT
+#define SQZ_T0_STRICT 1   // a best found at the nearest of an iteration's distances (t = 0) is strict at once
+#endif
 #ifndef SQZ_TIE_MASK
 #define SQZ_TIE_MASK 0
 #endif
@@ -457,7 +460,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
     bool gate_on = true;                    // need masks in use (decided per warp and group, see the end of the loop)
     // one word of warp-wide bookkeeping for that decision: bits 0-1 iterations of the current group, masks off,
     // in which some thread met a candidate; bits 2-8 consecutive groups without one; bits 9-15 how many of those
-    // it takes to drop the masks (doubles after a wrong guess)
+    // it takes to drop the masks
     uint32_t quiet = (uint32_t)kQuietGroups << 9;
     uint32_t entered = 0;                   // iterations of the current group in which this thread met a candidate
     // debugging aid (tools/tile_cycles.py, -DSQZ_DEBUG_COUNTERS builds only): what the scalar path sees
@@ -554,26 +557,43 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                 // candidate brings the masks back at once
                 if (__any_sync(0xFFFFFFFFu, none != 0xFFFFFFFFu) && (++quiet & 3u) == 3u) {
                     gate_on = true;
-                    quiet = min(2u * (quiet >> 9), 64u) << 9; // no quiet groups, and the next attempt waits twice as long
+                    quiet = (uint32_t)kQuietGroups << 9;      // no quiet groups
                 }
             }
             if (none != 0xFFFFFFFFu) {
                 // ---- scalar path: exact decision for the few surviving positions ----
+                // The match words e[][] are not kept for this path (16 registers the loop has no room for):
+                // a (block, distance) pair with a survivor rebuilds its two words from the plane words,
+                // 16 instructions each.
                 entered++;
                 SQZ_COUNT(c_iter_slow);
+                const int shx = sh;
 #pragma unroll
-                for (int t = 0; t < kQ; t++) {
-                    const uint32_t d = (uint32_t)(32 * (m0 + t) - sh);
-                    if (d > reach) { continue; }
-                    if (kQ > 1) {                             // one test for the four blocks of this distance
-                        uint32_t live = 0;
-#pragma unroll
-                        for (int q = 0; q < kQ; q++) { live |= ~ib[q][t] & ~closed_m[q]; }
-                        if (live == 0) { continue; }
+                for (int q = 0; q < kQ; q++) {
+                    if (kQ > 1) {                             // one test for the four distances of this block
+                        if ((~(ib[q][0] & ib[q][1] & ib[q][kQ > 2 ? 2 : 0] & ib[q][kQ > 3 ? 3 : 0]) & ~closed_m[q]) == 0) { continue; }
                     }
 #pragma unroll
-                    for (int q = 0; q < kQ; q++) {
+                    for (int t = 0; t < kQ; t++) {            // ascending distance for every position
                         uint32_t todo = ~ib[q][t] & ~closed_m[q];       // closed since the masks were formed?
+                        if (todo == 0) { continue; }
+                        const uint32_t d = (uint32_t)(32 * (m0 + t) - sh);
+                        if (d > reach) { continue; }
+                        uint32_t lo = 0, hi = 0;
+#pragma unroll
+                        for (int b = 0; b < 8; b++) {
+                            lo |= fsr(cr[q - t + kQ - 1][b], cr[q - t + kQ][b], shx) ^ qv[q][b];
+                        }
+                        if (kEdge) { lo |= ~vq[q] | ~fsr(vr[q - t + kQ - 1], vr[q - t + kQ], shx); }
+                        if (q + 1 < kQ) {
+#pragma unroll
+                            for (int b = 0; b < 8; b++) {
+                                hi |= fsr(cr[q + 1 - t + kQ - 1][b], cr[q + 1 - t + kQ][b], shx) ^ qv[q + 1][b];
+                            }
+                            if (kEdge) { hi |= ~vq[q + 1] | ~fsr(vr[q + 1 - t + kQ - 1], vr[q + 1 - t + kQ], shx); }
+                        } else {
+                            hi = en[t];
+                        }
                         while (todo != 0) {
                             const int p = __ffs((int)todo) - 1;
                             todo &= todo - 1;
@@ -583,7 +603,6 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                             SQZ_CHECK(k >= 0 && k < kTilePos && tile_pos0 + k < n, "phase 1: survivor outside the tile or the shard");
                             const uint32_t state = best_len[k];         // low 5 bits: best, high 3: near-ties seen
                             const uint32_t have = state & 31u;
-                            const uint32_t lo = e[q][t], hi = q + 1 < kQ ? e[q + 1][t] : en[t];
                             const uint32_t win = fsr(lo, hi, p);        // differing bytes from position p on
                             uint32_t* slot = table + tile_pos0 + k;
                             if (win == 0) {
@@ -602,10 +621,14 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                                 SQZ_COUNT(c_better);
                                 best_len[k] = (uint8_t)run;
                                 *slot = (run << 16) | d;
-                                fresh[q] |= bit;
+                                // the first of an iteration's distances (t = 0) has nothing nearer left in the group
+                                // -- a later candidate is nearer only if its t is smaller -- so its best is
+                                // strict at once; the others stay fresh until the group ends
+                                const bool strict_now = SQZ_T0_STRICT && t == 0;
+                                if (strict_now) { fresh[q] &= ~bit; } else { fresh[q] |= bit; }
 #pragma unroll
                                 for (int g = 0; g < kGated; g++) {
-                                    if (run > (uint32_t)(kMinLen + g)) { G[g][q] |= bit; }
+                                    if (run + (strict_now ? 1u : 0u) > (uint32_t)(kMinLen + g)) { G[g][q] |= bit; }
                                 }
                             } else if ((SQZ_COUNT(c_reject), (d & kTieMask) == 0) && gate_on) {
                                 // a candidate that only ties or falls short although the need masks let it
