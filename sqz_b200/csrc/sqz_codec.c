@@ -163,7 +163,8 @@ static inline uint64_t get_bits(struct sqz_bitstream* bs, int count) {
  * ======================================================================== */
 
 enum { none = -1, no_node = 0xFFFF,
-       lit_lut_bits = 10, pos_lut_bits = 6 };   /* sizes of sqz.h's lit_lut / pos_lut */
+       lit_lut_bits = 10, pos_lut_bits = 6,     /* sizes of sqz.h's lit_lut / pos_lut */
+       lut_node_bits = 10 };                    /* a table entry: node (< 1023) | bits to consume << 10 */
 
 static void note_change(struct sqz_tree* t, int32_t leaf);
 
@@ -222,7 +223,8 @@ static void relabel(struct sqz_tree* t, int32_t top) {
         if (t->lut != NULL && bits > 0 && bits <= t->lut_bits && (i < t->n || bits == t->lut_bits)) {
             const int32_t spread = t->lut_bits - bits;
             const uint64_t first = (reverse64(path) >> (64 - bits)) << spread;
-            for (uint64_t k = 0; k < ((uint64_t)1 << spread); k++) { t->lut[first + k] = (uint16_t)i; }
+            const uint16_t entry = (uint16_t)(i | (bits << lut_node_bits));   /* the node and the bits its code takes */
+            for (uint64_t k = 0; k < ((uint64_t)1 << spread); k++) { t->lut[first + k] = entry; }
         }
     }
     t->depth = depth;
@@ -420,7 +422,7 @@ static void selfcheck(struct sqz_tree* t) {
     for (uint32_t look = 0; t->lut != NULL && look < (1u << t->lut_bits); look++) {
         int32_t i = root;
         for (int b = t->lut_bits - 1; b >= 0 && i >= t->n; b--) { i = (look >> b) & 1 ? t->hi[i] : t->lo[i]; }
-        if (t->lut[look] != (i >= 0 ? (uint16_t)i : (uint16_t)no_node)) {
+        if (t->lut[look] != (i >= 0 ? (uint16_t)(i | (t->bits[i] << lut_node_bits)) : (uint16_t)no_node)) {
             fprintf(stderr, "sqz selfcheck: stale decode table entry %u\n", look);
             abort();
         }
@@ -1222,15 +1224,25 @@ struct window {
     uint64_t acc, pend;
     int32_t have, pend_bits;
     int32_t dry;                        /* errno met while reading ahead */
+    int32_t bad;                        /* errno of the stream: bits consumed that are not there, a code that leads nowhere */
 };
 
 static inline void window_fill(struct window* w) {
     if (w->have >= 32) { return; }
     if (w->pend_bits == 0 && w->dry == 0) {
-        word_in(w->bs);
-        if (w->bs->error != 0) { w->dry = w->bs->error; w->bs->error = 0; }
-        else { w->pend = w->bs->b64; w->pend_bits = 64; }
-        w->bs->bits = 0;
+        struct sqz_bitstream* const bs = w->bs;
+        if (bs->data != NULL && bs->bytes >= 8 && bs->read <= bs->bytes - 8) {    /* memory source: one big-endian load */
+            uint64_t be;
+            memcpy(&be, bs->data + bs->read, 8);
+            bs->read += 8;
+            w->pend = __builtin_bswap64(be);
+            w->pend_bits = 64;
+        } else {
+            word_in(bs);
+            if (bs->error != 0) { w->dry = bs->error; bs->error = 0; }
+            else { w->pend = bs->b64; w->pend_bits = 64; }
+        }
+        bs->bits = 0;
     }
     if (w->pend_bits > 0) {
         const int32_t room = 64 - w->have;
@@ -1242,34 +1254,36 @@ static inline void window_fill(struct window* w) {
     }
 }
 
-/* drop `count` bits; 0 when they were not all there */
-static inline int window_skip(struct sqz* s, struct window* w, int32_t count) {
-    if (count > w->have) { s->error = w->dry != 0 ? w->dry : E2BIG; return 0; }
+/* drop `count` bits; 0 when they were not all there.  The window keeps the error to itself (`bad`):
+ * the decode loop looks at it once per token instead of reading s->error back after every field. */
+static inline int window_skip(struct window* w, int32_t count) {
+    if (count > w->have) { w->bad = w->dry != 0 ? w->dry : E2BIG; return 0; }
     w->acc <<= count;
     w->have -= count;
     return 1;
 }
 
 /* `count` <= 16 raw bits, first bit = least significant (bitstream.h:97-110) */
-static inline uint32_t window_bits(struct sqz* s, struct window* w, int32_t count) {
+static inline uint32_t window_bits(struct window* w, int32_t count) {
     window_fill(w);
     const uint32_t top = (uint32_t)(w->acc >> 48);          /* the next 16 bits */
     const uint32_t v = reverse_field(top, 16) & ((1u << count) - 1);
-    return window_skip(s, w, count) ? v : 0;
+    return window_skip(w, count) ? v : 0;
 }
 
-static inline int32_t window_symbol(struct sqz* s, struct window* w, struct sqz_tree* t,
+static inline int32_t window_symbol(struct window* w, struct sqz_tree* t,
                                     const int lut_bits, const int usual) {  /* squeeze.h:429-442 */
     window_fill(w);
-    int32_t i = t->lut[w->acc >> (64 - lut_bits)];   /* one lookup walks lut_bits levels */
-    if (i == no_node) { s->error = EINVAL; return -1; }
-    if (!window_skip(s, w, i < t->n ? t->bits[i] : lut_bits)) { return -1; }
+    const uint32_t entry = t->lut[w->acc >> (64 - lut_bits)];   /* one lookup walks lut_bits levels */
+    if (entry == no_node) { w->bad = EINVAL; return -1; }
+    int32_t i = (int32_t)(entry & ((1u << lut_node_bits) - 1));
+    if (!window_skip(w, (int32_t)(entry >> lut_node_bits))) { return -1; }
     while (i >= t->n) {                              /* a longer code: leaves are the nodes below n */
         window_fill(w);
         const int bit = (int)(w->acc >> 63);
-        if (!window_skip(s, w, 1)) { return -1; }
+        if (!window_skip(w, 1)) { return -1; }
         i = bit ? t->hi[i] : t->lo[i];
-        if (i < 0) { s->error = EINVAL; return -1; }
+        if (i < 0) { w->bad = EINVAL; return -1; }
     }
     tree_count_as(t, i, usual);
     SQZ_CHECK(t);
@@ -1286,48 +1300,54 @@ static void decode_stream(struct sqz* s, struct sqz_bitstream* bs, uint8_t* data
     memset(s->pos_lut, 0xFF, sizeof(s->pos_lut));
     coder_begin(s, bs);
     if (bs->error != 0) { s->error = bs->error; }
-    struct window w = { bs, bs->bits > 0 ? bs->b64 : 0, 0, bs->bits, 0, 0 };
+    struct window w = { bs, bs->bits > 0 ? bs->b64 : 0, 0, bs->bits, 0, 0, 0 };
+    struct sqz_tree* const lit = &s->lit;
+    struct sqz_tree* const pos = &s->pos;
     uint64_t i = 0;
-    while (i < bytes && s->error == 0) {
-        int32_t sym = window_symbol(s, &w, &s->lit, lit_lut_bits, lit_plan);
-        if (s->error != 0) { break; }
-        if (sym == sqz_lit_nyt) {
-            sym = (int32_t)window_bits(s, &w, 9);
-            if (s->error != 0) { break; }
-            if (s->lit.up[sym] >= 0) { s->error = EINVAL; break; }  /* already known */
-            if (!tree_insert(&s->lit, sym)) { s->error = E2BIG; break; }
-            SQZ_CHECK(&s->lit);
-        }
-        if (sym <= 0xFF) {
+    int err = s->error;
+    while (i < bytes && err == 0) {
+        int32_t sym = window_symbol(&w, lit, lit_lut_bits, lit_plan);
+        if (sym <= 0xFF && sym >= 0) {                              /* a literal seen before: the common case */
             if (data != NULL) { data[i] = (uint8_t)sym; }
             if (n_tokens < cap) { tokens[n_tokens] = (uint32_t)sym; }
             n_tokens++;
             i++;
             continue;
         }
+        if (w.bad != 0) { err = w.bad; break; }
+        if (sym == sqz_lit_nyt) {
+            sym = (int32_t)window_bits(&w, 9);
+            if (w.bad != 0) { err = w.bad; break; }
+            if (lit->up[sym] >= 0) { err = EINVAL; break; }         /* already known */
+            if (!tree_insert(lit, sym)) { err = E2BIG; break; }
+            SQZ_CHECK(lit);
+            if (sym <= 0xFF) {
+                if (data != NULL) { data[i] = (uint8_t)sym; }
+                if (n_tokens < cap) { tokens[n_tokens] = (uint32_t)sym; }
+                n_tokens++;
+                i++;
+                continue;
+            }
+        }
         const int32_t b = sym - len_symbol0;
-        if (b < 0 || b >= 28) { s->error = EINVAL; break; }
+        if (b < 0 || b >= 28) { err = EINVAL; break; }
         uint32_t len = len_base[b];
-        if (len_extra[b] > 0) { len += window_bits(s, &w, len_extra[b]); }
-        if (s->error != 0) { break; }
-        if (len < sqz_min_len || len > sqz_max_len) { s->error = EINVAL; break; }
-        int32_t pb = window_symbol(s, &w, &s->pos, pos_lut_bits, pos_plan);
-        if (s->error != 0) { break; }
+        if (len_extra[b] > 0) { len += window_bits(&w, len_extra[b]); }
+        if (len < sqz_min_len || len > sqz_max_len) { err = w.bad != 0 ? w.bad : EINVAL; break; }
+        int32_t pb = window_symbol(&w, pos, pos_lut_bits, pos_plan);
+        if (w.bad != 0) { err = w.bad; break; }
         if (pb == sqz_pos_nyt) {
-            pb = (int32_t)window_bits(s, &w, 5);
-            if (s->error != 0) { break; }
-            if (pb >= 30 || s->pos.up[pb] >= 0) { s->error = EINVAL; break; }
-            if (!tree_insert(&s->pos, pb)) { s->error = E2BIG; break; }
-            SQZ_CHECK(&s->pos);
+            pb = (int32_t)window_bits(&w, 5);
+            if (w.bad != 0) { err = w.bad; break; }
+            if (pb >= 30 || pos->up[pb] >= 0) { err = EINVAL; break; }
+            if (!tree_insert(pos, pb)) { err = E2BIG; break; }
+            SQZ_CHECK(pos);
         }
-        if (pb >= 30) { s->error = EINVAL; break; }
+        if (pb >= 30) { err = EINVAL; break; }
         uint32_t dist = pos_base[pb];
-        if (pos_extra[pb] > 0) { dist += window_bits(s, &w, pos_extra[pb]); }
-        if (s->error != 0) { break; }
-        if (dist == 0 || dist > 0x7FFF || dist > i || len > bytes - i) {
-            s->error = EINVAL;
-            break;
-        }
+        if (pos_extra[pb] > 0) { dist += window_bits(&w, pos_extra[pb]); }
+        if (w.bad != 0) { err = w.bad; break; }
+        if (dist == 0 || dist > 0x7FFF || dist > i || len > bytes - i) { err = EINVAL; break; }
         /* squeeze.h:533-539 copies byte by byte because the source may overlap the
          * destination; the result is the same as these three cases */
         if (data != NULL) {
@@ -1341,6 +1361,7 @@ static void decode_stream(struct sqz* s, struct sqz_bitstream* bs, uint8_t* data
         n_tokens++;
         i += len;
     }
+    if (err != 0 && s->error == 0) { s->error = err; }
     if (count != NULL) { *count = n_tokens; }
     if (tokens != NULL && n_tokens > cap && s->error == 0) { s->error = E2BIG; }
     /* Leave the bitstream where the reference's bit-at-a-time reader would stand

@@ -430,3 +430,20 @@ def test_shards_of_a_few_waves(mib, offset, oracle):
     tk = sq.tokens(d)
     ot, end = oracle.tokens_from_table(d, oln, ods)
     assert end == n and tk.size == ot.size and (tk == ot).all()
+
+
+def test_shard_in_pieces_with_overlapped_phase_two(oracle):
+    """A shard of more than 16 waves of tiles is cut into pieces whose tiles alternate between two
+    streams while phase 2 of a finished piece runs beside them (sqz_gpu.cu: launch_v2).  240 MiB =
+    4 pieces, as a shard with halos on both sides and from position 0: full table == oracle B."""
+    from sqz_b200 import device
+    n = 240 << 20
+    d = corpus.synthetic(n, 5 << 20)
+    oln, ods = oracle.match_table(d, 1 << 15, fast=True)
+    buf = torch.cat([torch.from_numpy(d).cuda(), torch.zeros(64, dtype=torch.uint8, device="cuda")])
+    for first, cnt, back, ahead in ((0, n, 0, 0), (40000, n - 50000, 32767, 257)):
+        t = device.match_table(buf, first, cnt, back, ahead)
+        sl, sd = unpack(t)
+        bad = np.nonzero((sl != oln[first:first + cnt]) | (sd != ods[first:first + cnt]))[0]
+        assert bad.size == 0, (first, bad[:5], sl[bad[:5]], oln[first + bad[:5]], sd[bad[:5]], ods[first + bad[:5]])
+        del t, sl, sd
