@@ -82,6 +82,36 @@ __host__ __device__ constexpr int stage_blocks(int q) { return tile_blocks(q) - 
 // need is tracked exactly up to min_len + gated(q): three levels measure best for the throughput
 // shape (each level costs 4-5 % of its loop)
 __host__ __device__ constexpr int gated(int q) { return q == 1 ? SQZ_GATED_Q1 : SQZ_GATED; }
+// Bit planes 0..kQuietPlanes-1 hold a linear hash of each byte -- its low bits XOR a constant chosen by
+// its high bits -- and the remaining planes the high bits as they are: hash and high bits together
+// determine the byte, so a compare over all eight planes is the byte compare it always was.  A compare
+// over the hashed planes alone lets every candidate through that the exact one would, plus those whose
+// bytes differ by one of three patterns: 0.12 candidates per position over the whole window on random
+// bytes, 5-7 on ELF (contexts like 00 00 xx carry eight bits, six after hashing;
+// tools/plane_hash_false_positives.c).  A warp whose data is quiet -- the same warps that drop the need masks,
+// see the adaptive gate -- compares the hashed planes only: 46 of the 246 ALU instructions of its loop
+// body.  The scalar path measures runs on all eight planes, so every decision stays exact.
+#ifndef SQZ_QUIET_PLANES
+#define SQZ_QUIET_PLANES 6
+#endif
+constexpr int kQuietPlanes = SQZ_QUIET_PLANES;
+static_assert(kQuietPlanes >= 6 && kQuietPlanes <= 8, "6, 7 or 8 planes");
+// byte k of the constant = what is XORed into a byte whose high 8-kQuietPlanes bits are k
+constexpr uint32_t kFold = kQuietPlanes == 6 ? (0x2Bu << 8 | 0x16u << 16 | (0x2Bu ^ 0x16u) << 24) : kQuietPlanes == 7 ? (0x1Du << 8) : 0u;
+__host__ __device__ constexpr uint32_t fold_byte(uint32_t byte) { return byte ^ ((kFold >> (8 * (byte >> kQuietPlanes))) & 0xFFu); }
+
+#ifndef SQZ_BUSY_ITERATIONS
+#define SQZ_BUSY_ITERATIONS 8
+#endif
+#ifndef SQZ_GATE_Q1
+#define SQZ_GATE_Q1 0     // 1: the latency shape adapts its gate as well
+#endif
+#ifndef SQZ_QUIET_ENTRIES
+#define SQZ_QUIET_ENTRIES 5
+#endif
+#ifndef SQZ_BUSY_ENTRIES
+#define SQZ_BUSY_ENTRIES 10
+#endif
 #ifndef SQZ_T0_STRICT
 #define SQZ_T0_STRICT 1   // a best found at the nearest of an iteration's distances (t = 0) is strict at once
 #endif
@@ -127,6 +157,31 @@ __host__ __device__ inline Geometry geometry(uint32_t max_len, uint32_t max_dist
 
 __device__ __forceinline__ uint32_t fsr(uint32_t lo, uint32_t hi, int s) {
     return __funnelshift_r(lo, hi, s);               // bits [s, s+32) of hi:lo
+}
+
+// a | (b ^ c) as the one LOP3 it is (left to itself the compiler regroups the two planes the gated body
+// adds into three instructions per pair instead of two)
+__device__ __forceinline__ uint32_t or_xor(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xF6;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
+// Planes kQuietPlanes..7 (the bytes' high bits as they are) of the pair (query block qb, candidate blocks cb, cb+1
+// shifted by sh): what a compare over the hashed planes cannot tell.  Shared memory; the scalar path only.
+__device__ __forceinline__ uint32_t high_planes_differ(const uint4* __restrict__ PL, int qb, int cb, int sh) {
+    const uint32_t* W = reinterpret_cast<const uint32_t*>(PL);
+    uint32_t x = 0;
+#pragma unroll
+    for (int b = kQuietPlanes; b < 8; b++) { x |= fsr(W[8 * cb + b], W[8 * (cb + 1) + b], sh) ^ W[8 * qb + b]; }
+    return x;
+}
+
+// the eight plane words of plane block `blk` (shared memory)
+__device__ __forceinline__ void load_planes(const uint4* __restrict__ PL, int blk, uint32_t (&w)[8]) {
+    const uint4 a = PL[2 * blk], b = PL[2 * blk + 1];
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+    w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
 }
 
 // ---------------------------------------------------------------------------
@@ -312,7 +367,10 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
     constexpr int kWarpOwned = warp_owned(kQ), kTileBlocks = tile_blocks(kQ), kTilePos = tile_pos(kQ);
     constexpr int kStageBlocks = stage_blocks(kQ);
     constexpr int kGated = gated(kQ);
-    constexpr int kQuietGroups = 4;                // groups (of 128 distances) without a candidate before the need masks are dropped
+    constexpr int kQuietGroups = 4;                // quiet groups (of 128 distances) before the need masks are dropped
+    constexpr int kQuietEntries = SQZ_QUIET_ENTRIES;   // a group is quiet when the warp's threads met at most this many candidates' iterations
+    constexpr int kBusyEntries = SQZ_BUSY_ENTRIES;     // ... and brings the masks back when they met this many
+    constexpr int kBusyIterations = SQZ_BUSY_ITERATIONS;             // masks off: iterations with a candidate in one group that bring them back at once
     const Geometry geo = geometry(max_len, max_dist, kEdge, init_table != nullptr, kQ);
     const uint4* PL = reinterpret_cast<const uint4*>(smem_raw);           // [plane_blocks][2]
     uint8_t* best_len = smem_raw + geo.region_bytes;                      // [kTilePos + 32]
@@ -361,7 +419,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
             for (int blk = b0 + warp; blk < b0 + nb; blk += kWarps) {
                 const long long pos = plane_pos0 + (long long)blk * 32 + lane;
                 const bool ok = pos >= -back && pos < n + ahead;
-                const uint32_t byte = stage[mis + (blk - b0) * 32 + lane];   // zero where there is no data
+                const uint32_t byte = fold_byte(stage[mis + (blk - b0) * 32 + lane]);   // zero where there is no data
                 uint32_t mine = 0;
 #pragma unroll
                 for (int bit = 0; bit < 8; bit++) {
@@ -414,9 +472,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
 #pragma unroll
     for (int q = 0; q < kQ; q++) {
         SQZ_CHECK(blk0 + q >= 0 && blk0 + q < geo.plane_blocks, "phase 1: query plane block out of range");
-        const uint4 a = PL[2 * (blk0 + q)], b = PL[2 * (blk0 + q) + 1];
-        qv[q][0] = a.x; qv[q][1] = a.y; qv[q][2] = a.z; qv[q][3] = a.w;
-        qv[q][4] = b.x; qv[q][5] = b.y; qv[q][6] = b.z; qv[q][7] = b.w;
+        load_planes(PL, blk0 + q, qv[q]);
         // closed from the start: the look-ahead block and positions past the shard
         const long long p0 = tile_pos0 + (long long)(own0 + q) * 32;
         uint32_t closed = 0;
@@ -458,14 +514,14 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
 #pragma unroll
     for (int q = 0; q < kQ; q++) { fresh[q] = 0; }
     bool gate_on = true;                    // need masks in use (decided per warp and group, see the end of the loop)
-    // one word of warp-wide bookkeeping for that decision: bits 0-1 iterations of the current group, masks off,
-    // in which some thread met a candidate; bits 2-8 consecutive groups without one; bits 9-15 how many of those
+    // one word of warp-wide bookkeeping for that decision: bits 0-3 iterations of the current group, masks off,
+    // in which some thread met a candidate; bits 4-10 consecutive quiet groups; bits 11-17 how many of those
     // it takes to drop the masks
-    uint32_t quiet = (uint32_t)kQuietGroups << 9;
+    uint32_t quiet = (uint32_t)kQuietGroups << 11;
     uint32_t entered = 0;                   // iterations of the current group in which this thread met a candidate
     // debugging aid (tools/tile_cycles.py, -DSQZ_DEBUG_COUNTERS builds only): what the scalar path sees
 #ifdef SQZ_DEBUG_COUNTERS
-    unsigned int c_surv = 0, c_better = 0, c_tie_fresh = 0, c_reject = 0, c_hand = 0, c_iter_slow = 0;
+    unsigned int c_surv = 0, c_better = 0, c_tie_fresh = 0, c_reject = 0, c_hand = 0, c_iter_slow = 0, c_false = 0;
 #define SQZ_COUNT(x) ((x)++)
 #else
 #define SQZ_COUNT(x) ((void)0)
@@ -482,9 +538,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
 #pragma unroll
         for (int j = 0; j < 2 * kQ; j++) {
             SQZ_CHECK(jb + j >= 0 && jb + j < geo.plane_blocks, "phase 1: candidate plane block out of range");
-            const uint4 a = PL[2 * (jb + j)], b = PL[2 * (jb + j) + 1];
-            cr[j][0] = a.x; cr[j][1] = a.y; cr[j][2] = a.z; cr[j][3] = a.w;
-            cr[j][4] = b.x; cr[j][5] = b.y; cr[j][6] = b.z; cr[j][7] = b.w;
+            load_planes(PL, jb + j, cr[j]);
             vr[j] = kEdge ? VL[jb + j] : 0xFFFFFFFFu;
         }
 #pragma unroll 1
@@ -493,15 +547,18 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
             uint32_t e[kQ][kQ];
 #pragma unroll
             for (int b = 0; b < 8; b++) {
-                uint32_t sw[2 * kQ - 1];
+                // quiet data: the hashed planes only (the same for the whole warp)
+                if (b < kQuietPlanes || gate_on) {
+                    uint32_t sw[2 * kQ - 1];
 #pragma unroll
-                for (int j = 0; j < 2 * kQ - 1; j++) { sw[j] = fsr(cr[j][b], cr[j + 1][b], sh); }
+                    for (int j = 0; j < 2 * kQ - 1; j++) { sw[j] = fsr(cr[j][b], cr[j + 1][b], sh); }
 #pragma unroll
-                for (int q = 0; q < kQ; q++) {
+                    for (int q = 0; q < kQ; q++) {
 #pragma unroll
-                    for (int t = 0; t < kQ; t++) {
-                        const uint32_t x = sw[q - t + kQ - 1] ^ qv[q][b];
-                        e[q][t] = b == 0 ? x : (e[q][t] | x);
+                        for (int t = 0; t < kQ; t++) {
+                            if (b == 0) { e[q][t] = sw[q - t + kQ - 1] ^ qv[q][b]; }
+                            else        { e[q][t] = or_xor(e[q][t], sw[q - t + kQ - 1], qv[q][b]); }
+                        }
                     }
                 }
             }
@@ -539,7 +596,8 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                 }
             } else {
                 // quiet data (an image): hardly any candidate matches even min_len bytes, so the need
-                // masks filter nothing; test min_len bytes only and let the scalar path judge the rest
+                // masks filter nothing; test min_len bytes only, on the hashed planes only, and let the scalar
+                // path judge the rest
 #pragma unroll
                 for (int q = 0; q < kQ; q++) {
                     uint32_t all_t = 0xFFFFFFFFu;
@@ -553,11 +611,12 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                     }
                     none &= all_t | closed_m[q];
                 }
-                // a wrong guess must not last: the third iteration of a group in which some thread meets a
-                // candidate brings the masks back at once
-                if (__any_sync(0xFFFFFFFFu, none != 0xFFFFFFFFu) && (++quiet & 3u) == 3u) {
+                // a wrong guess must not last: the eighth iteration of a group in which some thread meets a
+                // candidate brings the masks back at once (incompressible data has two or three such
+                // iterations per group: candidates whose hashed bytes agree, see kQuietPlanes)
+                if (__any_sync(0xFFFFFFFFu, none != 0xFFFFFFFFu) && (++quiet & 15u) == (uint32_t)kBusyIterations) {
                     gate_on = true;
-                    quiet = (uint32_t)kQuietGroups << 9;      // no quiet groups
+                    quiet = (uint32_t)kQuietGroups << 11;     // no quiet groups
                 }
             }
             if (none != 0xFFFFFFFFu) {
@@ -592,7 +651,10 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                             }
                             if (kEdge) { hi |= ~vq[q + 1] | ~fsr(vr[q + 1 - t + kQ - 1], vr[q + 1 - t + kQ], shx); }
                         } else {
+                            // the next lane's word: exact only if that lane compared all eight planes.  A warp in
+                            // its quiet body compared the hashed ones; the others come from shared memory here.
                             hi = en[t];
+                            if (kQuietPlanes < 8 && (kQ > 1 || SQZ_GATE_Q1)) { hi |= high_planes_differ(PL, blk0 + kQ, jb + 2 * kQ - 1 - t, shx); }
                         }
                         while (todo != 0) {
                             const int p = __ffs((int)todo) - 1;
@@ -615,6 +677,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                                 continue;
                             }
                             const uint32_t run = (uint32_t)(__ffs((int)win) - 1);
+                            if (kQuietPlanes < 8 && run < (uint32_t)kMinLen) { SQZ_COUNT(c_false); continue; }   // equal hashes, different bytes
                             bool better = run > have;
                             if (run == have && (fresh[q] & bit)) { better = d < (*slot & 0xFFFFu); SQZ_COUNT(c_tie_fresh); }
                             if (better) {
@@ -656,21 +719,21 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
             fresh[q] = 0;
         }
         // The need masks are a filter, not part of the decision: the warp drops them after four groups
-        // (512 distances) in which none of its threads met a candidate, and takes them up again as soon as
-        // two threads do in one group.  The asymmetry is deliberate: without the masks, text makes every
-        // thread meet candidates in every iteration, so a wrong guess must not last.
+        // (512 distances) in which its threads met next to no candidate, and takes them up again as soon
+        // as a group brings more than a few.  The asymmetry is deliberate: without the masks, text makes
+        // every thread meet candidates in every iteration, so a wrong guess must not last.
         {
-            const int busy = __popc(__ballot_sync(0xFFFFFFFFu, entered != 0));
+            const uint32_t met = __reduce_add_sync(0xFFFFFFFFu, entered);   // thread-iterations with a candidate
 #ifndef SQZ_GATE_ALWAYS
-            if (kQ > 1) {       // (the latency shape keeps the masks: its loop is short, dropping them measured slower)
-                const uint32_t need = quiet >> 9;
-                uint32_t groups = (quiet >> 2) & 127u;
-                if (busy >= 2) { groups = 0; } else if (busy == 0 && groups < need) { groups++; }
+            if (kQ > 1 || SQZ_GATE_Q1) {       // (the latency shape keeps the masks: its loop is short, dropping them measured slower)
+                const uint32_t need = quiet >> 11;
+                uint32_t groups = (quiet >> 4) & 127u;
+                if (met >= (uint32_t)kBusyEntries) { groups = 0; } else if (met <= (uint32_t)kQuietEntries && groups < need) { groups++; }
                 gate_on = groups < need;
-                quiet = (need << 9) | (groups << 2);
+                quiet = (need << 11) | (groups << 4);
             }
 #else
-            (void)busy;
+            (void)met;
 #endif
             entered = 0;
         }
@@ -693,6 +756,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
         atomicAdd(dbg2 + 0, (unsigned long long)c_surv); atomicAdd(dbg2 + 1, (unsigned long long)c_better);
         atomicAdd(dbg2 + 2, (unsigned long long)c_tie_fresh); atomicAdd(dbg2 + 3, (unsigned long long)c_reject);
         atomicAdd(dbg2 + 4, (unsigned long long)c_hand); atomicAdd(dbg2 + 5, (unsigned long long)c_iter_slow);
+        atomicAdd(dbg2 + 6, (unsigned long long)c_false);
         __syncthreads();
         if (threadIdx.x == 0) { tile_cycles[tile] = (unsigned long long)(clock64() - t_begin); }
     }

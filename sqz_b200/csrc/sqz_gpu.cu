@@ -545,8 +545,7 @@ constexpr int kMaxDevices = 64;
 struct DeviceState {
     std::once_flag once;
     cudaError_t err = cudaSuccess;
-    cudaStream_t side = nullptr, side2 = nullptr;   // edge tiles
-    cudaStream_t alt = nullptr, fin = nullptr;      // large shards: every other piece's tiles; phase 2 of a piece (high priority)
+    cudaStream_t side = nullptr, side2 = nullptr;
     int sms = 0;
 };
 static DeviceState g_dev[kMaxDevices];
@@ -587,12 +586,6 @@ static int device_state(DeviceState** out) {
         if (e == cudaSuccess) { e = cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev); }
         if (e == cudaSuccess) { e = cudaStreamCreateWithFlags(&d.side, cudaStreamNonBlocking); }
         if (e == cudaSuccess) { e = cudaStreamCreateWithFlags(&d.side2, cudaStreamNonBlocking); }
-        if (e == cudaSuccess) { e = cudaStreamCreateWithFlags(&d.alt, cudaStreamNonBlocking); }
-        if (e == cudaSuccess) {
-            int least = 0, greatest = 0;
-            e = cudaDeviceGetStreamPriorityRange(&least, &greatest);
-            if (e == cudaSuccess) { e = cudaStreamCreateWithPriority(&d.fin, cudaStreamNonBlocking, greatest); }
-        }
         d.err = e;
     });
     if (d.err != cudaSuccess) { return fail(cuda_code(d.err), "per-device set-up", d.err); }
@@ -756,15 +749,9 @@ static int launch_v1(const uint8_t* d_shard, size_t back, size_t n, size_t ahead
     return 0;
 }
 
-// One launch sequence over a shard (or a piece of one): edge tiles, interior tiles, the fold of the
-// slices, phase 2.  `fin` is the stream phase 2 runs on: `s` itself, or -- pieces of a large shard,
-// launch_v2 -- the device's high-priority stream with `finish_ctas_per_sm` persistent CTAs per SM, so
-// that the latency-bound phase 2 of one piece shares the SMs with the ALU-bound tiles of the next.
-// `fin_done` is recorded on `fin` behind phase 2 then.
 template <int kMinLen, int kQ>
 static int launch_tiles(const SlicePlan& sp, const uint8_t* d_shard, size_t back, size_t n, size_t ahead, uint32_t max_len,
-                        uint32_t max_dist, uint32_t* d_table, unsigned int* d_counters, uint32_t* d_open, uint32_t* d_slices,
-                        cudaStream_t s, cudaStream_t fin, int finish_ctas_per_sm, cudaEvent_t fin_done) {
+                        uint32_t max_dist, uint32_t* d_table, void* d_work, cudaStream_t s) {
     DeviceState* dv = nullptr;
     if (int r = device_state(&dv)) { return r; }
     // Tiles whose every position sees the full max_dist window and max_len of
@@ -779,12 +766,14 @@ static int launch_tiles(const SlicePlan& sp, const uint8_t* d_shard, size_t back
     t_lo = std::min(t_lo, tiles);
     t_hi = std::max(std::min(t_hi, tiles), t_lo);
     if ((unsigned long long)n > 0xFFFFFFFFull) { return fail(EINVAL, "shard too large for one launch"); }
-    CU(cudaMemsetAsync(d_counters, 0, sizeof(unsigned int), s));
+    unsigned int* d_counters = static_cast<unsigned int*>(d_work);
+    uint32_t* d_open = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(d_work) + kCursorBytes);
+    CU(cudaMemsetAsync(d_counters, 0, 16, s));
     const int smem_main = v2::geometry(max_len, max_dist, false, false, kQ).smem_bytes;
     const int smem_edge = v2::geometry(max_len, max_dist, true, false, kQ).smem_bytes;
     // small shards: the distance range is split across CTAs as well, the slices' tables sit behind
     // the work list and are folded into d_table afterwards
-    if (sp.slices <= 1) { d_slices = nullptr; }
+    uint32_t* d_slices = sp.slices > 1 ? reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(d_work) + kCursorBytes + mask_bytes(n)) : nullptr;
     // The few edge tiles run concurrently with the interior tiles: leading and trailing edge
     // tiles each on a side stream of the device, forked from and joined back into `s`.
     const bool lead = t_lo > 0, trail = tiles > t_hi;
@@ -838,78 +827,20 @@ static int launch_tiles(const SlicePlan& sp, const uint8_t* d_shard, size_t back
     }
     const v2::FinishShape fs = v2::finish_shape((long long)n, max_len, max_dist, dv->sms);
     const long long chunks = ((long long)n + fs.chunk - 1) / fs.chunk;
-    const unsigned finish_ctas = (unsigned)std::min<long long>(chunks, (long long)dv->sms * finish_ctas_per_sm);
-    if (fin != s) {
-        ScopedEvent tiles_done;
-        CU(tiles_done.create());
-        CU(cudaEventRecord(tiles_done.e, s));
-        CU(cudaStreamWaitEvent(fin, tiles_done.e, 0));
-    }
-    v2::finish_marked<<<finish_ctas, v2::kThreads, fs.smem_bytes, fin>>>(
+    const unsigned finish_ctas = (unsigned)std::min<long long>(chunks, (long long)dv->sms * v2::kFinishCtasPerSm);
+    v2::finish_marked<<<finish_ctas, v2::kThreads, fs.smem_bytes, s>>>(
         d_shard, (long long)back, (long long)n, (long long)ahead, (uint32_t)kMinLen, max_len, max_dist, d_table, d_open,
         d_counters, g_tile_cycles ? g_tile_cycles + (1 << 20) : nullptr, fs.chunk, fs.sub);
     LAUNCHED("match_finish_marked");
-    if (fin != s) { CU(cudaEventRecord(fin_done, fin)); }
     return 0;
 }
-
-// Large shards are cut into pieces of about eight waves of tiles.  The pieces' tiles alternate between
-// the caller's stream and a second one, so that a piece starts in the slots the previous one's last
-// tiles leave free; phase 2 of a piece runs on a third, high-priority stream with two persistent CTAs
-// per SM while the next pieces' tiles keep the ALU pipe busy (phase 2 waits on shared-memory and L2
-// latency; run alone it leaves the pipe idle for 8 % of a step).  A piece is a shard of its own with
-// the rest of the shard as its halos, so nothing is exchanged; its last position, which has no
-// neighbour above inside the piece, is searched instead of inheriting -- the result is the same.
-constexpr size_t kPieceWaves = 8;
-constexpr int kMaxPieces = (int)(kCursorBytes / 8);
-constexpr int kOverlapFinishCtasPerSm = 2;
 
 template <int kMinLen>
 static int launch_v2(const uint8_t* d_shard, size_t back, size_t n, size_t ahead, uint32_t max_len,
                      uint32_t max_dist, uint32_t* d_table, void* d_work, cudaStream_t s) {
     const SlicePlan sp = slice_plan(n, max_dist);
-    unsigned int* d_counters = static_cast<unsigned int*>(d_work);
-    uint32_t* d_open = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(d_work) + kCursorBytes);
-    uint32_t* d_slices = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(d_work) + kCursorBytes + mask_bytes(n));
-    if (sp.q == 1) {
-        return launch_tiles<kMinLen, 1>(sp, d_shard, back, n, ahead, max_len, max_dist, d_table, d_counters, d_open, d_slices,
-                                        s, s, v2::kFinishCtasPerSm, nullptr);
-    }
-    const size_t tp = (size_t)v2::tile_pos(4);
-    const size_t tiles = (n + tp - 1) / tp;
-    int pieces = (int)std::min<size_t>(tiles / (kPieceWaves * kWaveQ4), (size_t)kMaxPieces);
-    int overlap_ctas = kOverlapFinishCtasPerSm;
-#ifdef SQZ_TUNING
-    if (const char* e = getenv("SQZ_PIECES")) { pieces = std::min(atoi(e), kMaxPieces); }
-    if (const char* e = getenv("SQZ_FIN_CTAS")) { overlap_ctas = atoi(e); }
-#endif
-    if (pieces < 2 || sp.slices > 1) {
-        return launch_tiles<kMinLen, 4>(sp, d_shard, back, n, ahead, max_len, max_dist, d_table, d_counters, d_open, d_slices,
-                                        s, s, v2::kFinishCtasPerSm, nullptr);
-    }
-    DeviceState* dv = nullptr;
-    if (int r = device_state(&dv)) { return r; }
-    ScopedEvent fork, alt_done, fin_done;
-    CU(fork.create());
-    CU(alt_done.create());
-    CU(fin_done.create());
-    CU(cudaEventRecord(fork.e, s));
-    CU(cudaStreamWaitEvent(dv->alt, fork.e, 0));
-    for (int k = 0; k < pieces; k++) {
-        const size_t a = tiles * (size_t)k / (size_t)pieces * tp;                       // whole tiles, so whole mask words
-        const size_t b = k + 1 == pieces ? n : tiles * (size_t)(k + 1) / (size_t)pieces * tp;
-        const bool last = k + 1 == pieces;
-        cudaStream_t on = (k & 1) ? dv->alt : s;
-        // the last piece has nothing to share the device with: its phase 2 stays behind its tiles, at full width
-        const int r = launch_tiles<kMinLen, 4>(sp, d_shard + a, back + a, b - a, ahead + (n - b), max_len, max_dist, d_table + a,
-                                               d_counters + 2 * k, d_open + a / 32, nullptr, on, last ? on : dv->fin,
-                                               last ? v2::kFinishCtasPerSm : overlap_ctas, fin_done.e);
-        if (r != 0) { return r; }
-    }
-    CU(cudaEventRecord(alt_done.e, dv->alt));
-    CU(cudaStreamWaitEvent(s, alt_done.e, 0));
-    CU(cudaStreamWaitEvent(s, fin_done.e, 0));           // recorded behind the last phase 2 queued on the stream
-    return 0;
+    return sp.q == 1 ? launch_tiles<kMinLen, 1>(sp, d_shard, back, n, ahead, max_len, max_dist, d_table, d_work, s)
+                     : launch_tiles<kMinLen, 4>(sp, d_shard, back, n, ahead, max_len, max_dist, d_table, d_work, s);
 }
 
 extern "C" int sqz_gpu_match_table_device_ws(const uint8_t* d_shard, size_t back, size_t n,

@@ -432,10 +432,9 @@ def test_shards_of_a_few_waves(mib, offset, oracle):
     assert end == n and tk.size == ot.size and (tk == ot).all()
 
 
-def test_shard_in_pieces_with_overlapped_phase_two(oracle):
-    """A shard of more than 16 waves of tiles is cut into pieces whose tiles alternate between two
-    streams while phase 2 of a finished piece runs beside them (sqz_gpu.cu: launch_v2).  240 MiB =
-    4 pieces, as a shard with halos on both sides and from position 0: full table == oracle B."""
+def test_large_device_shard_with_and_without_halos(oracle):
+    """The device ABI on a 240 MiB shard (35 waves of tiles), from position 0 and as a shard with halos on
+    both sides: full table == oracle B."""
     from sqz_b200 import device
     n = 240 << 20
     d = corpus.synthetic(n, 5 << 20)

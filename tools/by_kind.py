@@ -23,6 +23,10 @@ for name, base in kinds.items():
         e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
     c = cyc.cpu().numpy(); dbg = c[1 << 20:]; cyc.zero_()
-    print("%-6s rc %d %.1f ms %.0f MB/s | per position (3 runs): survivors %.2f better %.2f fresh-ties %.2f rejects %.2f handed %.3f | slow iterations %.1f%% of %d thread-iterations | phase2: searched %.3f%% inherited %.3f%% steps/search %.0f verifies/search %.1f" % (
-        name, rc, best, size / 1e3 / best, dbg[8] / 3 / size, dbg[9] / 3 / size, dbg[10] / 3 / size, dbg[11] / 3 / size, dbg[12] / 3 / size,
+    print("%-6s rc %d %.1f ms %.0f MB/s | per position (3 runs): survivors %.2f better %.2f fresh-ties %.2f rejects %.2f handed %.3f hash-only %.3f | slow iterations %.1f%% of %d thread-iterations | phase2: searched %.3f%% inherited %.3f%% steps/search %.0f verifies/search %.1f" % (
+        name, rc, best, size / 1e3 / best, dbg[8] / 3 / size, dbg[9] / 3 / size, dbg[10] / 3 / size, dbg[11] / 3 / size, dbg[12] / 3 / size, dbg[14] / 3 / size,
         100.0 * dbg[13] / max(1, 3 * (size // 128 + 1) * 8192), 3 * (size // 128 + 1) * 8192, 100.0 * dbg[0] / 3 / size, 100.0 * dbg[5] / 3 / size, dbg[1] / max(dbg[0], 1), dbg[2] / max(dbg[0], 1)), flush=True)
+    why = {16: "neighbour open", 17: "neighbour without a match", 18: "neighbour at max_len, byte differs", 19: "byte differs",
+           20: "no neighbour in the shard", 21: "other", 22: "capped inheritance's search"}
+    print("       phase 2 searches by reason (% of positions): " + ", ".join("%s %.3f" % (w, 100.0 * dbg[k] / 3 / size) for k, w in why.items()) +
+          " | verify rounds/search %.1f" % (dbg[4] / max(dbg[0], 1)), flush=True)

@@ -75,8 +75,20 @@ def hot_loop(lib=None, kernel="match_tableILi3ELb0ELi4E"):
         for t in lines:
             hist[op(t)] = hist.get(op(t), 0) + 1
         return hist
+    # planes only the gated body compares: a conditional forward branch in front of the exchange that lands in front of it
+    p_at = p_to = None
+    for a, t in ins:
+        m = re.search(r"^@!?U?P\d+\s+BRA\s+0x([0-9a-f]+)", t)
+        if m and head < a < first and a < int(m.group(1), 16) <= first:
+            p_at, p_to = a, int(m.group(1), 16)
+            break
+    gated_only = [t for a, t in ins if p_at is not None and p_at < a < p_to]
     full = count(common + bodies[1])
-    quiet = count(common + bodies[0]) if bodies[0] else None
+    quiet = None
+    if bodies[0]:
+        quiet = count(common + bodies[0])
+        for k, v in count(gated_only).items():
+            quiet[k] -= v
     alu = full.get("LOP3", 0) + full.get("SHF", 0)
     out = {"kernel": "v2::match_table<3,false,4>", "loop_head": hex(head), "skip_branch": hex(skip_at), "skip_target": hex(skip_to),
            "back_branch": hex(back), "fast_path_instructions": sum(full.values()), "alu_instr_per_warp_iteration": alu,
@@ -86,7 +98,8 @@ def hot_loop(lib=None, kernel="match_tableILi3ELb0ELi4E"):
     if quiet:
         out["quiet_body"] = {"fast_path_instructions": sum(quiet.values()),
                              "alu_instr_per_warp_iteration": quiet.get("LOP3", 0) + quiet.get("SHF", 0),
-                             "note": "the loop body a warp runs while hardly any of its threads meets a candidate (no need masks)"}
+                             "note": "the loop body a warp runs while hardly any of its threads meets a candidate (no need masks, hashed planes only)",
+                             "gated_only_plane_instructions": len(gated_only)}
     return out
 
 
