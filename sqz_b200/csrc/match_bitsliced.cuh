@@ -103,9 +103,6 @@ __host__ __device__ constexpr uint32_t fold_byte(uint32_t byte) { return byte ^ 
 #ifndef SQZ_BUSY_ITERATIONS
 #define SQZ_BUSY_ITERATIONS 8
 #endif
-#ifndef SQZ_GATE_Q1
-#define SQZ_GATE_Q1 0     // 1: the latency shape adapts its gate as well
-#endif
 #ifndef SQZ_QUIET_ENTRIES
 #define SQZ_QUIET_ENTRIES 5
 #endif
@@ -654,7 +651,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
                             // the next lane's word: exact only if that lane compared all eight planes.  A warp in
                             // its quiet body compared the hashed ones; the others come from shared memory here.
                             hi = en[t];
-                            if (kQuietPlanes < 8 && (kQ > 1 || SQZ_GATE_Q1)) { hi |= high_planes_differ(PL, blk0 + kQ, jb + 2 * kQ - 1 - t, shx); }
+                            if (kQuietPlanes < 8 && kQ > 1) { hi |= high_planes_differ(PL, blk0 + kQ, jb + 2 * kQ - 1 - t, shx); }
                         }
                         while (todo != 0) {
                             const int p = __ffs((int)todo) - 1;
@@ -725,7 +722,7 @@ match_table(const uint8_t* __restrict__ shard, long long back, long long n, long
         {
             const uint32_t met = __reduce_add_sync(0xFFFFFFFFu, entered);   // thread-iterations with a candidate
 #ifndef SQZ_GATE_ALWAYS
-            if (kQ > 1 || SQZ_GATE_Q1) {       // (the latency shape keeps the masks: its loop is short, dropping them measured slower)
+            if (kQ > 1) {       // (the latency shape keeps the masks and all eight planes: its loop is short, adapting measured slower)
                 const uint32_t need = quiet >> 11;
                 uint32_t groups = (quiet >> 4) & 127u;
                 if (met >= (uint32_t)kBusyEntries) { groups = 0; } else if (met <= (uint32_t)kQuietEntries && groups < need) { groups++; }
