@@ -167,6 +167,10 @@ enum { none = -1, no_node = 0xFFFF,
        lut_node_bits = 10 };                    /* a table entry: node (< 1023) | bits to consume << 10 */
 
 static void note_change(struct sqz_tree* t, int32_t leaf);
+struct code_tables;
+struct duo;
+/* who is told when a leaf's code changes: the one-thread coder's tables, or the two-thread coder's log */
+struct watch { struct code_tables* tables; struct duo* d; };
 
 static inline int32_t tree_root(const struct sqz_tree* t) { return 2 * t->n - 2; }
 static inline uint32_t always_node(const struct sqz_tree* t) { return 2 * (uint32_t)t->n - 1; } /* weight 0 */
@@ -199,8 +203,15 @@ static void tree_init(struct sqz_tree* t) {
 /* Re-derive code length and code of everything below `top` from top's own.
  * A relabel that starts at the root restarts the depth high-water mark
  * (huffman.h:41-62).  Iterative: the order of visits does not matter.       */
+#ifdef SQZ_SELFCHECK
+static _Thread_local uint64_t selfcheck_relabels;    /* how often this thread changed a tree's shape */
+#endif
+
 static void relabel(struct sqz_tree* t, int32_t top) {
     int16_t stack[2 * sqz_lit_symbols];
+#ifdef SQZ_SELFCHECK
+    selfcheck_relabels++;
+#endif
     int sp = 0;
     int32_t depth = (top == tree_root(t)) ? 0 : t->depth;
     stack[sp++] = (int16_t)top;
@@ -215,7 +226,7 @@ static void relabel(struct sqz_tree* t, int32_t top) {
         if (i < t->n) {
             if (bits > 0) {
                 t->code[i] = reverse64(path) >> (64 - bits);
-                if (t->watcher != NULL) { note_change(t, i); }      /* two-thread coder: tell the emitter */
+                if (t->watcher != NULL) { note_change(t, i); }      /* the emitter's tables follow */
             }
             t->steps[i] = 0;            /* the shape above this leaf changed: its plan is void */
         }
@@ -630,6 +641,177 @@ static void tree_count(struct sqz_tree* t, int32_t s) {
 }
 
 /* ======================================================================== *
+ *  counting a block of symbols at once                                      *
+ *  A reordering happens about once per 2700 symbols; in between the model   *
+ *  only adds 1 along a path per symbol, and additions commute.  So a block  *
+ *  of symbols is tallied per leaf and every distinct leaf walks its plan    *
+ *  once, adding its count -- provided no walk of the block, taken one by    *
+ *  one in any order, could have reordered anything: all weights only grow   *
+ *  during the block, so if a node's weight at the END of the block does not *
+ *  exceed its comparator's weight at the START of the block, it exceeded it *
+ *  at no moment in between.  A block that fails the test is undone from the *
+ *  snapshot the start weights are kept in, and its symbols go through the   *
+ *  one-by-one path in smaller portions.  Exact, not approximate: the test   *
+ *  only ever errs towards the slow path.                                    *
+ * ======================================================================== */
+
+#ifndef SQZ_BLOCK_MOST
+#define SQZ_BLOCK_MOST 2048
+#endif
+enum { block_most = SQZ_BLOCK_MOST,    /* tokens per block when all goes well */
+       block_least = 32 };             /* below this a block is not worth its snapshot */
+
+struct tally {
+    uint16_t lit_count[sqz_lit_symbols];
+    uint16_t pos_count[sqz_pos_symbols + 8];       /* + slots a literal's "no distance" goes to, in turn */
+    uint16_t lit_seen[block_most];      /* distinct symbols in order of first appearance */
+    uint16_t pos_seen[sqz_pos_symbols];
+    uint64_t lit_start[2 * sqz_lit_symbols + 1];   /* weights as they were when the block began, and */
+    uint64_t pos_start[2 * sqz_pos_symbols + 1];   /* the comparators "always" (0) and "never" (2^63-1) */
+};
+
+static void tally_init(struct tally* y) {
+    memset(y->lit_count, 0, sizeof(y->lit_count));
+    memset(y->pos_count, 0, sizeof(y->pos_count));
+    y->lit_start[2 * sqz_lit_symbols - 1] = 0;  y->lit_start[2 * sqz_lit_symbols] = (uint64_t)INT64_MAX;
+    y->pos_start[2 * sqz_pos_symbols - 1] = 0;  y->pos_start[2 * sqz_pos_symbols] = (uint64_t)INT64_MAX;
+}
+
+static inline void keep_weights(const struct sqz_tree* t, uint64_t* start) {
+    memcpy(start, t->freq, sizeof(uint64_t) * (size_t)t->n);                         /* the leaves */
+    memcpy(start + t->next, t->freq + t->next, sizeof(uint64_t) * (size_t)(2 * t->n - 1 - t->next));
+}
+
+static inline void restore_weights(struct sqz_tree* t, const uint64_t* start) {
+    memcpy(t->freq, start, sizeof(uint64_t) * (size_t)t->n);
+    memcpy(t->freq + t->next, start + t->next, sizeof(uint64_t) * (size_t)(2 * t->n - 1 - t->next));
+}
+
+/* `kinds` distinct leaves `seen[]`, leaf s occurring count[s] times, `total` occurrences in all.
+ * 1: the weights now are what counting them one by one would have left and nothing else changed;
+ * 0: nothing changed, the caller has to take another way (a symbol not yet in the tree or not a
+ * symbol at all, the lazy stretch too short, a path deeper than a plan, a possible reordering).   */
+static inline __attribute__((always_inline))
+int tree_count_block(struct sqz_tree* t, const uint16_t* seen, uint32_t kinds, const uint16_t* count,
+                     uint32_t total, uint64_t* start, const int usual, const int32_t nyt) {
+    if (total == 0) { return 1; }
+    if (t->lazy < (int32_t)total) { return 0; }
+    for (uint32_t j = 0; j < kinds; j++) {
+        const int32_t s = seen[j];
+        if (t->up[s] < 0 || s == nyt) { return 0; }
+        if (t->steps[s] == 0) { settle(t); make_plan(t, s); }
+        if (t->steps[s] == plan_too_deep) { return 0; }
+    }
+    keep_weights(t, start);
+    uint64_t* const freq = t->freq;
+    int64_t fires = 0;
+#define SQZ_BLOCK_STEP(k_) do {                                                              \
+        const int64_t w_ = (int64_t)freq[plan[k_]] + c;                                      \
+        fires |= (int64_t)start[plan[plan_levels + (k_)]] - w_;                              \
+        freq[plan[k_]] = (uint64_t)w_; } while (0)
+    for (uint32_t j = 0; j < kinds; j++) {
+        const int32_t s = seen[j];
+        const int64_t c = count[s];
+        const uint16_t* const plan = t->plan + (size_t)s * 2 * plan_levels;
+        SQZ_BLOCK_STEP(0);
+#pragma GCC unroll 16
+        for (int k = top_levels + 1; k < usual; k++) { SQZ_BLOCK_STEP(k); }
+        if (t->steps[s] != usual) {
+            for (int k = usual; k < plan_levels; k++) { SQZ_BLOCK_STEP(k); }
+        }
+    }
+#undef SQZ_BLOCK_STEP
+    if (fires < 0) {
+        restore_weights(t, start);
+        return 0;
+    }
+    t->lazy -= (int32_t)total;
+    return 1;
+}
+
+static inline void forget_tally(struct tally* y, uint32_t lit_kinds, uint32_t pos_kinds) {
+    for (uint32_t j = 0; j < lit_kinds; j++) { y->lit_count[y->lit_seen[j]] = 0; }
+    for (uint32_t j = 0; j < pos_kinds; j++) { y->pos_count[y->pos_seen[j]] = 0; }
+}
+
+/* count the symbols of the words [0, n); returns the number of distinct literal/length symbols */
+static __attribute__((noinline))
+uint32_t tally_words(struct tally* y, const uint32_t* words, uint32_t n) {
+    uint16_t* const lit_count = y->lit_count;
+    uint16_t* const pos_count = y->pos_count;
+    uint16_t* const lit_seen = y->lit_seen;
+    uint32_t lit_kinds = 0;
+    for (uint32_t k = 0; k < n; k++) {
+        const uint32_t w = words[k];
+        const uint32_t sym = w & 0x1FF, pb = (w >> 14) & 31;
+        /* a literal counts into one of eight idle slots: one slot would chain every literal's
+         * load-add-store to the one before */
+        const uint32_t idle = sqz_pos_symbols + (k & 7);
+        const uint32_t slot = sym >= len_symbol0 ? pb : idle;
+        const uint32_t c = lit_count[sym];
+        lit_seen[lit_kinds] = (uint16_t)sym;
+        lit_kinds += c == 0;
+        lit_count[sym] = (uint16_t)(c + 1);
+        pos_count[slot]++;
+    }
+    return lit_kinds;
+}
+
+/* Model the symbol words [0, n) of both trees as one block.  1 = done; 0 = nothing changed.
+ * n <= block_most.  Words that are no symbol words never pass (their symbol is not in the tree,
+ * or is the escape) except for flaws the model does not look at -- the emitter reports those.   */
+static int count_block(struct sqz* s, struct tally* y, const uint32_t* words, uint32_t n) {
+    struct sqz_tree* const lit = &s->lit;
+    struct sqz_tree* const pos = &s->pos;
+    uint32_t pos_kinds = 0, matches = 0;
+    const uint32_t lit_kinds = tally_words(y, words, n);
+    for (uint32_t pb = 0; pb < sqz_pos_symbols; pb++) {
+        y->pos_seen[pos_kinds] = (uint16_t)pb;
+        pos_kinds += y->pos_count[pb] != 0;
+        matches += y->pos_count[pb];
+    }
+#ifdef SQZ_SELFCHECK
+    settle(lit); settle(pos);           /* so that the replay below starts from the very same weights */
+#endif
+    int ok = tree_count_block(pos, y->pos_seen, pos_kinds, y->pos_count, matches, y->pos_start,
+                              pos_plan, sqz_pos_nyt);
+    if (ok && !tree_count_block(lit, y->lit_seen, lit_kinds, y->lit_count, n, y->lit_start,
+                                lit_plan, sqz_lit_nyt)) {
+        ok = 0;
+        if (matches != 0) { restore_weights(pos, y->pos_start); pos->lazy += (int32_t)matches; }
+    }
+    forget_tally(y, lit_kinds, pos_kinds);
+#ifdef SQZ_SELFCHECK
+    if (ok) {
+        /* the same symbols one by one from the same start: no reordering, the same weights */
+        static _Thread_local uint64_t lit_after[2 * sqz_lit_symbols - 1], pos_after[2 * sqz_pos_symbols - 1];
+        settle(lit); settle(pos);
+        memcpy(lit_after, lit->freq, sizeof(lit_after));
+        memcpy(pos_after, pos->freq, sizeof(pos_after));
+        restore_weights(lit, y->lit_start);
+        if (matches != 0) { restore_weights(pos, y->pos_start); }
+        lit->lazy = lit->lazy_start = lit->eager = 0;       /* the top is exact, nothing is decided */
+        pos->lazy = pos->lazy_start = pos->eager = 0;
+        const uint64_t shape = selfcheck_relabels;
+        for (uint32_t k = 0; k < n; k++) {
+            const uint32_t w = words[k], sym = w & 0x1FF;
+            tree_count_as(lit, (int32_t)sym, lit_plan);
+            if (sym >= len_symbol0) { tree_count_as(pos, (int32_t)((w >> 14) & 31), pos_plan); }
+        }
+        settle(lit); settle(pos);
+        if (shape != selfcheck_relabels ||
+            memcmp(lit_after, lit->freq, sizeof(uint64_t) * (size_t)(2 * lit->n - 2)) != 0 ||
+            memcmp(pos_after, pos->freq, sizeof(uint64_t) * (size_t)(2 * pos->n - 2)) != 0) {
+            fprintf(stderr, "sqz selfcheck: a block of %u symbols differs from the same symbols one by one\n", n);
+            abort();
+        }
+        selfcheck(lit); selfcheck(pos);
+    }
+#endif
+    return ok;
+}
+
+/* ======================================================================== *
  *  token coder  (reference squeeze.h:151-172, 239-315)                      *
  * ======================================================================== */
 
@@ -724,10 +906,6 @@ static inline uint32_t symbols_of_token(const struct sqz* s, uint32_t t) {
            pb << 14 | reverse_field(dist - pos_base[pb], pos_extra[pb]) << 19;
 }
 
-/* The coder proper.  The bit register lives in locals for the whole run and a
- * full word goes straight to memory when the sink is a buffer with room;
- * everything unusual (first occurrence of a symbol, callback sinks, a full
- * buffer) goes through the general functions above with the register synced. */
 static inline int word_is_valid(uint32_t w) {
     const uint32_t sym = w & 0x1FF;
     /* bucket 27 with all five extra bits set would be length 258, which no decoder accepts
@@ -736,17 +914,8 @@ static inline int word_is_valid(uint32_t w) {
                            !(sym == len_symbol0 + 27 && ((w >> 9) & 31) == 31));
 }
 
-static void code_symbols(struct sqz* s, const uint32_t* words, uint64_t count) {
-    struct sqz_bitstream* const bs = s->bs;
-    struct sqz_tree* const lit = &s->lit;
-    struct sqz_tree* const pos = &s->pos;
-    uint64_t acc = bs->b64;
-    uint32_t fill = (uint32_t)bs->bits;
-    uint64_t matches = 0;
-    if (s->error != 0) { return; }
-
-#define SQZ_SYNC_OUT()  do { bs->b64 = acc; bs->bits = (int32_t)fill; } while (0)
-#define SQZ_SYNC_IN()   do { acc = bs->b64; fill = (uint32_t)bs->bits; } while (0)
+/* Append `count_` bits `seq_` (first bit out = most significant) to the register acc/fill; a full
+ * word goes straight to memory when the sink is a buffer with room, else through word_out.      */
 #define SQZ_APPEND(seq_, count_) do {                                            \
         const uint64_t q_ = (seq_); const uint32_t c_ = (count_);                \
         const uint32_t f_ = fill + c_;                                           \
@@ -767,11 +936,191 @@ static void code_symbols(struct sqz* s, const uint32_t* words, uint64_t count) {
             fill = rest_;                                                        \
         } } while (0)
 
-    for (uint64_t k = 0; k < count; k++) {
+/* What a 9-bit symbol of the literal/length tree is: 0 = nothing a word may carry (256, the
+ * escape, anything above), 0x40 = a byte, 0x80 | extra bits = a length bucket.                 */
+static const uint8_t symbol_kind[sqz_lit_symbols] = {
+    [0 ... 255] = 0x40,
+    [257 ... 264] = 0x80, [265 ... 268] = 0x81, [269 ... 272] = 0x82, [273 ... 276] = 0x83,
+    [277 ... 280] = 0x84, [281 ... 284] = 0x85 };
+
+/* What the emitter reads: the codes of both trees as they stand for the token being emitted --
+ * plain, and as *words*: (code << extra bits) << 8 | code length + extra bits, ready to take the
+ * extra bits in with one OR; 0 where a symbol has to go the general way (no code yet, not a symbol
+ * a word may carry, more than word_lit_most / word_pos_most bits -- together 56, what one store of
+ * the byte-wise emitter takes).  pos_word[32..63] stay 0: that is where a literal looks.        */
+enum { word_lit_most = 30, word_pos_most = 26 };
+
+struct code_tables {
+    uint64_t lit_word[sqz_lit_symbols];
+    uint64_t pos_word[2 * sqz_pos_symbols];
+    uint64_t lit_code[sqz_lit_symbols];
+    uint64_t pos_code[sqz_pos_symbols];
+    uint8_t lit_bits[sqz_lit_symbols];
+    uint8_t pos_bits[sqz_pos_symbols];
+};
+
+static inline void tables_set(struct code_tables* ct, int distance_tree, uint32_t leaf, uint64_t code, uint32_t bits) {
+    if (distance_tree) {
+        const uint32_t more = leaf < 30 ? pos_extra[leaf] : 0;
+        ct->pos_code[leaf] = code;
+        ct->pos_bits[leaf] = (uint8_t)bits;
+        ct->pos_word[leaf] = (leaf < 30 && bits != 0 && bits + more <= word_pos_most)
+                           ? (code << more) << 8 | (bits + more) : 0;
+    } else {
+        const uint32_t kind = symbol_kind[leaf], more = kind & 7;
+        ct->lit_code[leaf] = code;
+        ct->lit_bits[leaf] = (uint8_t)bits;
+        ct->lit_word[leaf] = (kind != 0 && bits != 0 && bits + more <= word_lit_most)
+                           ? (code << more) << 8 | (bits + more) : 0;
+    }
+}
+
+static void tables_from_trees(struct code_tables* ct, const struct sqz* s) {
+    memset(ct->pos_word, 0, sizeof(ct->pos_word));
+    for (uint32_t k = 0; k < sqz_lit_symbols; k++) { tables_set(ct, 0, k, s->lit.code[k], s->lit.bits[k]); }
+    for (uint32_t k = 0; k < sqz_pos_symbols; k++) { tables_set(ct, 1, k, s->pos.code[k], s->pos.bits[k]); }
+}
+
+/* Emit the words [from, until) with code tables that do not change on the way (a block the model
+ * took as a whole, or the stretch between two changes of a code in the two-thread coder).  A
+ * symbol without a code yet goes out as the escape plus its raw bits (squeeze.h:278-288, 300-315:
+ * only the two-thread coder gets here with one, its model inserts the symbol).  Returns the
+ * number of matches; on an error s->error is set and the rest is not emitted.                   */
+static uint64_t emit_run_anywhere(struct sqz* s, struct sqz_bitstream* bs, const uint32_t* words,
+                                  uint64_t from, uint64_t until, const struct code_tables* ct) {
+    uint64_t acc = bs->b64;
+    uint32_t fill = (uint32_t)bs->bits;
+    uint64_t matches = 0;
+    for (uint64_t k = from; k < until; k++) {
+        const uint32_t w = words[k];
+        const uint32_t sym = w & 0x1FF;
+        if (!word_is_valid(w)) {                     /* not a symbol word: the decoder would reject it */
+            s->error = EINVAL;
+            goto done;
+        }
+        if (ct->lit_bits[sym] == 0) {
+            SQZ_APPEND(ct->lit_code[sqz_lit_nyt], ct->lit_bits[sqz_lit_nyt]);
+            SQZ_APPEND(reverse_field(sym, 9), 9);
+        } else {
+            SQZ_APPEND(ct->lit_code[sym], ct->lit_bits[sym]);
+        }
+        if (sym >= len_symbol0) {                    /* length first, then distance: squeeze.h:379-380 */
+            const uint32_t pb = (w >> 14) & 31;
+            SQZ_APPEND((w >> 9) & 31, len_extra[sym - len_symbol0]);
+            if (ct->pos_bits[pb] == 0) {
+                SQZ_APPEND(ct->pos_code[sqz_pos_nyt], ct->pos_bits[sqz_pos_nyt]);
+                SQZ_APPEND(reverse_field(pb, 5), 5);
+            } else {
+                SQZ_APPEND(ct->pos_code[pb], ct->pos_bits[pb]);
+            }
+            SQZ_APPEND(w >> 19, pos_extra[pb]);
+            matches++;
+        }
+    }
+done:
+    bs->b64 = acc;
+    bs->bits = (int32_t)fill;
+    return matches;
+}
+
+/* The same into a memory sink with room for the worst case (8 bytes a token).  The stream is
+ * big-endian 64-bit words of bits entered first-bit-highest (bitstream.h:28-47), i.e. a byte
+ * stream with the first bit in the top of the first byte: the bits of a whole token -- code,
+ * length bits, distance code, distance bits, at most 56 -- are put together from the two table
+ * words, joined to the pending bits, stored as eight bytes, and the write position moves on by
+ * the whole bytes among them.  No branch depends on the data except the rare one to the general
+ * way.  Returns the index it stopped at (`until`, or the token that has to go the general way);
+ * *pending / *pending_bits: the bits not yet part of a whole byte, at the top of the register.
+ * A function of its own so that its few loop variables stay in registers.                      */
+static __attribute__((noinline))
+uint64_t emit_bytes(const uint32_t* words, uint64_t from, uint64_t until, const struct code_tables* ct,
+                    uint8_t** at_, uint64_t* pending, uint32_t* pending_bits, uint64_t* matches_) {
+    const uint64_t* const lit_word = ct->lit_word;
+    const uint64_t* const pos_word = ct->pos_word;
+    uint8_t* at = *at_;
+    uint64_t acc = *pending;
+    uint32_t fill = *pending_bits;
+    uint64_t matches = 0;
+    uint64_t k = from;
+    for (; k < until; k++) {
+        const uint32_t w = words[k];
+        const uint32_t match = (w >> 8) & 1;                     /* bit 8 of the symbol: a length */
+        const uint64_t e = lit_word[w & 0x1FF];
+        const uint64_t p = pos_word[((w >> 14) & 31) | ((~w >> 3) & 32)];
+        /* general way: no table word; bucket 27 with all extra bits set (length 258, squeeze.h:529-545) */
+        if (__builtin_expect((e == 0) | (match & (p == 0)) | ((w & 0x3FFF) == (len_symbol0 + 27 + (31u << 9))), 0)) {
+            break;
+        }
+        const uint32_t n = ((uint32_t)e & 0xFF) + ((uint32_t)p & 0xFF);
+        uint64_t v = (e >> 8) | ((w >> 9) & 31);
+        v = (v << (p & 0xFF)) | (p >> 8) | (w >> 19);
+        fill += n;
+        acc |= v << (64 - fill);
+        const uint64_t be = __builtin_bswap64(acc);
+        memcpy(at, &be, 8);
+        at += fill >> 3;
+        acc <<= fill & 56;
+        fill &= 7;
+        matches += match;
+    }
+    *at_ = at;
+    *pending = acc;
+    *pending_bits = fill;
+    *matches_ += matches;
+    return k;
+}
+
+static uint64_t emit_run(struct sqz* s, struct sqz_bitstream* bs, const uint32_t* words, uint64_t from, uint64_t until,
+                         const struct code_tables* ct) {
+    uint64_t matches = 0;
+    while (from < until && s->error == 0) {
+        if (bs->data == NULL || bs->capacity < bs->bytes || bs->bits < 0 || bs->bits > 63 ||
+            (bs->capacity - bs->bytes) / 8 < until - from + 3) {
+            return matches + emit_run_anywhere(s, bs, words, from, until, ct);
+        }
+        uint8_t* const start = bs->data + bs->bytes;
+        uint8_t* at = start;
+        uint32_t fill = (uint32_t)bs->bits;                      /* pending bits, kept at the top of acc */
+        uint64_t acc = fill == 0 ? 0 : bs->b64 << (64 - fill);
+        const uint64_t be = __builtin_bswap64(acc);
+        memcpy(at, &be, 8);
+        at += fill >> 3;
+        acc <<= fill & 56;
+        fill &= 7;
+        from = emit_bytes(words, from, until, ct, &at, &acc, &fill, &matches);
+        /* back to whole words in memory + the rest in the register */
+        const size_t bytes_out = (size_t)(at - start);
+        const size_t whole = bytes_out & ~(size_t)7;
+        uint64_t rest = 0;
+        for (size_t j = whole; j < bytes_out; j++) { rest = rest << 8 | start[j]; }
+        bs->bytes += whole;
+        bs->b64 = fill == 0 ? rest : (rest << fill) | (acc >> (64 - fill));
+        bs->bits = (int32_t)(8 * (bytes_out - whole) + fill);
+        if (from < until) {
+            matches += emit_run_anywhere(s, bs, words, from, from + 1, ct);
+            from++;
+        }
+    }
+    return matches;
+}
+
+/* The words [from, until) one by one: emit with the current code, count, next (the reference's
+ * order, squeeze.h:239-246); everything unusual (first occurrence of a symbol, callback sinks, a
+ * full buffer) goes through the general functions above with the register synced.              */
+static uint64_t code_one_by_one(struct sqz* s, const uint32_t* words, uint64_t from, uint64_t until) {
+    struct sqz_bitstream* const bs = s->bs;
+    struct sqz_tree* const lit = &s->lit;
+    struct sqz_tree* const pos = &s->pos;
+    uint64_t acc = bs->b64;
+    uint32_t fill = (uint32_t)bs->bits;
+    uint64_t matches = 0;
+#define SQZ_SYNC_OUT()  do { bs->b64 = acc; bs->bits = (int32_t)fill; } while (0)
+#define SQZ_SYNC_IN()   do { acc = bs->b64; fill = (uint32_t)bs->bits; } while (0)
+    for (uint64_t k = from; k < until; k++) {
         const uint32_t w = words[k];
         const uint32_t sym = w & 0x1FF;
         if (!word_is_valid(w)) {
-            s->error = EINVAL;                       /* not a symbol word: the decoder would reject it */
+            s->error = EINVAL;
             goto done;
         }
         if (lit->bits[sym] == 0) {                   /* first occurrence: escape + raw symbol */
@@ -784,7 +1133,7 @@ static void code_symbols(struct sqz* s, const uint32_t* words, uint64_t count) {
             tree_count_as(lit, (int32_t)sym, lit_plan);
             SQZ_CHECK(lit);
         }
-        if (sym >= len_symbol0) {                    /* length first, then distance: squeeze.h:379-380 */
+        if (sym >= len_symbol0) {
             const uint32_t pb = (w >> 14) & 31;
             SQZ_APPEND((w >> 9) & 31, len_extra[sym - len_symbol0]);
             if (pos->bits[pb] == 0) {
@@ -805,19 +1154,60 @@ static void code_symbols(struct sqz* s, const uint32_t* words, uint64_t count) {
     }
 done:
     SQZ_SYNC_OUT();
-    s->matches += matches;
-    s->tokens += count;
-#undef SQZ_APPEND
+    return matches;
 #undef SQZ_SYNC_IN
 #undef SQZ_SYNC_OUT
+}
+
+/* How the two coders below walk a chunk: `reach` tokens at a time as a block while that works
+ * (doubling up to block_most), a quarter of it after a block that did not pass, one by one at
+ * the bottom.                                                                                   */
+static inline uint32_t block_span(const struct sqz_tree* lit, uint64_t left, uint32_t reach) {
+    uint64_t n = left < reach ? left : reach;
+    if ((int64_t)n > lit->lazy) { n = lit->lazy > 0 ? (uint64_t)lit->lazy : 0; }
+    return (uint32_t)n;
+}
+
+/* The coder proper, one thread. */
+static void code_symbols(struct sqz* s, const uint32_t* words, uint64_t count) {
+    struct sqz_bitstream* const bs = s->bs;
+    struct tally y;
+    struct code_tables ct;              /* kept current by relabel through the trees' watcher */
+    struct watch eyes = { &ct, NULL };
+    uint32_t reach = block_most;
+    uint64_t matches = 0, k = 0;
+    if (s->error != 0) { return; }
+    tally_init(&y);
+    tables_from_trees(&ct, s);
+    s->lit.watcher = s->pos.watcher = &eyes;
+    while (k < count && s->error == 0) {
+        const uint32_t n = block_span(&s->lit, count - k, reach);
+        if (n >= block_least) {
+            if (count_block(s, &y, words + k, n)) {
+                /* no code changed while the block was counted: its bits are those of the codes as they are */
+                matches += emit_run(s, bs, words, k, k + n, &ct);
+                k += n;
+                reach = 2 * n < block_most ? 2 * n : block_most;
+                continue;
+            }
+            if (n >= 4 * block_least) { reach = n / 4; continue; }
+        }
+        const uint64_t stretch = n >= block_least ? n : (count - k < block_least ? count - k : block_least);
+        matches += code_one_by_one(s, words, k, k + stretch);
+        k += stretch;
+    }
+    s->lit.watcher = s->pos.watcher = NULL;
+    s->matches += matches;
+    s->tokens += count;
 }
 
 /* plain tokens (literal byte or (len << 16) | dist): checked, turned into symbol
  * words a block at a time, coded                                             */
 static void code_tokens(struct sqz* s, const uint32_t* tokens, uint64_t count) {
-    uint32_t words[1024];
-    for (uint64_t at = 0; at < count && s->error == 0; at += 1024) {
-        const uint64_t n = count - at < 1024 ? count - at : 1024;
+    enum { portion = 8 * block_most };   /* several blocks per call of the coder */
+    uint32_t words[portion];
+    for (uint64_t at = 0; at < count && s->error == 0; at += portion) {
+        const uint64_t n = count - at < portion ? count - at : portion;
         uint64_t good = 0;
         while (good < n && token_is_valid(tokens[at + good])) {
             words[good] = symbols_of_token(s, tokens[at + good]);
@@ -832,23 +1222,23 @@ static void code_tokens(struct sqz* s, const uint32_t* tokens, uint64_t count) {
  *  the coder on two threads                                                 *
  *  What is serial about the adaptive coder is the model: every symbol       *
  *  changes the weights the next one is judged by.  Turning a symbol into    *
- *  bits only needs the code table, and that changes about once per 2700     *
- *  symbols.  So the model of the literal/length tree runs ahead on a thread *
- *  of its own (walks, exact reorderings, insertions -- no output) and notes *
+ *  bits only needs the code tables, and those change about once per 2700    *
+ *  symbols.  So the model of both trees runs ahead on a thread of its own   *
+ *  (blocks, walks, exact reorderings, insertions -- no output) and notes    *
  *  every change of a code in a log, stamped with the index of the first     *
  *  token it applies to; the calling thread follows, keeps its own copy of   *
- *  that code table current from the log, packs the bits and models the      *
- *  small distance tree itself.  Same bytes as code_symbols, by              *
+ *  the code tables current from the log and packs the bits, from one change *
+ *  of a code to the next in one go.  Same bytes as code_symbols, by         *
  *  construction: token k is emitted with the codes as they were when the    *
  *  model reached token k.                                                   *
  * ======================================================================== */
 
-struct change { uint64_t at; uint64_t code; uint16_t leaf; uint8_t bits; };
+struct change { uint64_t at; uint64_t code; uint16_t leaf; uint8_t bits; };   /* leaf | pos_leaf: the distance tree's */
 
 #ifndef SQZ_LOG_SIZE
 #define SQZ_LOG_SIZE (1 << 16)        /* a power of two; tests build with a tiny one */
 #endif
-enum { log_size = SQZ_LOG_SIZE, publish_every = 256, duo_least = 1 << 16 };
+enum { log_size = SQZ_LOG_SIZE, duo_least = 1 << 16, pos_leaf = 0x8000 };
 
 struct duo {                            /* one cache line per writer: the two threads never share a dirty line */
     struct sqz* s;
@@ -859,7 +1249,7 @@ struct duo {                            /* one cache line per writer: the two th
     _Atomic uint64_t chunks;            /* chunks handed over so far */
     _Atomic int finish;                 /* no more chunks */
     _Alignas(64) _Atomic uint64_t log_head;   /* changes consumed */
-    /* written by the model (every 256 tokens), read by the emitter */
+    /* written by the model (after every block or one-by-one stretch), read by the emitter */
     _Alignas(64) _Atomic uint64_t modelled;   /* tokens of the current chunk the model is done with */
     _Atomic uint64_t log_tail;          /* changes written */
     int model_error;
@@ -874,8 +1264,8 @@ struct duo {                            /* one cache line per writer: the two th
     _Alignas(64) struct change* early;
     size_t early_count, early_room, early_next;
 
-    uint64_t lit_code[sqz_lit_symbols];
-    uint8_t lit_bits[sqz_lit_symbols];
+    struct watch eyes;
+    struct code_tables tables;
     struct change log[log_size];
 };
 
@@ -898,7 +1288,12 @@ static inline void spin_wait(unsigned* spins) {
 }
 
 static void note_change(struct sqz_tree* t, int32_t leaf) {
-    struct duo* d = (struct duo*)t->watcher;
+    const struct watch* const eyes = (const struct watch*)t->watcher;
+    if (eyes->tables != NULL) {
+        tables_set(eyes->tables, t->n == sqz_pos_symbols, (uint32_t)leaf, t->code[leaf], t->bits[leaf]);
+        return;
+    }
+    struct duo* d = eyes->d;
     const uint64_t tail = atomic_load_explicit(&d->log_tail, memory_order_relaxed);
     unsigned spins = 0;
     while (tail - atomic_load_explicit(&d->log_head, memory_order_acquire) >= log_size) {
@@ -910,7 +1305,7 @@ static void note_change(struct sqz_tree* t, int32_t leaf) {
     struct change* c = &d->log[tail & (log_size - 1)];
     c->at = d->now;
     c->code = t->code[leaf];
-    c->leaf = (uint16_t)leaf;
+    c->leaf = (uint16_t)(t->n == sqz_pos_symbols ? leaf | pos_leaf : leaf);
     c->bits = t->bits[leaf];
     atomic_store_explicit(&d->log_tail, tail + 1, memory_order_release);
 }
@@ -918,9 +1313,13 @@ static void note_change(struct sqz_tree* t, int32_t leaf) {
 
 static void* model_main(void* arg) {
     struct duo* d = (struct duo*)arg;
-    struct sqz_tree* const lit = &d->s->lit;      /* the distance tree belongs to the emitting thread */
+    struct sqz* const s = d->s;
+    struct sqz_tree* const lit = &s->lit;
+    struct sqz_tree* const pos = &s->pos;
+    struct tally y;
     uint64_t seen = 0;
     unsigned spins = 0;
+    tally_init(&y);
     for (;;) {
         while (atomic_load_explicit(&d->chunks, memory_order_acquire) == seen) {
             if (atomic_load_explicit(&d->finish, memory_order_acquire) ||
@@ -928,43 +1327,68 @@ static void* model_main(void* arg) {
             spin_wait(&spins);
         }
         seen++;
+        spins = 0;
         const uint32_t* const words = d->words;
         const uint64_t count = d->count;
+        uint32_t reach = block_most;
+        uint64_t k = 0;
         d->model_base = d->base;
-        for (uint64_t k = 0; k < count; k++) {
-            if ((k & (publish_every - 1)) == 0) {
-                atomic_store_explicit(&d->modelled, k, memory_order_release);
-                if (atomic_load_explicit(&d->stop, memory_order_relaxed)) { return NULL; }
+        while (k < count) {
+            atomic_store_explicit(&d->modelled, k, memory_order_release);
+            if (atomic_load_explicit(&d->stop, memory_order_relaxed)) { return NULL; }
+            const uint32_t n = block_span(lit, count - k, reach);
+            if (n >= block_least) {
+                if (count_block(s, &y, words + k, n)) {          /* no code changes: nothing to log */
+                    k += n;
+                    reach = 2 * n < block_most ? 2 * n : block_most;
+                    continue;
+                }
+                if (n >= 4 * block_least) { reach = n / 4; continue; }
             }
-            const uint32_t w = words[k];
-            const uint32_t sym = w & 0x1FF;
-            d->k_now = k;
-            d->now = d->model_base + k + 1;
-            if (!word_is_valid(w)) {                 /* the emitter reports it when it gets there */
-                atomic_store_explicit(&d->modelled, k + 1, memory_order_release);
-                return NULL;
-            }
-            if (lit->bits[sym] == 0) {               /* squeeze.h:278-288: escape, then the new symbol */
-                tree_count(lit, sqz_lit_nyt);
-                if (!tree_insert(lit, (int32_t)sym)) { d->model_error = E2BIG; }
-            } else {
-                tree_count_as(lit, (int32_t)sym, lit_plan);
-            }
-            if (d->model_error != 0) {
-                atomic_store_explicit(&d->stop, 1, memory_order_release);
-                return NULL;
+            const uint64_t until = k + (n >= block_least ? n : (count - k < block_least ? count - k : block_least));
+            for (; k < until; k++) {
+                const uint32_t w = words[k];
+                const uint32_t sym = w & 0x1FF;
+                d->k_now = k;
+                d->now = d->model_base + k + 1;
+                if (!word_is_valid(w)) {                 /* the emitter reports it when it gets there */
+                    atomic_store_explicit(&d->modelled, k + 1, memory_order_release);
+                    return NULL;
+                }
+                if (lit->bits[sym] == 0) {               /* squeeze.h:278-288: escape, then the new symbol */
+                    tree_count(lit, sqz_lit_nyt);
+                    if (!tree_insert(lit, (int32_t)sym)) { d->model_error = E2BIG; }
+                } else {
+                    tree_count_as(lit, (int32_t)sym, lit_plan);
+                    SQZ_CHECK(lit);
+                }
+                if (sym >= len_symbol0 && d->model_error == 0) {
+                    const uint32_t pb = (w >> 14) & 31;
+                    if (pos->bits[pb] == 0) {            /* squeeze.h:300-315 */
+                        tree_count(pos, sqz_pos_nyt);
+                        if (!tree_insert(pos, (int32_t)pb)) { d->model_error = E2BIG; }
+                    } else {
+                        tree_count_as(pos, (int32_t)pb, pos_plan);
+                        SQZ_CHECK(pos);
+                    }
+                }
+                if (d->model_error != 0) {
+                    atomic_store_explicit(&d->stop, 1, memory_order_release);
+                    return NULL;
+                }
             }
         }
         atomic_store_explicit(&d->modelled, count, memory_order_release);
     }
 }
 
+static inline void take_change(struct duo* d, const struct change* c) {
+    tables_set(&d->tables, (c->leaf & pos_leaf) != 0, c->leaf & (pos_leaf - 1u), c->code, c->bits);
+}
+
 /* the emitter's half of one chunk */
 static void duo_emit(struct sqz* s, struct duo* d, const uint32_t* words, uint64_t count) {
     struct sqz_bitstream* const bs = s->bs;
-    struct sqz_tree* const pos = &s->pos;           /* small and touched by every sixth token: modelled here */
-    uint64_t acc = bs->b64;
-    uint32_t fill = (uint32_t)bs->bits;
     uint64_t matches = 0;
     uint64_t head = atomic_load_explicit(&d->log_head, memory_order_relaxed);
     uint64_t tail = atomic_load_explicit(&d->log_tail, memory_order_acquire);
@@ -976,27 +1400,8 @@ static void duo_emit(struct sqz* s, struct duo* d, const uint32_t* words, uint64
     atomic_store_explicit(&d->modelled, 0, memory_order_relaxed);
     atomic_fetch_add_explicit(&d->chunks, 1, memory_order_release);
 
-#define DUO_APPEND(seq_, count_) do {                                            \
-        const uint64_t q_ = (seq_); const uint32_t c_ = (count_);                \
-        const uint32_t f_ = fill + c_;                                           \
-        if (f_ < 64) { acc = (acc << c_) | q_; fill = f_; }                      \
-        else {                                                                   \
-            const uint32_t rest_ = f_ - 64;                                      \
-            const uint64_t word_ = (fill == 0 ? 0 : acc << (64 - fill)) | (q_ >> rest_); \
-            if (bs->data != NULL && bs->capacity - bs->bytes >= 8 && bs->capacity >= bs->bytes) { \
-                const uint64_t be_ = __builtin_bswap64(word_);                   \
-                memcpy(bs->data + bs->bytes, &be_, 8);                           \
-                bs->bytes += 8;                                                  \
-            } else {                                                             \
-                bs->b64 = word_; bs->bits = 64;                                  \
-                word_out(bs);                                                    \
-                if (bs->error != 0) { s->error = bs->error; goto done; }         \
-            }                                                                    \
-            acc = rest_ == 0 ? 0 : (q_ & (((uint64_t)1 << rest_) - 1));          \
-            fill = rest_;                                                        \
-        } } while (0)
-
-    for (uint64_t k = 0; k < count; k++) {
+    uint64_t k = 0;
+    while (k < count) {
         if (k >= avail) {                            /* wait for the model to be past this token */
             for (;;) {
                 avail = atomic_load_explicit(&d->modelled, memory_order_acquire);
@@ -1022,56 +1427,38 @@ static void duo_emit(struct sqz* s, struct duo* d, const uint32_t* words, uint64
                 atomic_store_explicit(&d->log_head, head, memory_order_release);   /* everything is taken */
                 spin_wait(&spins);
             }
+            spins = 0;
+            /* everything the model logged for tokens below `avail` is visible from here on */
             tail = atomic_load_explicit(&d->log_tail, memory_order_acquire);
         }
         /* code changes made by tokens before this one: those set aside first, they are older */
         const uint64_t stamp = base + k;
         while (d->early_next != d->early_count && d->early[d->early_next].at <= stamp) {
-            const struct change* c = &d->early[d->early_next++];
-            d->lit_code[c->leaf] = c->code;
-            d->lit_bits[c->leaf] = c->bits;
+            take_change(d, &d->early[d->early_next++]);
         }
         while (d->early_next == d->early_count && head != tail && d->log[head & (log_size - 1)].at <= stamp) {
-            const struct change* c = &d->log[head & (log_size - 1)];
-            d->lit_code[c->leaf] = c->code;
-            d->lit_bits[c->leaf] = c->bits;
+            take_change(d, &d->log[head & (log_size - 1)]);
             head++;
             if ((head & 1023) == 0) { atomic_store_explicit(&d->log_head, head, memory_order_release); }
         }
-        const uint32_t w = words[k];
-        const uint32_t sym = w & 0x1FF;
-        if (!word_is_valid(w)) { s->error = EINVAL; goto done; }
-        if (d->lit_bits[sym] == 0) {                 /* first occurrence: escape, then 9 raw bits */
-            DUO_APPEND(d->lit_code[sqz_lit_nyt], d->lit_bits[sqz_lit_nyt]);
-            DUO_APPEND(reverse_field(sym, 9), 9);
-        } else {
-            DUO_APPEND(d->lit_code[sym], d->lit_bits[sym]);
+        /* the tables hold until the next change is due (it applies from token `at - base` on) or the
+         * model's progress ends */
+        uint64_t until = avail < count ? avail : count;
+        if (d->early_next != d->early_count) {
+            if (d->early[d->early_next].at - base < until) { until = d->early[d->early_next].at - base; }
+        } else if (head != tail) {
+            if (d->log[head & (log_size - 1)].at - base < until) { until = d->log[head & (log_size - 1)].at - base; }
         }
-        if (sym >= len_symbol0) {                    /* length first, then distance: squeeze.h:379-380 */
-            const uint32_t pb = (w >> 14) & 31;
-            DUO_APPEND((w >> 9) & 31, len_extra[sym - len_symbol0]);
-            if (pos->bits[pb] == 0) {                /* squeeze.h:300-315: escape, 5 raw bits, new symbol */
-                DUO_APPEND(pos->code[sqz_pos_nyt], pos->bits[sqz_pos_nyt]);
-                tree_count(pos, sqz_pos_nyt);
-                DUO_APPEND(reverse_field(pb, 5), 5);
-                if (!tree_insert(pos, (int32_t)pb)) { s->error = E2BIG; goto done; }
-            } else {
-                DUO_APPEND(pos->code[pb], pos->bits[pb]);
-                tree_count_as(pos, (int32_t)pb, pos_plan);
-            }
-            DUO_APPEND(w >> 19, pos_extra[pb]);
-            matches++;
-        }
+        matches += emit_run(s, bs, words, k, until, &d->tables);
+        if (s->error != 0) { goto done; }
+        k = until;
     }
 done:
     atomic_store_explicit(&d->log_head, head, memory_order_release);
     if (s->error != 0) { atomic_store_explicit(&d->stop, 1, memory_order_release); }
-    bs->b64 = acc;
-    bs->bits = (int32_t)fill;
     d->base = base + count;
     s->matches += matches;
     s->tokens += count;
-#undef DUO_APPEND
 }
 
 struct duo_run { struct duo* d; pthread_t model; };
@@ -1084,11 +1471,12 @@ static int duo_start(struct sqz* s, struct duo_run* run, uint64_t expected_token
     if (d == NULL) { return 0; }                    /* no memory for the log: one thread will do */
     memset(d, 0, sizeof(struct duo));
     d->s = s;
-    memcpy(d->lit_code, s->lit.code, sizeof(d->lit_code));
-    memcpy(d->lit_bits, s->lit.bits, sizeof(d->lit_bits));
-    s->lit.watcher = d;
+    tables_from_trees(&d->tables, s);
+    d->eyes.tables = NULL;
+    d->eyes.d = d;
+    s->lit.watcher = s->pos.watcher = &d->eyes;
     if (pthread_create(&run->model, NULL, model_main, d) != 0) {
-        s->lit.watcher = NULL;
+        s->lit.watcher = s->pos.watcher = NULL;
         free(d);
         return 0;
     }
@@ -1100,7 +1488,7 @@ static void duo_finish(struct sqz* s, struct duo_run* run) {
     if (run->d == NULL) { return; }
     atomic_store_explicit(&run->d->finish, 1, memory_order_release);
     pthread_join(run->model, NULL);
-    s->lit.watcher = NULL;
+    s->lit.watcher = s->pos.watcher = NULL;
     free(run->d->early);
     free(run->d);
     run->d = NULL;
