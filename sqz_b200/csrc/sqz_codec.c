@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <unistd.h>
 
 /* ---- deflate-style bucket tables (RFC 1951 3.2.5; reference squeeze.h:29-79) */
 static const uint16_t len_base[29] = {
@@ -169,8 +170,12 @@ enum { none = -1, no_node = 0xFFFF,
 static void note_change(struct sqz_tree* t, int32_t leaf);
 struct code_tables;
 struct duo;
-/* who is told when a leaf's code changes: the one-thread coder's tables, or the two-thread coder's log */
-struct watch { struct code_tables* tables; struct duo* d; };
+struct segment;
+/* who is told when a leaf's code changes: the one-thread coder's tables, the two-thread coder's ring
+ * of changes, or the segment the model of the several-thread coder is working on.  `now` is the
+ * stamp a change gets: index (within the stream or chunk) of the token being modelled, + 1 = the
+ * first token the new code applies to; `k_now` that token's index within the chunk.              */
+struct watch { struct code_tables* tables; struct duo* d; struct segment* seg; uint64_t now, k_now; int error; };
 
 static inline int32_t tree_root(const struct sqz_tree* t) { return 2 * t->n - 2; }
 static inline uint32_t always_node(const struct sqz_tree* t) { return 2 * (uint32_t)t->n - 1; } /* weight 0 */
@@ -655,24 +660,31 @@ static void tree_count(struct sqz_tree* t, int32_t s) {
  *  only ever errs towards the slow path.                                    *
  * ======================================================================== */
 
-#ifndef SQZ_BLOCK_MOST
-#define SQZ_BLOCK_MOST 2048
-#endif
-enum { block_most = SQZ_BLOCK_MOST,    /* tokens per block when all goes well */
+enum { part_tokens = 128,              /* tokens per part: the unit a block is tallied in and falls back to */
+       parts_most = 16,
+       block_most = part_tokens * parts_most,       /* tokens per block when all goes well */
+       mini_tokens = 32,               /* a part that does not pass is tallied again in four minis */
        block_least = 32 };             /* below this a block is not worth its snapshot */
 
+/* A block is tallied once, part by part; the counts of a span of parts are the sums of the parts'.
+ * When the whole block does not pass, its quarters are tried, then their parts, each from the
+ * tallies already made; only a part that does not pass is walked one by one.                    */
 struct tally {
-    uint16_t lit_count[sqz_lit_symbols];
-    uint16_t pos_count[sqz_pos_symbols + 8];       /* + slots a literal's "no distance" goes to, in turn */
-    uint16_t lit_seen[block_most];      /* distinct symbols in order of first appearance */
+    /* rows of 16-bit counters, 8-byte aligned: a span's counts are added four symbols at a time (no
+     * count reaches 2^16, so nothing carries from one into the next) */
+    _Alignas(8) uint16_t lit_part[parts_most][sqz_lit_symbols];
+    _Alignas(8) uint16_t pos_part[parts_most][sqz_pos_symbols + 8];   /* + slots a literal's "no distance" goes to, in turn */
+    _Alignas(8) uint16_t lit_count[sqz_lit_symbols];           /* the span being tried */
+    _Alignas(8) uint16_t pos_count[sqz_pos_symbols + 8];
+    uint16_t lit_seen[sqz_lit_symbols];            /* its distinct symbols */
     uint16_t pos_seen[sqz_pos_symbols];
-    uint64_t lit_start[2 * sqz_lit_symbols + 1];   /* weights as they were when the block began, and */
+    uint64_t lit_start[2 * sqz_lit_symbols + 1];   /* weights as they were when the span began, and */
     uint64_t pos_start[2 * sqz_pos_symbols + 1];   /* the comparators "always" (0) and "never" (2^63-1) */
 };
 
 static void tally_init(struct tally* y) {
-    memset(y->lit_count, 0, sizeof(y->lit_count));
-    memset(y->pos_count, 0, sizeof(y->pos_count));
+    memset(y->lit_part, 0, sizeof(y->lit_part));
+    memset(y->pos_part, 0, sizeof(y->pos_part));
     y->lit_start[2 * sqz_lit_symbols - 1] = 0;  y->lit_start[2 * sqz_lit_symbols] = (uint64_t)INT64_MAX;
     y->pos_start[2 * sqz_pos_symbols - 1] = 0;  y->pos_start[2 * sqz_pos_symbols] = (uint64_t)INT64_MAX;
 }
@@ -729,42 +741,57 @@ int tree_count_block(struct sqz_tree* t, const uint16_t* seen, uint32_t kinds, c
     return 1;
 }
 
-static inline void forget_tally(struct tally* y, uint32_t lit_kinds, uint32_t pos_kinds) {
-    for (uint32_t j = 0; j < lit_kinds; j++) { y->lit_count[y->lit_seen[j]] = 0; }
-    for (uint32_t j = 0; j < pos_kinds; j++) { y->pos_count[y->pos_seen[j]] = 0; }
-}
-
-/* count the symbols of the words [0, n); returns the number of distinct literal/length symbols */
+/* count the symbols of the words [0, n) into one part's tallies */
 static __attribute__((noinline))
-uint32_t tally_words(struct tally* y, const uint32_t* words, uint32_t n) {
-    uint16_t* const lit_count = y->lit_count;
-    uint16_t* const pos_count = y->pos_count;
-    uint16_t* const lit_seen = y->lit_seen;
-    uint32_t lit_kinds = 0;
+void tally_words(uint16_t* lit_count, uint16_t* pos_count, const uint32_t* words, uint32_t n) {
     for (uint32_t k = 0; k < n; k++) {
         const uint32_t w = words[k];
-        const uint32_t sym = w & 0x1FF, pb = (w >> 14) & 31;
-        /* a literal counts into one of eight idle slots: one slot would chain every literal's
-         * load-add-store to the one before */
-        const uint32_t idle = sqz_pos_symbols + (k & 7);
-        const uint32_t slot = sym >= len_symbol0 ? pb : idle;
-        const uint32_t c = lit_count[sym];
-        lit_seen[lit_kinds] = (uint16_t)sym;
-        lit_kinds += c == 0;
-        lit_count[sym] = (uint16_t)(c + 1);
+        /* a literal (bit 8 of the symbol clear; its distance field is 0) counts into one of eight idle
+         * slots instead: one slot would chain every literal's load-add-store to the one before.  No
+         * branch: which of the two a token is cannot be predicted */
+        const uint32_t slot = ((w >> 14) & 31) | ((0u - ((~w >> 8) & 1)) & (sqz_pos_symbols | (k & 7)));
+        lit_count[w & 0x1FF]++;
         pos_count[slot]++;
     }
-    return lit_kinds;
 }
 
-/* Model the symbol words [0, n) of both trees as one block.  1 = done; 0 = nothing changed.
- * n <= block_most.  Words that are no symbol words never pass (their symbol is not in the tree,
- * or is the escape) except for flaws the model does not look at -- the emitter reports those.   */
-static int count_block(struct sqz* s, struct tally* y, const uint32_t* words, uint32_t n) {
+/* The symbol words [0, n) -- parts [first, first + parts) of the block tallied in y -- on both trees
+ * as one span.  1 = done; 0 = nothing changed.  Words that are no symbol words never pass (their
+ * symbol is not in the tree, or is the escape) except for flaws the model does not look at -- the
+ * emitter reports those.                                                                        */
+#ifdef SQZ_STATS
+uint64_t st_tries[3], st_fails[3], st_one, st_kinds, st_t[4], st_lv[3][2][2], st_kl[3][2];
+#include <x86intrin.h>
+#endif
+static int count_span(struct sqz* s, struct tally* y, const uint32_t* words, uint32_t n,
+                      uint32_t first, uint32_t parts, uint64_t* matches_) {
+#ifdef SQZ_STATS
+    const int lv = parts > 4 ? 0 : parts > 1 ? 1 : 2; st_tries[lv]++; uint64_t t0 = __rdtsc();
+#endif
     struct sqz_tree* const lit = &s->lit;
     struct sqz_tree* const pos = &s->pos;
-    uint32_t pos_kinds = 0, matches = 0;
-    const uint32_t lit_kinds = tally_words(y, words, n);
+    uint32_t lit_kinds = 0, pos_kinds = 0, matches = 0, strays = 0;
+    /* four 16-bit counters per addition; the symbols in use end at the escape, the rest of a row only
+     * ever holds strays (symbols no tree has) */
+    enum { lit_quads = sqz_lit_symbols / 4, pos_quads = sqz_pos_symbols / 4 };
+    {
+        uint64_t* const ls = (uint64_t*)(void*)y->lit_count;
+        uint64_t* const ps = (uint64_t*)(void*)y->pos_count;
+        memcpy(ls, y->lit_part[first], sizeof(y->lit_count));
+        memcpy(ps, y->pos_part[first], sizeof(uint16_t) * sqz_pos_symbols);
+        for (uint32_t q = first + 1; q < first + parts; q++) {
+            const uint64_t* const lp = (const uint64_t*)(const void*)y->lit_part[q];
+            const uint64_t* const pp = (const uint64_t*)(const void*)y->pos_part[q];
+            for (uint32_t k = 0; k < lit_quads; k++) { ls[k] += lp[k]; }
+            for (uint32_t k = 0; k < pos_quads; k++) { ps[k] += pp[k]; }
+        }
+    }
+    for (uint32_t k = 0; k <= sqz_lit_nyt; k++) {
+        y->lit_seen[lit_kinds] = (uint16_t)k;
+        lit_kinds += y->lit_count[k] != 0;
+    }
+    for (uint32_t k = sqz_lit_nyt + 1; k < sqz_lit_symbols; k++) { strays |= y->lit_count[k]; }
+    if (strays != 0) { return 0; }                   /* symbols no tree has */
     for (uint32_t pb = 0; pb < sqz_pos_symbols; pb++) {
         y->pos_seen[pos_kinds] = (uint16_t)pb;
         pos_kinds += y->pos_count[pb] != 0;
@@ -773,6 +800,9 @@ static int count_block(struct sqz* s, struct tally* y, const uint32_t* words, ui
 #ifdef SQZ_SELFCHECK
     settle(lit); settle(pos);           /* so that the replay below starts from the very same weights */
 #endif
+#ifdef SQZ_STATS
+    st_kinds += lit_kinds; uint64_t t1 = __rdtsc(); st_t[0] += t1 - t0;
+#endif
     int ok = tree_count_block(pos, y->pos_seen, pos_kinds, y->pos_count, matches, y->pos_start,
                               pos_plan, sqz_pos_nyt);
     if (ok && !tree_count_block(lit, y->lit_seen, lit_kinds, y->lit_count, n, y->lit_start,
@@ -780,7 +810,10 @@ static int count_block(struct sqz* s, struct tally* y, const uint32_t* words, ui
         ok = 0;
         if (matches != 0) { restore_weights(pos, y->pos_start); pos->lazy += (int32_t)matches; }
     }
-    forget_tally(y, lit_kinds, pos_kinds);
+    if (ok) { *matches_ += matches; }
+#ifdef SQZ_STATS
+    { const uint64_t t2 = __rdtsc(); st_t[1] += t2 - t1; if (!ok) st_fails[lv]++; st_lv[lv][ok][0] += t1 - t0; st_lv[lv][ok][1] += t2 - t1; st_kl[lv][ok] += lit_kinds; }
+#endif
 #ifdef SQZ_SELFCHECK
     if (ok) {
         /* the same symbols one by one from the same start: no reordering, the same weights */
@@ -802,11 +835,13 @@ static int count_block(struct sqz* s, struct tally* y, const uint32_t* words, ui
         if (shape != selfcheck_relabels ||
             memcmp(lit_after, lit->freq, sizeof(uint64_t) * (size_t)(2 * lit->n - 2)) != 0 ||
             memcmp(pos_after, pos->freq, sizeof(uint64_t) * (size_t)(2 * pos->n - 2)) != 0) {
-            fprintf(stderr, "sqz selfcheck: a block of %u symbols differs from the same symbols one by one\n", n);
+            fprintf(stderr, "sqz selfcheck: a span of %u symbols differs from the same symbols one by one\n", n);
             abort();
         }
         selfcheck(lit); selfcheck(pos);
     }
+#else
+    (void)words;
 #endif
     return ok;
 }
@@ -930,7 +965,7 @@ static inline int word_is_valid(uint32_t w) {
             } else {                                                             \
                 bs->b64 = word_; bs->bits = 64;                                  \
                 word_out(bs);                                                    \
-                if (bs->error != 0) { s->error = bs->error; goto done; }         \
+                if (bs->error != 0) { *err = bs->error; goto done; }             \
             }                                                                    \
             acc = rest_ == 0 ? 0 : (q_ & (((uint64_t)1 << rest_) - 1));          \
             fill = rest_;                                                        \
@@ -984,18 +1019,17 @@ static void tables_from_trees(struct code_tables* ct, const struct sqz* s) {
 /* Emit the words [from, until) with code tables that do not change on the way (a block the model
  * took as a whole, or the stretch between two changes of a code in the two-thread coder).  A
  * symbol without a code yet goes out as the escape plus its raw bits (squeeze.h:278-288, 300-315:
- * only the two-thread coder gets here with one, its model inserts the symbol).  Returns the
- * number of matches; on an error s->error is set and the rest is not emitted.                   */
-static uint64_t emit_run_anywhere(struct sqz* s, struct sqz_bitstream* bs, const uint32_t* words,
-                                  uint64_t from, uint64_t until, const struct code_tables* ct) {
+ * only the coders on several threads get here with one, their model inserts the symbol).  On an
+ * error *err is set and the rest is not emitted.                                                */
+static void emit_run_anywhere(int32_t* err, struct sqz_bitstream* bs, const uint32_t* words,
+                              uint64_t from, uint64_t until, const struct code_tables* ct) {
     uint64_t acc = bs->b64;
     uint32_t fill = (uint32_t)bs->bits;
-    uint64_t matches = 0;
     for (uint64_t k = from; k < until; k++) {
         const uint32_t w = words[k];
         const uint32_t sym = w & 0x1FF;
         if (!word_is_valid(w)) {                     /* not a symbol word: the decoder would reject it */
-            s->error = EINVAL;
+            *err = EINVAL;
             goto done;
         }
         if (ct->lit_bits[sym] == 0) {
@@ -1014,13 +1048,11 @@ static uint64_t emit_run_anywhere(struct sqz* s, struct sqz_bitstream* bs, const
                 SQZ_APPEND(ct->pos_code[pb], ct->pos_bits[pb]);
             }
             SQZ_APPEND(w >> 19, pos_extra[pb]);
-            matches++;
         }
     }
 done:
     bs->b64 = acc;
     bs->bits = (int32_t)fill;
-    return matches;
 }
 
 /* The same into a memory sink with room for the worst case (8 bytes a token).  The stream is
@@ -1034,13 +1066,12 @@ done:
  * A function of its own so that its few loop variables stay in registers.                      */
 static __attribute__((noinline))
 uint64_t emit_bytes(const uint32_t* words, uint64_t from, uint64_t until, const struct code_tables* ct,
-                    uint8_t** at_, uint64_t* pending, uint32_t* pending_bits, uint64_t* matches_) {
+                    uint8_t** at_, uint64_t* pending, uint32_t* pending_bits) {
     const uint64_t* const lit_word = ct->lit_word;
     const uint64_t* const pos_word = ct->pos_word;
     uint8_t* at = *at_;
     uint64_t acc = *pending;
     uint32_t fill = *pending_bits;
-    uint64_t matches = 0;
     uint64_t k = from;
     for (; k < until; k++) {
         const uint32_t w = words[k];
@@ -1061,22 +1092,20 @@ uint64_t emit_bytes(const uint32_t* words, uint64_t from, uint64_t until, const 
         at += fill >> 3;
         acc <<= fill & 56;
         fill &= 7;
-        matches += match;
     }
     *at_ = at;
     *pending = acc;
     *pending_bits = fill;
-    *matches_ += matches;
     return k;
 }
 
-static uint64_t emit_run(struct sqz* s, struct sqz_bitstream* bs, const uint32_t* words, uint64_t from, uint64_t until,
-                         const struct code_tables* ct) {
-    uint64_t matches = 0;
-    while (from < until && s->error == 0) {
+static void emit_run(int32_t* err, struct sqz_bitstream* bs, const uint32_t* words, uint64_t from, uint64_t until,
+                     const struct code_tables* ct) {
+    while (from < until && *err == 0) {
         if (bs->data == NULL || bs->capacity < bs->bytes || bs->bits < 0 || bs->bits > 63 ||
             (bs->capacity - bs->bytes) / 8 < until - from + 3) {
-            return matches + emit_run_anywhere(s, bs, words, from, until, ct);
+            emit_run_anywhere(err, bs, words, from, until, ct);
+            return;
         }
         uint8_t* const start = bs->data + bs->bytes;
         uint8_t* at = start;
@@ -1087,7 +1116,7 @@ static uint64_t emit_run(struct sqz* s, struct sqz_bitstream* bs, const uint32_t
         at += fill >> 3;
         acc <<= fill & 56;
         fill &= 7;
-        from = emit_bytes(words, from, until, ct, &at, &acc, &fill, &matches);
+        from = emit_bytes(words, from, until, ct, &at, &acc, &fill);
         /* back to whole words in memory + the rest in the register */
         const size_t bytes_out = (size_t)(at - start);
         const size_t whole = bytes_out & ~(size_t)7;
@@ -1097,11 +1126,10 @@ static uint64_t emit_run(struct sqz* s, struct sqz_bitstream* bs, const uint32_t
         bs->b64 = fill == 0 ? rest : (rest << fill) | (acc >> (64 - fill));
         bs->bits = (int32_t)(8 * (bytes_out - whole) + fill);
         if (from < until) {
-            matches += emit_run_anywhere(s, bs, words, from, from + 1, ct);
+            emit_run_anywhere(err, bs, words, from, from + 1, ct);
             from++;
         }
     }
-    return matches;
 }
 
 /* The words [from, until) one by one: emit with the current code, count, next (the reference's
@@ -1111,6 +1139,7 @@ static uint64_t code_one_by_one(struct sqz* s, const uint32_t* words, uint64_t f
     struct sqz_bitstream* const bs = s->bs;
     struct sqz_tree* const lit = &s->lit;
     struct sqz_tree* const pos = &s->pos;
+    int32_t* const err = &s->error;
     uint64_t acc = bs->b64;
     uint32_t fill = (uint32_t)bs->bits;
     uint64_t matches = 0;
@@ -1159,45 +1188,137 @@ done:
 #undef SQZ_SYNC_OUT
 }
 
-/* How the two coders below walk a chunk: `reach` tokens at a time as a block while that works
- * (doubling up to block_most), a quarter of it after a block that did not pass, one by one at
- * the bottom.                                                                                   */
-static inline uint32_t block_span(const struct sqz_tree* lit, uint64_t left, uint32_t reach) {
-    uint64_t n = left < reach ? left : reach;
+/* One pass over a chunk of symbol words, by one thread: model and emit (`ct` set: the one-thread
+ * coder), or model only (the model thread of the coders on several threads).                     */
+struct pass {
+    struct sqz* s;
+    struct tally* y;
+    struct watch* eyes;
+    const uint32_t* words;              /* the chunk */
+    uint64_t base;                      /* stamp of words[0] */
+    struct code_tables* ct;             /* NULL: model only */
+    uint64_t matches;
+    int flaw;                           /* model only: stopped at a word that is no symbol word */
+};
+
+/* the model alone over [k, until), one by one; returns where it stopped (`until`; or earlier with
+ * p->flaw at a word that is no symbol word, not modelled, or with eyes->error set) */
+static uint64_t model_one_by_one(struct pass* p, uint64_t k, uint64_t until) {
+    struct sqz_tree* const lit = &p->s->lit;
+    struct sqz_tree* const pos = &p->s->pos;
+    struct watch* const eyes = p->eyes;
+    for (; k < until; k++) {
+        const uint32_t w = p->words[k];
+        const uint32_t sym = w & 0x1FF;
+        eyes->k_now = k;
+        eyes->now = p->base + k + 1;
+        if (!word_is_valid(w)) {
+            p->flaw = 1;
+            return k;
+        }
+        if (lit->bits[sym] == 0) {               /* squeeze.h:278-288: escape, then the new symbol */
+            tree_count(lit, sqz_lit_nyt);
+            if (!tree_insert(lit, (int32_t)sym)) { eyes->error = E2BIG; }
+        } else {
+            tree_count_as(lit, (int32_t)sym, lit_plan);
+            SQZ_CHECK(lit);
+        }
+        if (sym >= len_symbol0 && eyes->error == 0) {
+            const uint32_t pb = (w >> 14) & 31;
+            if (pos->bits[pb] == 0) {            /* squeeze.h:300-315 */
+                tree_count(pos, sqz_pos_nyt);
+                if (!tree_insert(pos, (int32_t)pb)) { eyes->error = E2BIG; }
+            } else {
+                tree_count_as(pos, (int32_t)pb, pos_plan);
+                SQZ_CHECK(pos);
+            }
+            p->matches++;
+        }
+        if (eyes->error != 0) { return k; }
+    }
+    return k;
+}
+
+/* [k, until) one by one; 1 = go on, 0 = stop (an error, a flaw) */
+static int pass_one_by_one(struct pass* p, uint64_t k, uint64_t until) {
+#ifdef SQZ_STATS
+    st_one += until - k; const uint64_t t0_ = __rdtsc();
+    const int r_ = p->ct != NULL ? (p->matches += code_one_by_one(p->s, p->words, k, until), p->s->error == 0) : model_one_by_one(p, k, until) == until;
+    st_t[2] += __rdtsc() - t0_; return r_;
+#endif
+    if (p->ct != NULL) {
+        p->matches += code_one_by_one(p->s, p->words, k, until);
+        return p->s->error == 0;
+    }
+    return model_one_by_one(p, k, until) == until;
+}
+
+/* The tokens [k, k + n) = parts [first, first + parts) of the tallied block: as one span if that
+ * passes, else its quarters, else its parts, else one by one.  1 = go on, 0 = stop.             */
+static int pass_span(struct pass* p, uint64_t k, uint32_t n, uint32_t first, uint32_t parts) {
+    if (count_span(p->s, p->y, p->words + k, n, first, parts, &p->matches)) {
+        if (p->ct != NULL) {
+            /* no code changed while the span was counted: its bits are those of the codes as they are */
+            emit_run(&p->s->error, p->s->bs, p->words, k, k + n, p->ct);
+            return p->s->error == 0;
+        }
+        return 1;
+    }
+    if (parts == 1) { return pass_one_by_one(p, k, k + n); }
+    const uint32_t step = parts > 4 ? 4 : 1;
+    for (uint32_t q = 0; q < parts; q += step) {
+        const uint32_t some = parts - q < step ? parts - q : step;
+        const uint32_t from = q * part_tokens;
+        const uint32_t to = (q + some) * part_tokens < n ? (q + some) * part_tokens : n;
+        if (!pass_span(p, k + from, to - from, first + q, some)) { return 0; }
+    }
+    return 1;
+}
+
+/* the next block of the chunk, at most up to `until`; returns the tokens dealt with (fewer than it
+ * took on when something stopped the pass: p->flaw, p->eyes->error, p->s->error) */
+static uint64_t pass_block(struct pass* p, uint64_t k, uint64_t until) {
+    struct tally* const y = p->y;
+    const struct sqz_tree* const lit = &p->s->lit;
+    uint64_t n = until - k < block_most ? until - k : block_most;
     if ((int64_t)n > lit->lazy) { n = lit->lazy > 0 ? (uint64_t)lit->lazy : 0; }
-    return (uint32_t)n;
+    if (n < block_least) {              /* no lazy stretch is on (or it ends): the one-by-one path renews it */
+        n = until - k < block_least ? until - k : block_least;
+        if (p->ct != NULL) {
+            p->matches += code_one_by_one(p->s, p->words, k, k + n);
+            return n;
+        }
+        return model_one_by_one(p, k, k + n) - k;
+    }
+    const uint32_t parts = (uint32_t)((n + part_tokens - 1) / part_tokens);
+    for (uint32_t q = 0; q < parts; q++) {
+        const uint64_t from = k + (uint64_t)q * part_tokens;
+        const uint64_t to = from + part_tokens < k + n ? from + part_tokens : k + n;
+        tally_words(y->lit_part[q], y->pos_part[q], p->words + from, (uint32_t)(to - from));
+    }
+    const int went = pass_span(p, k, (uint32_t)n, 0, parts);
+    memset(y->lit_part, 0, sizeof(y->lit_part[0]) * parts);
+    memset(y->pos_part, 0, sizeof(y->pos_part[0]) * parts);
+    if (!went && p->flaw) {             /* where the model stopped is what its caller wants to know */
+        return p->eyes->k_now - k;
+    }
+    return n;
 }
 
 /* The coder proper, one thread. */
 static void code_symbols(struct sqz* s, const uint32_t* words, uint64_t count) {
-    struct sqz_bitstream* const bs = s->bs;
     struct tally y;
     struct code_tables ct;              /* kept current by relabel through the trees' watcher */
-    struct watch eyes = { &ct, NULL };
-    uint32_t reach = block_most;
-    uint64_t matches = 0, k = 0;
+    struct watch eyes = { &ct, NULL, NULL, 0, 0, 0 };
+    struct pass p = { s, &y, &eyes, words, 0, &ct, 0, 0 };
+    uint64_t k = 0;
     if (s->error != 0) { return; }
     tally_init(&y);
     tables_from_trees(&ct, s);
     s->lit.watcher = s->pos.watcher = &eyes;
-    while (k < count && s->error == 0) {
-        const uint32_t n = block_span(&s->lit, count - k, reach);
-        if (n >= block_least) {
-            if (count_block(s, &y, words + k, n)) {
-                /* no code changed while the block was counted: its bits are those of the codes as they are */
-                matches += emit_run(s, bs, words, k, k + n, &ct);
-                k += n;
-                reach = 2 * n < block_most ? 2 * n : block_most;
-                continue;
-            }
-            if (n >= 4 * block_least) { reach = n / 4; continue; }
-        }
-        const uint64_t stretch = n >= block_least ? n : (count - k < block_least ? count - k : block_least);
-        matches += code_one_by_one(s, words, k, k + stretch);
-        k += stretch;
-    }
+    while (k < count && s->error == 0) { k += pass_block(&p, k, count); }
     s->lit.watcher = s->pos.watcher = NULL;
-    s->matches += matches;
+    s->matches += p.matches;
     s->tokens += count;
 }
 
@@ -1253,19 +1374,17 @@ struct duo {                            /* one cache line per writer: the two th
     _Alignas(64) _Atomic uint64_t modelled;   /* tokens of the current chunk the model is done with */
     _Atomic uint64_t log_tail;          /* changes written */
     int model_error;
+    uint64_t model_matches;             /* read after the model thread was joined */
     /* either side gives up (written once) */
     _Alignas(64) _Atomic int stop;
     /* model thread only (written for every token) */
-    _Alignas(64) uint64_t now;          /* stamp for changes: index of the token being modelled + 1 */
-    uint64_t k_now;                     /* its index within the chunk */
-    uint64_t model_base;
+    _Alignas(64) struct watch eyes;
     /* emitter only: changes taken out of the log before they were due (so that the model never waits
      * for room while the emitter waits for the model), and the code tables as of the token being emitted */
     _Alignas(64) struct change* early;
     size_t early_count, early_room, early_next;
 
-    struct watch eyes;
-    struct code_tables tables;
+    _Alignas(64) struct code_tables tables;
     struct change log[log_size];
 };
 
@@ -1287,10 +1406,17 @@ static inline void spin_wait(unsigned* spins) {
     }
 }
 
+static void segment_note(struct watch* eyes, uint16_t leaf, uint64_t code, uint8_t bits);
+
 static void note_change(struct sqz_tree* t, int32_t leaf) {
-    const struct watch* const eyes = (const struct watch*)t->watcher;
+    struct watch* const eyes = (struct watch*)t->watcher;
+    const uint16_t tagged = (uint16_t)(t->n == sqz_pos_symbols ? leaf | pos_leaf : leaf);
     if (eyes->tables != NULL) {
         tables_set(eyes->tables, t->n == sqz_pos_symbols, (uint32_t)leaf, t->code[leaf], t->bits[leaf]);
+        return;
+    }
+    if (eyes->seg != NULL) {
+        segment_note(eyes, tagged, t->code[leaf], t->bits[leaf]);
         return;
     }
     struct duo* d = eyes->d;
@@ -1298,24 +1424,34 @@ static void note_change(struct sqz_tree* t, int32_t leaf) {
     unsigned spins = 0;
     while (tail - atomic_load_explicit(&d->log_head, memory_order_acquire) >= log_size) {
         /* let the emitter come up to this token; once it waits for the model it empties the log */
-        atomic_store_explicit(&d->modelled, d->k_now, memory_order_release);
+        atomic_store_explicit(&d->modelled, eyes->k_now, memory_order_release);
         if (atomic_load_explicit(&d->stop, memory_order_relaxed)) { return; }
         spin_wait(&spins);
     }
     struct change* c = &d->log[tail & (log_size - 1)];
-    c->at = d->now;
+    c->at = eyes->now;
     c->code = t->code[leaf];
-    c->leaf = (uint16_t)(t->n == sqz_pos_symbols ? leaf | pos_leaf : leaf);
+    c->leaf = tagged;
     c->bits = t->bits[leaf];
     atomic_store_explicit(&d->log_tail, tail + 1, memory_order_release);
 }
 
+/* The model's walk over the words [k, until) of a chunk whose first token has the stamp `base`: as
+ * blocks where that works, one by one elsewhere (code_symbols without the output).  Returns where
+ * it stopped: `until`; or earlier with *flaw = 1 at a word that is no symbol word (not modelled;
+ * the emitter reports it when it gets there) or with eyes->error set.                            */
+static uint64_t model_words(struct sqz* s, struct tally* y, struct watch* eyes, const uint32_t* words,
+                            uint64_t k, uint64_t until, uint64_t base, int* flaw, uint64_t* matches) {
+    struct pass p = { s, y, eyes, words, base, NULL, 0, 0 };
+    while (k < until && !p.flaw && eyes->error == 0) { k += pass_block(&p, k, until); }
+    *flaw = p.flaw;
+    *matches += p.matches;
+    return k;
+}
 
 static void* model_main(void* arg) {
     struct duo* d = (struct duo*)arg;
     struct sqz* const s = d->s;
-    struct sqz_tree* const lit = &s->lit;
-    struct sqz_tree* const pos = &s->pos;
     struct tally y;
     uint64_t seen = 0;
     unsigned spins = 0;
@@ -1330,52 +1466,22 @@ static void* model_main(void* arg) {
         spins = 0;
         const uint32_t* const words = d->words;
         const uint64_t count = d->count;
-        uint32_t reach = block_most;
+        const uint64_t base = d->base;
         uint64_t k = 0;
-        d->model_base = d->base;
         while (k < count) {
             atomic_store_explicit(&d->modelled, k, memory_order_release);
             if (atomic_load_explicit(&d->stop, memory_order_relaxed)) { return NULL; }
-            const uint32_t n = block_span(lit, count - k, reach);
-            if (n >= block_least) {
-                if (count_block(s, &y, words + k, n)) {          /* no code changes: nothing to log */
-                    k += n;
-                    reach = 2 * n < block_most ? 2 * n : block_most;
-                    continue;
-                }
-                if (n >= 4 * block_least) { reach = n / 4; continue; }
+            int flaw = 0;
+            const uint64_t until = count - k < block_most ? count : k + block_most;
+            k = model_words(s, &y, &d->eyes, words, k, until, base, &flaw, &d->model_matches);
+            if (flaw) {                                  /* the emitter reports it when it gets there */
+                atomic_store_explicit(&d->modelled, k + 1, memory_order_release);
+                return NULL;
             }
-            const uint64_t until = k + (n >= block_least ? n : (count - k < block_least ? count - k : block_least));
-            for (; k < until; k++) {
-                const uint32_t w = words[k];
-                const uint32_t sym = w & 0x1FF;
-                d->k_now = k;
-                d->now = d->model_base + k + 1;
-                if (!word_is_valid(w)) {                 /* the emitter reports it when it gets there */
-                    atomic_store_explicit(&d->modelled, k + 1, memory_order_release);
-                    return NULL;
-                }
-                if (lit->bits[sym] == 0) {               /* squeeze.h:278-288: escape, then the new symbol */
-                    tree_count(lit, sqz_lit_nyt);
-                    if (!tree_insert(lit, (int32_t)sym)) { d->model_error = E2BIG; }
-                } else {
-                    tree_count_as(lit, (int32_t)sym, lit_plan);
-                    SQZ_CHECK(lit);
-                }
-                if (sym >= len_symbol0 && d->model_error == 0) {
-                    const uint32_t pb = (w >> 14) & 31;
-                    if (pos->bits[pb] == 0) {            /* squeeze.h:300-315 */
-                        tree_count(pos, sqz_pos_nyt);
-                        if (!tree_insert(pos, (int32_t)pb)) { d->model_error = E2BIG; }
-                    } else {
-                        tree_count_as(pos, (int32_t)pb, pos_plan);
-                        SQZ_CHECK(pos);
-                    }
-                }
-                if (d->model_error != 0) {
-                    atomic_store_explicit(&d->stop, 1, memory_order_release);
-                    return NULL;
-                }
+            if (d->eyes.error != 0) {
+                d->model_error = d->eyes.error;
+                atomic_store_explicit(&d->stop, 1, memory_order_release);
+                return NULL;
             }
         }
         atomic_store_explicit(&d->modelled, count, memory_order_release);
@@ -1389,7 +1495,6 @@ static inline void take_change(struct duo* d, const struct change* c) {
 /* the emitter's half of one chunk */
 static void duo_emit(struct sqz* s, struct duo* d, const uint32_t* words, uint64_t count) {
     struct sqz_bitstream* const bs = s->bs;
-    uint64_t matches = 0;
     uint64_t head = atomic_load_explicit(&d->log_head, memory_order_relaxed);
     uint64_t tail = atomic_load_explicit(&d->log_tail, memory_order_acquire);
     uint64_t avail = 0;
@@ -1449,7 +1554,7 @@ static void duo_emit(struct sqz* s, struct duo* d, const uint32_t* words, uint64
         } else if (head != tail) {
             if (d->log[head & (log_size - 1)].at - base < until) { until = d->log[head & (log_size - 1)].at - base; }
         }
-        matches += emit_run(s, bs, words, k, until, &d->tables);
+        emit_run(&s->error, bs, words, k, until, &d->tables);
         if (s->error != 0) { goto done; }
         k = until;
     }
@@ -1457,22 +1562,19 @@ done:
     atomic_store_explicit(&d->log_head, head, memory_order_release);
     if (s->error != 0) { atomic_store_explicit(&d->stop, 1, memory_order_release); }
     d->base = base + count;
-    s->matches += matches;
     s->tokens += count;
 }
 
 struct duo_run { struct duo* d; pthread_t model; };
 
-/* after coder_begin: start the model thread; NULL (and no error) when two threads are not wanted */
-static int duo_start(struct sqz* s, struct duo_run* run, uint64_t expected_tokens) {
+/* after coder_begin: start the model thread; 0 when that cannot be had */
+static int duo_start(struct sqz* s, struct duo_run* run) {
     run->d = NULL;
-    if (s->coder_threads == 1 || (s->coder_threads == 0 && expected_tokens < duo_least)) { return 0; }
     struct duo* d = (struct duo*)aligned_alloc(64, (sizeof(struct duo) + 63) & ~(size_t)63);
     if (d == NULL) { return 0; }                    /* no memory for the log: one thread will do */
     memset(d, 0, sizeof(struct duo));
     d->s = s;
     tables_from_trees(&d->tables, s);
-    d->eyes.tables = NULL;
     d->eyes.d = d;
     s->lit.watcher = s->pos.watcher = &d->eyes;
     if (pthread_create(&run->model, NULL, model_main, d) != 0) {
@@ -1488,10 +1590,318 @@ static void duo_finish(struct sqz* s, struct duo_run* run) {
     if (run->d == NULL) { return; }
     atomic_store_explicit(&run->d->finish, 1, memory_order_release);
     pthread_join(run->model, NULL);
+    s->matches += run->d->model_matches;
     s->lit.watcher = s->pos.watcher = NULL;
     free(run->d->early);
     free(run->d);
     run->d = NULL;
+}
+
+/* ======================================================================== *
+ *  the coder on several threads                                             *
+ *  With blocks the model needs less time per token than the emitter, and    *
+ *  emitting is only serial in where the bits go.  So for coder_threads >= 3 *
+ *  the model cuts the stream into segments (seg_tokens tokens; shorter at a *
+ *  chunk's end or when a segment's changes pile up), gives each the code    *
+ *  tables as they stand at its first token and the list of changes made     *
+ *  while it modelled the segment, and publishes it; coder_threads - 1       *
+ *  emitter threads take segments in turn and emit each into a buffer of its *
+ *  own, starting at bit 0; the calling thread appends the buffers in order  *
+ *  to the caller's bitstream, shifted to where the bits belong.  Same bytes *
+ *  by construction: a token's bits are those of the codes the model had     *
+ *  when it reached the token, and they land behind the previous token's.    *
+ * ======================================================================== */
+
+enum { seg_tokens = 1 << 14,
+       seg_out_room = 24 * seg_tokens + 64,  /* a token is at most 63 + 9 + 5 + 63 + 5 + 13 bits */
+       seg_changes_most = 1 << 18,           /* a segment ends early beyond this many changes */
+       crew_most = 7,                        /* emitter threads */
+       crew_least = 1 << 20 };               /* tokens from which the automatic choice takes a crew */
+
+struct segment {
+    /* the model's, until `modelled` passes the segment; then read by one emitter */
+    const uint32_t* words;              /* the chunk */
+    uint64_t from, until;               /* the segment's tokens within it */
+    struct change* log;                 /* `at` = index within the chunk of the first token a change applies to */
+    size_t log_count, log_room;
+    uint64_t lit_code[sqz_lit_symbols]; /* the codes as they stand at `from` */
+    uint64_t pos_code[sqz_pos_symbols];
+    uint8_t lit_bits[sqz_lit_symbols];
+    uint8_t pos_bits[sqz_pos_symbols];
+    /* the emitter's, until `emitted` names the segment; then read by the calling thread */
+    uint8_t* out;                       /* whole 64-bit words, big-endian */
+    uint64_t out_bytes;
+    uint64_t tail;                      /* and the bits that did not fill a word */
+    int32_t tail_bits;
+    int32_t error;
+    _Alignas(64) _Atomic uint64_t emitted;   /* number of the segment + 1 */
+};
+
+struct crew {
+    struct sqz* s;
+    int emitters, ring, threads_up;
+    pthread_t model;
+    pthread_t emitter[crew_most];
+    struct segment* seg;                /* [ring] */
+    struct watch eyes;                  /* the model's */
+    int model_error;
+    uint64_t model_matches;             /* read after the model thread was joined */
+    /* the calling thread -> the model */
+    _Alignas(64) const uint32_t* words;
+    uint64_t count;
+    _Atomic uint64_t chunks;
+    _Atomic int finish;
+    _Alignas(64) _Atomic uint64_t merged;     /* segments appended to the bitstream: their slots are free */
+    /* the model -> the emitters */
+    _Alignas(64) _Atomic uint64_t modelled;   /* segments published */
+    /* the emitters among themselves */
+    _Alignas(64) _Atomic uint64_t next;       /* the next segment to take */
+    /* anybody gives up (written once) */
+    _Alignas(64) _Atomic int stop;
+};
+
+static void segment_note(struct watch* eyes, uint16_t leaf, uint64_t code, uint8_t bits) {
+    struct segment* const g = eyes->seg;
+    if (g->log_count == g->log_room) {
+        const size_t room = g->log_room == 0 ? 1024 : 2 * g->log_room;
+        struct change* grown = (struct change*)realloc(g->log, room * sizeof(struct change));
+        if (grown == NULL) { eyes->error = ENOMEM; return; }
+        g->log = grown;
+        g->log_room = room;
+    }
+    struct change* c = &g->log[g->log_count++];
+    c->at = eyes->now;
+    c->code = code;
+    c->leaf = leaf;
+    c->bits = bits;
+}
+
+static void* crew_model_main(void* arg) {
+    struct crew* c = (struct crew*)arg;
+    struct sqz* const s = c->s;
+    struct tally y;
+    uint64_t seen = 0, published = 0;
+    unsigned spins = 0;
+    tally_init(&y);
+    for (;;) {
+        while (atomic_load_explicit(&c->chunks, memory_order_acquire) == seen) {
+            if (atomic_load_explicit(&c->finish, memory_order_acquire) ||
+                atomic_load_explicit(&c->stop, memory_order_relaxed)) { return NULL; }
+            spin_wait(&spins);
+        }
+        seen++;
+        spins = 0;
+        const uint32_t* const words = c->words;
+        const uint64_t count = c->count;
+        uint64_t k = 0;
+        while (k < count) {
+            while (published - atomic_load_explicit(&c->merged, memory_order_acquire) >= (uint64_t)c->ring) {
+                if (atomic_load_explicit(&c->stop, memory_order_relaxed)) { return NULL; }
+                spin_wait(&spins);                   /* every slot holds a segment on its way */
+            }
+            spins = 0;
+            struct segment* const g = &c->seg[published % (uint64_t)c->ring];
+            g->words = words;
+            g->from = k;
+            g->log_count = 0;
+            memcpy(g->lit_code, s->lit.code, sizeof(g->lit_code));
+            memcpy(g->pos_code, s->pos.code, sizeof(g->pos_code));
+            memcpy(g->lit_bits, s->lit.bits, sizeof(g->lit_bits));
+            memcpy(g->pos_bits, s->pos.bits, sizeof(g->pos_bits));
+            c->eyes.seg = g;
+            const uint64_t end = count - k < seg_tokens ? count : k + seg_tokens;
+            int flaw = 0;
+            while (k < end && !flaw && g->log_count <= seg_changes_most) {
+                const uint64_t until = end - k < block_most ? end : k + block_most;
+                k = model_words(s, &y, &c->eyes, words, k, until, 0, &flaw, &c->model_matches);
+                if (c->eyes.error != 0) {
+                    c->model_error = c->eyes.error;
+                    atomic_store_explicit(&c->stop, 1, memory_order_release);
+                    return NULL;
+                }
+            }
+            g->until = flaw ? k + 1 : k;             /* a word that is no symbol word: its emitter reports it */
+            published++;
+            atomic_store_explicit(&c->modelled, published, memory_order_release);
+            if (flaw) { return NULL; }
+        }
+    }
+}
+
+/* one segment into its buffer: the codes as they were at its start, each change from the token on
+ * that it applies to */
+static void emit_segment(struct segment* g, struct code_tables* ct) {
+    struct sqz_bitstream bs;
+    memset(&bs, 0, sizeof(bs));
+    bs.data = g->out;
+    bs.capacity = seg_out_room;
+    memset(ct->pos_word, 0, sizeof(ct->pos_word));
+    for (uint32_t k = 0; k < sqz_lit_symbols; k++) { tables_set(ct, 0, k, g->lit_code[k], g->lit_bits[k]); }
+    for (uint32_t k = 0; k < sqz_pos_symbols; k++) { tables_set(ct, 1, k, g->pos_code[k], g->pos_bits[k]); }
+    g->error = 0;
+    size_t next = 0;
+    uint64_t k = g->from;
+    while (k < g->until && g->error == 0) {
+        while (next < g->log_count && g->log[next].at <= k) {
+            const struct change* ch = &g->log[next++];
+            tables_set(ct, (ch->leaf & pos_leaf) != 0, ch->leaf & (pos_leaf - 1u), ch->code, ch->bits);
+        }
+        const uint64_t until = next < g->log_count && g->log[next].at < g->until ? g->log[next].at : g->until;
+        emit_run(&g->error, &bs, g->words, k, until, ct);
+        k = until;
+    }
+    g->out_bytes = bs.bytes;
+    g->tail = bs.b64;
+    g->tail_bits = bs.bits;
+}
+
+static void* crew_emitter_main(void* arg) {
+    struct crew* c = (struct crew*)arg;
+    struct code_tables* ct = (struct code_tables*)malloc(sizeof(struct code_tables));
+    unsigned spins = 0;
+    for (;;) {
+        const uint64_t j = atomic_fetch_add_explicit(&c->next, 1, memory_order_relaxed);
+        while (atomic_load_explicit(&c->modelled, memory_order_acquire) <= j) {
+            if (atomic_load_explicit(&c->finish, memory_order_acquire) ||
+                atomic_load_explicit(&c->stop, memory_order_relaxed)) { free(ct); return NULL; }
+            spin_wait(&spins);
+        }
+        spins = 0;
+        struct segment* const g = &c->seg[j % (uint64_t)c->ring];
+        if (ct == NULL) { g->error = ENOMEM; } else { emit_segment(g, ct); }
+        atomic_store_explicit(&g->emitted, j + 1, memory_order_release);
+    }
+}
+
+/* the calling thread's part of one chunk: hand it to the model, append its segments as they come */
+static void crew_emit(struct sqz* s, struct crew* c, const uint32_t* words, uint64_t count) {
+    struct sqz_bitstream* const bs = s->bs;
+    int32_t* const err = &s->error;
+    uint64_t acc = bs->b64;
+    uint32_t fill = (uint32_t)bs->bits;
+    uint64_t merged = atomic_load_explicit(&c->merged, memory_order_relaxed);
+    uint64_t done_tokens = 0;
+    unsigned spins = 0;
+    if (count == 0 || s->error != 0) { return; }
+    c->words = words;
+    c->count = count;
+    atomic_fetch_add_explicit(&c->chunks, 1, memory_order_release);
+    while (done_tokens < count) {
+        struct segment* const g = &c->seg[merged % (uint64_t)c->ring];
+        while (atomic_load_explicit(&g->emitted, memory_order_acquire) != merged + 1) {
+            if (atomic_load_explicit(&c->stop, memory_order_acquire)) {
+                s->error = c->model_error != 0 ? c->model_error : EIO;
+                goto done;
+            }
+            spin_wait(&spins);
+        }
+        spins = 0;
+        if (g->error != 0) { s->error = g->error; goto done; }
+        for (uint64_t at = 0; at < g->out_bytes; at += 8) {
+            uint64_t be;
+            memcpy(&be, g->out + at, 8);
+            const uint64_t word = __builtin_bswap64(be);
+            SQZ_APPEND(word >> 32, 32);
+            SQZ_APPEND(word & 0xFFFFFFFFu, 32);
+        }
+        if (g->tail_bits > 0) { SQZ_APPEND(g->tail, (uint32_t)g->tail_bits); }
+        done_tokens += g->until - g->from;
+        merged++;
+        atomic_store_explicit(&c->merged, merged, memory_order_release);
+    }
+done:
+    if (s->error != 0) { atomic_store_explicit(&c->stop, 1, memory_order_release); }
+    bs->b64 = acc;
+    bs->bits = (int32_t)fill;
+    s->tokens += count;
+}
+
+static void crew_free(struct crew* c) {
+    if (c->seg != NULL) {
+        for (int k = 0; k < c->ring; k++) { free(c->seg[k].log); free(c->seg[k].out); }
+        free(c->seg);
+    }
+    free(c);
+}
+
+static struct crew* crew_start(struct sqz* s, int emitters) {
+    struct crew* c = (struct crew*)aligned_alloc(64, (sizeof(struct crew) + 63) & ~(size_t)63);
+    if (c == NULL) { return NULL; }
+    memset(c, 0, sizeof(struct crew));
+    c->s = s;
+    c->emitters = emitters < 1 ? 1 : (emitters > crew_most ? crew_most : emitters);
+    c->ring = 4 * c->emitters;
+    c->seg = (struct segment*)aligned_alloc(64, sizeof(struct segment) * (size_t)c->ring);
+    if (c->seg == NULL) { crew_free(c); return NULL; }
+    memset(c->seg, 0, sizeof(struct segment) * (size_t)c->ring);
+    for (int k = 0; k < c->ring; k++) {
+        c->seg[k].out = (uint8_t*)malloc(seg_out_room);
+        if (c->seg[k].out == NULL) { crew_free(c); return NULL; }
+    }
+    s->lit.watcher = s->pos.watcher = &c->eyes;
+    if (pthread_create(&c->model, NULL, crew_model_main, c) != 0) {
+        s->lit.watcher = s->pos.watcher = NULL;
+        crew_free(c);
+        return NULL;
+    }
+    for (int k = 0; k < c->emitters; k++) {
+        if (pthread_create(&c->emitter[k], NULL, crew_emitter_main, c) != 0) { break; }
+        c->threads_up++;
+    }
+    if (c->threads_up == 0) {                        /* nobody to emit: not a crew */
+        atomic_store_explicit(&c->stop, 1, memory_order_release);
+        pthread_join(c->model, NULL);
+        s->lit.watcher = s->pos.watcher = NULL;
+        crew_free(c);
+        return NULL;
+    }
+    return c;
+}
+
+static void crew_finish(struct sqz* s, struct crew* c) {
+    atomic_store_explicit(&c->finish, 1, memory_order_release);
+    pthread_join(c->model, NULL);
+    for (int k = 0; k < c->threads_up; k++) { pthread_join(c->emitter[k], NULL); }
+    s->matches += c->model_matches;
+    s->lit.watcher = s->pos.watcher = NULL;
+    crew_free(c);
+}
+
+/* ---- one front for the coders on more than one thread ---- */
+
+struct team { struct duo_run two; struct crew* crew; };
+
+static int host_cores(void) {
+    const long n = sysconf(_SC_NPROCESSORS_ONLN);
+    return n < 1 ? 1 : (int)n;
+}
+
+/* after coder_begin: start the threads coder_threads asks for (0: by the stream's length and the
+ * host's cores); 0 = none were started (not wanted, or not to be had), one thread will do */
+static int team_start(struct sqz* s, struct team* t, uint64_t expected_tokens) {
+    t->two.d = NULL;
+    t->crew = NULL;
+    int threads = s->coder_threads;
+    if (threads <= 0) {
+        const int cores = host_cores();
+        threads = expected_tokens < duo_least || cores < 2 ? 1 :
+                  expected_tokens < crew_least || cores < 8 ? 2 : 4;
+    }
+    if (threads >= 3) {
+        t->crew = crew_start(s, threads - 1);
+        if (t->crew != NULL) { return 1; }
+        threads = 2;
+    }
+    return threads == 2 ? duo_start(s, &t->two) : 0;
+}
+
+static void team_emit(struct sqz* s, struct team* t, const uint32_t* words, uint64_t count) {
+    if (t->crew != NULL) { crew_emit(s, t->crew, words, count); } else { duo_emit(s, t->two.d, words, count); }
+}
+
+static void team_finish(struct sqz* s, struct team* t) {
+    if (t->crew != NULL) { crew_finish(s, t->crew); t->crew = NULL; }
+    duo_finish(s, &t->two);
 }
 
 void sqz_write_header(struct sqz_bitstream* bs, uint64_t bytes, uint8_t win_bits) {
@@ -1533,10 +1943,10 @@ void sqz_encode_symbols(struct sqz* s, struct sqz_bitstream* bs,
                         const uint32_t* words, uint64_t count) {
     coder_begin(s, bs);
     double t0 = now_seconds();
-    struct duo_run run;
-    if (s->error == 0 && duo_start(s, &run, count)) {
-        duo_emit(s, run.d, words, count);
-        duo_finish(s, &run);
+    struct team run;
+    if (s->error == 0 && team_start(s, &run, count)) {
+        team_emit(s, &run, words, count);
+        team_finish(s, &run);
     } else {
         code_symbols(s, words, count);
     }
@@ -1547,14 +1957,14 @@ void sqz_encode_symbols(struct sqz* s, struct sqz_bitstream* bs,
 void sqz_encode_symbols_chunked(struct sqz* s, struct sqz_bitstream* bs,
                                 const uint32_t* words, uint64_t count, uint64_t chunk) {
     coder_begin(s, bs);
-    struct duo_run run;
-    const int two = s->error == 0 && duo_start(s, &run, count);
+    struct team run;
+    const int two = s->error == 0 && team_start(s, &run, count);
     if (chunk == 0) { chunk = count; }
     for (uint64_t at = 0; at < count && s->error == 0; at += chunk) {
         const uint64_t n = count - at < chunk ? count - at : chunk;
-        if (two) { duo_emit(s, run.d, words + at, n); } else { code_symbols(s, words + at, n); }
+        if (two) { team_emit(s, &run, words + at, n); } else { code_symbols(s, words + at, n); }
     }
-    if (two) { duo_finish(s, &run); }
+    if (two) { team_finish(s, &run); }
     if (s->error == 0) { pad_to_word(bs); s->error = bs->error; }
 }
 
@@ -1575,8 +1985,8 @@ void sqz_compress(struct sqz* s, struct sqz_bitstream* bs,
                                 sqz_min_len, sqz_max_len, window - 1, 0, SQZ_GPU_STREAM_SYMBOLS);
     t_search += now_seconds() - t0;
     if (r != 0) { s->error = r; return; }
-    struct duo_run run;
-    const int two = duo_start(s, &run, bytes / 2);     /* about 0.6 tokens per byte on mixed data */
+    struct team run;
+    const int two = team_start(s, &run, bytes / 2);    /* about 0.6 tokens per byte on mixed data */
     for (;;) {
         const uint32_t* words = NULL;
         size_t count = 0;
@@ -1586,11 +1996,11 @@ void sqz_compress(struct sqz* s, struct sqz_bitstream* bs,
         if (r != 0) { s->error = r; break; }
         if (count == 0) { break; }
         t0 = now_seconds();
-        if (two) { duo_emit(s, run.d, words, count); } else { code_symbols(s, words, count); }
+        if (two) { team_emit(s, &run, words, count); } else { code_symbols(s, words, count); }
         t_code += now_seconds() - t0;
         if (s->error != 0) { break; }
     }
-    duo_finish(s, &run);
+    if (two) { team_finish(s, &run); }
     sqz_gpu_stream_close(st);
     if (s->error == 0) { pad_to_word(bs); s->error = bs->error; }
     s->search_seconds = t_search;

@@ -247,9 +247,12 @@ def test_two_thread_coder_gives_the_same_bytes(seed, reference):
     one = sq.encode_symbols(words, nbytes, 15, threads=1)
     two = sq.encode_symbols(words, nbytes, 15, threads=2)
     assert one == two == reference.encode_tokens(toks, nbytes, 15)
+    # coder_threads >= 3: the model cuts the stream into segments, coder_threads - 1 emitters work on them
+    assert sq.encode_symbols(words, nbytes, 15, threads=3 + seed % 4) == one
     if seed % 5 == 0:
-        assert sq.encode_symbols(words, nbytes, 15, file_mode=True, threads=2) == \
-            sq.encode_symbols(words, nbytes, 15, file_mode=True, threads=1)
+        by_callback = sq.encode_symbols(words, nbytes, 15, file_mode=True, threads=1)
+        assert sq.encode_symbols(words, nbytes, 15, file_mode=True, threads=2) == by_callback
+        assert sq.encode_symbols(words, nbytes, 15, file_mode=True, threads=4) == by_callback
 
 
 @pytest.mark.parametrize("seed", range(12))
@@ -261,7 +264,7 @@ def test_two_thread_coder_with_a_full_log(seed, tiny_log_lib, reference):
     assert sq.encode_symbols(words, nbytes, 15, threads=2, lib=tiny_log_lib) == reference.encode_tokens(toks, nbytes, 15)
 
 
-@pytest.mark.parametrize("threads", [1, 2])
+@pytest.mark.parametrize("threads", [1, 2, 3, 5])
 @pytest.mark.parametrize("chunk", [1, 255, 256, 257, 5000, 100000])
 def test_chunked_hand_over_like_sqz_compress(chunk, threads, oracle, reference, inputs):
     """sqz_compress feeds the coder chunk by chunk from the GPU stream; here the same from a host array."""
@@ -289,14 +292,32 @@ def test_two_thread_coder_errors():
     L.sqz_write_header(C.byref(bs), 200000, 15)
     s = _lib.State()
     L.sqz_init(C.byref(s))
-    s.coder_threads = 2
-    L.sqz_encode_symbols(C.byref(s), C.byref(bs), words.ctypes.data_as(_lib.u32p), words.size)
-    assert s.error == errno.E2BIG
-    bad = words.copy()
-    bad[150000] = 256
-    with pytest.raises(sq.SqzError) as e:
-        sq.encode_symbols(bad, 200000, 15, threads=2)
-    assert e.value.errno == errno.EINVAL
+    for threads in (2, 4):
+        bs = _bs(buf)
+        L.sqz_write_header(C.byref(bs), 200000, 15)
+        L.sqz_init(C.byref(s))
+        s.coder_threads = threads
+        L.sqz_encode_symbols(C.byref(s), C.byref(bs), words.ctypes.data_as(_lib.u32p), words.size)
+        assert s.error == errno.E2BIG
+    for where, what in ((150000, 256), (0, 285), (199999, 300), (77777, 284 | 31 << 9 | 3 << 14), (5, 257 | 30 << 14)):
+        bad = words.copy()
+        bad[where] = what
+        for threads in (1, 2, 4):
+            with pytest.raises(sq.SqzError) as e:
+                sq.encode_symbols(bad, 200000, 15, threads=threads)
+            assert e.value.errno == errno.EINVAL
+
+
+def test_coders_agree_on_a_long_stream(oracle, reference):
+    """3 MiB of the bench corpus (1.9 M tokens, 115 segments of the several-thread coder, some 500
+    reorderings): one thread, two threads and crews of 2, 3 and 7 emitters give the reference's bytes."""
+    from sqz_b200 import corpus
+    d = corpus.synthetic(3 << 20, 5 << 20)
+    t = oracle_tokens(oracle, d, 15)
+    words = sq.symbols_of_tokens(t)
+    want = reference.encode_tokens(t, d.size, 15)
+    for threads in (1, 2, 3, 4, 8):
+        assert sq.encode_symbols(words, d.size, 15, threads=threads) == want, threads
 
 
 def test_header_bytes():
