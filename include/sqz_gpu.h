@@ -100,9 +100,18 @@ int sqz_gpu_tokens_multi(const int* devices, int n_devices,
 
 /* Streaming form used by sqz_compress(): tokens arrive chunk by chunk, in
  * parse order, from double-buffered pinned memory while the device already
- * works on the next chunk.  *tokens stays valid until the next call.        */
+ * works on the next chunk.  *tokens stays valid until the next call.
+ * chunk_bytes = 0: chunks of 2, 4, 8, 16, then 32 MiB -- a consumer slower
+ * than the search starts after milliseconds.  chunk_bytes > 0: chunks of that
+ * size -- for a consumer faster than the search, which only has to keep the
+ * device on chunks it is efficient at; with SQZ_GPU_STREAM_SHORT_START the
+ * first two are a quarter and a half of it.  The searches of consecutive
+ * chunks run one after the other (a consumer wants them in order, not both
+ * late), a chunk's parse and copy at the highest stream priority beside the
+ * next chunk's search.                                                      */
 typedef struct sqz_gpu_stream sqz_gpu_stream;
-#define SQZ_GPU_STREAM_SYMBOLS 1u   /* deliver symbol words instead of plain tokens */
+#define SQZ_GPU_STREAM_SYMBOLS 1u       /* deliver symbol words instead of plain tokens */
+#define SQZ_GPU_STREAM_SHORT_START 2u   /* explicit chunk_bytes: start with chunk_bytes / 4, then / 2 */
 int  sqz_gpu_stream_open(sqz_gpu_stream** st, int device,
                          const uint8_t* data, size_t bytes,
                          uint32_t window, uint32_t min_len, uint32_t max_len,

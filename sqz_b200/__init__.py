@@ -5,8 +5,8 @@ greedy parse on the GPU (csrc/sqz_gpu.cu), the host entropy stage that consumes
 the token stream unchanged (csrc/sqz_codec.c), and this thin ctypes mirror of
 the reference's codec interface.  See DESIGN.md.
 """
-from .api import (SqzError, compress, decode_tokens, decompress, decompress_gpu, device_count, expand_tokens, encode_symbols, encode_tokens, launch_count,
+from .api import (SqzError, capacity, compress, decode_tokens, decompress, decompress_gpu, device_count, expand_tokens, encode_symbols, encode_tokens, launch_count,
                   match_table, read_header, release, select_kernel, symbols_of_tokens, tokens, tokens_multi)
 
-__all__ = ["SqzError", "compress", "decode_tokens", "decompress", "decompress_gpu", "device_count", "expand_tokens", "encode_symbols", "encode_tokens",
+__all__ = ["SqzError", "capacity", "compress", "decode_tokens", "decompress", "decompress_gpu", "device_count", "expand_tokens", "encode_symbols", "encode_tokens",
            "launch_count", "match_table", "read_header", "release", "select_kernel", "symbols_of_tokens", "tokens", "tokens_multi"]

@@ -123,11 +123,19 @@ def _capacity(nbytes: int) -> int:
 
 
 def compress(data, win_bits: int = 15, file_mode: bool = False, stats: dict | None = None,
-             threads: int = 0) -> bytes:
-    """squeeze.write_header + squeeze.compress: GPU search, host entropy stage."""
+             threads: int = 0, into=None):
+    """squeeze.write_header + squeeze.compress: GPU search, host entropy stage.  Returns the bitstream as
+    bytes -- or, with `into` (a C-contiguous writable uint8 array of at least capacity(len(data)) bytes, the
+    caller's buffer as in the C API), a view of the part of it that was written, without a copy."""
     L = _lib.load()
     d = _u8(data)
-    out = np.empty(_capacity(d.size), dtype=np.uint8)
+    if into is not None:
+        if not (isinstance(into, np.ndarray) and into.dtype == np.uint8 and into.flags.c_contiguous and
+                into.flags.writeable and into.size >= _capacity(d.size)):
+            raise ValueError("into: a writable C-contiguous uint8 array of at least capacity(len(data)) bytes")
+        out = into
+    else:
+        out = np.empty(_capacity(d.size), dtype=np.uint8)
     bs = Bitstream()
     sink = {"at": 0}
     if file_mode:
@@ -152,7 +160,12 @@ def compress(data, win_bits: int = 15, file_mode: bool = False, stats: dict | No
     if stats is not None:
         stats.update(tokens=int(s.tokens), matches=int(s.matches),
                      search_seconds=float(s.search_seconds), entropy_seconds=float(s.entropy_seconds))
-    return out[: bs.bytes].tobytes()
+    return out[: bs.bytes].tobytes() if into is None else out[: bs.bytes]
+
+
+def capacity(nbytes: int) -> int:
+    """Bytes a bitstream of `nbytes` input bytes can need at most (what `compress(into=...)` asks for)."""
+    return _capacity(nbytes)
 
 
 def _encode(entry: str, arr, nbytes: int, win_bits: int, file_mode: bool, lib=None, threads: int = 0) -> bytes:

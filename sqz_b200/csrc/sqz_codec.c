@@ -14,6 +14,7 @@
 #include <pthread.h>
 #include <sched.h>
 #include <stdatomic.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
@@ -640,6 +641,16 @@ void tree_count_as(struct sqz_tree* t, int32_t s, const int usual) {   /* huffma
     }
 }
 
+/* What tree_count_as does first thing when no stretch is on, done ahead of the tree's next symbol:
+ * the decision only depends on the tree as it stands, and that does not change until then.       */
+static void renew_stretch(struct sqz_tree* t) {
+    if (!t->complete && t->depth < 63 && t->lazy == 0 && t->eager == 0) {
+        settle(t);
+        t->lazy = t->lazy_start = lazy_budget(t);
+        if (t->lazy == 0) { t->eager = eager_run; }
+    }
+}
+
 static void tree_count(struct sqz_tree* t, int32_t s) {
     if (t->n == sqz_lit_symbols) { tree_count_as(t, s, lit_plan); } else { tree_count_as(t, s, pos_plan); }
     SQZ_CHECK(t);
@@ -660,7 +671,10 @@ static void tree_count(struct sqz_tree* t, int32_t s) {
  *  only ever errs towards the slow path.                                    *
  * ======================================================================== */
 
-enum { part_tokens = 128,              /* tokens per part: the unit a block is tallied in and falls back to */
+#ifndef SQZ_PART_TOKENS
+#define SQZ_PART_TOKENS 256
+#endif
+enum { part_tokens = SQZ_PART_TOKENS,              /* tokens per part: the unit a block is tallied in and falls back to */
        parts_most = 16,
        block_most = part_tokens * parts_most,       /* tokens per block when all goes well */
        mini_tokens = 32,               /* a part that does not pass is tallied again in four minis */
@@ -678,6 +692,9 @@ struct tally {
     _Alignas(8) uint16_t pos_count[sqz_pos_symbols + 8];
     uint16_t lit_seen[sqz_lit_symbols];            /* its distinct symbols */
     uint16_t pos_seen[sqz_pos_symbols];
+    uint8_t lit_suspect[sqz_lit_symbols], pos_suspect[sqz_pos_symbols];   /* span_apply's verdict per seen leaf */
+    uint8_t lit_below[sqz_lit_symbols], lit_beside[sqz_lit_symbols];      /* culprit_leaves */
+    uint8_t pos_below[sqz_pos_symbols], pos_beside[sqz_pos_symbols];
     uint64_t lit_start[2 * sqz_lit_symbols + 1];   /* weights as they were when the span began, and */
     uint64_t pos_start[2 * sqz_pos_symbols + 1];   /* the comparators "always" (0) and "never" (2^63-1) */
 };
@@ -699,24 +716,43 @@ static inline void restore_weights(struct sqz_tree* t, const uint64_t* start) {
     memcpy(t->freq + t->next, start + t->next, sizeof(uint64_t) * (size_t)(2 * t->n - 1 - t->next));
 }
 
-/* `kinds` distinct leaves `seen[]`, leaf s occurring count[s] times, `total` occurrences in all.
- * 1: the weights now are what counting them one by one would have left and nothing else changed;
- * 0: nothing changed, the caller has to take another way (a symbol not yet in the tree or not a
- * symbol at all, the lazy stretch too short, a path deeper than a plan, a possible reordering).   */
-static inline __attribute__((always_inline))
-int tree_count_block(struct sqz_tree* t, const uint16_t* seen, uint32_t kinds, const uint16_t* count,
-                     uint32_t total, uint64_t* start, const int usual, const int32_t nyt) {
-    if (total == 0) { return 1; }
-    if (t->lazy < (int32_t)total) { return 0; }
+/* A span on one tree, in steps.  `kinds` distinct leaves `seen[]`, leaf s occurring count[s] times,
+ * `total` occurrences in all.
+ * span_ready: 0 when the span cannot be counted at once on this tree (a symbol not yet in the tree
+ *   or not a symbol at all, the lazy stretch too short, a path deeper than a plan); makes the plans.
+ * span_apply: keeps the weights in `start`, adds the counts along the plans; 1 when no node's end
+ *   weight exceeds its comparator's start weight (then nothing can have reordered, whatever the order
+ *   of the symbols), 0 when some do -- the culprits.
+ * span_culprits: which (node, comparator) pairs those are.
+ * restore_weights undoes span_apply; span_done closes a span that stands.                          */
+enum { span_lazily = 1, span_fully = 2 };
+
+static inline int span_ready(struct sqz_tree* t, const uint16_t* seen, uint32_t kinds, uint32_t total,
+                             const int32_t nyt) {
+    int how = span_lazily;
+    renew_stretch(t);                   /* between two stretches: decide the next one, as the next symbol would */
+    if (t->lazy < (int32_t)total) {
+        /* no lazy stretch that long: the span walks the top of the tree as well, from exact weights */
+        if (t->complete || t->depth >= 63) { return 0; }
+        settle(t);
+        t->lazy = t->lazy_start = 0;
+        how = span_fully;
+    }
     for (uint32_t j = 0; j < kinds; j++) {
         const int32_t s = seen[j];
         if (t->up[s] < 0 || s == nyt) { return 0; }
         if (t->steps[s] == 0) { settle(t); make_plan(t, s); }
         if (t->steps[s] == plan_too_deep) { return 0; }
     }
+    return how;
+}
+
+static inline __attribute__((always_inline))
+int span_apply(struct sqz_tree* t, const uint16_t* seen, uint32_t kinds, const uint16_t* count,
+               uint64_t* start, uint8_t* suspect, const int usual, const int how) {
     keep_weights(t, start);
     uint64_t* const freq = t->freq;
-    int64_t fires = 0;
+    int64_t any = 0;
 #define SQZ_BLOCK_STEP(k_) do {                                                              \
         const int64_t w_ = (int64_t)freq[plan[k_]] + c;                                      \
         fires |= (int64_t)start[plan[plan_levels + (k_)]] - w_;                              \
@@ -725,48 +761,136 @@ int tree_count_block(struct sqz_tree* t, const uint16_t* seen, uint32_t kinds, c
         const int32_t s = seen[j];
         const int64_t c = count[s];
         const uint16_t* const plan = t->plan + (size_t)s * 2 * plan_levels;
+        int64_t fires = 0;
         SQZ_BLOCK_STEP(0);
+        if (how == span_fully) {
+            for (int k = 1; k <= top_levels; k++) { SQZ_BLOCK_STEP(k); }
+        }
 #pragma GCC unroll 16
         for (int k = top_levels + 1; k < usual; k++) { SQZ_BLOCK_STEP(k); }
         if (t->steps[s] != usual) {
             for (int k = usual; k < plan_levels; k++) { SQZ_BLOCK_STEP(k); }
         }
+        suspect[j] = (uint8_t)((uint64_t)fires >> 63);   /* some node on this leaf's walk, as far as it got */
+        any |= fires;
     }
 #undef SQZ_BLOCK_STEP
-    if (fires < 0) {
-        restore_weights(t, start);
-        return 0;
+    return any >= 0;
+}
+
+enum { culprits_most = 8 };
+struct culprits {                       /* nodes that may have outgrown their comparators during a span */
+    int32_t count;                      /* -1: more than culprits_most */
+    uint16_t node[culprits_most], over[culprits_most];
+};
+
+/* after a span_apply that returned 0, before the weights are restored */
+static void span_culprits(const struct sqz_tree* t, const uint16_t* seen, uint32_t kinds,
+                          const uint64_t* start, const uint8_t* suspect, const int how, struct culprits* who) {
+    const uint64_t* const freq = t->freq;
+    who->count = 0;
+    for (uint32_t j = 0; j < kinds; j++) {
+        /* a node outgrows its comparator at the latest when the last leaf below it has walked, so it
+         * shows in that leaf's verdict */
+        if (!suspect[j]) { continue; }
+        const int32_t s = seen[j];
+        const uint16_t* const plan = t->plan + (size_t)s * 2 * plan_levels;
+        const int steps = t->steps[s];
+        for (int k = 0; k < steps; k++) {
+            if (how == span_lazily && k >= 1 && k <= top_levels) { continue; }   /* not walked, not judged */
+            const uint16_t node = plan[k], over = plan[plan_levels + k];
+            if ((int64_t)start[over] - (int64_t)freq[node] >= 0) { continue; }
+            int known = 0;
+            for (int32_t q = 0; q < who->count; q++) { known |= who->node[q] == node; }
+            if (known) { continue; }
+            if (who->count == culprits_most) { who->count = -1; return; }
+            who->node[who->count] = node;
+            who->over[who->count] = over;
+            who->count++;
+        }
     }
-    t->lazy -= (int32_t)total;
+}
+
+static inline void span_done(struct sqz_tree* t, uint32_t total, const int how) {
+    if (how == span_lazily) { t->lazy -= (int32_t)total; }
+    else { t->eager = t->eager > (int32_t)total ? t->eager - (int32_t)total : 0; }
+}
+
+/* Which leaves lie below a culprit (bit q of below[s]) or below its comparator (bit q of beside[s]),
+ * by walking the two subtrees (small ones as a rule: what reorders is deep in the tree); and the
+ * same as lists: crowd[edge[2q] .. edge[2q+1]) the leaves below culprit q, crowd[edge[2q+1] ..
+ * edge[2q+2]) those below its comparator.  0 when the lists do not fit.                          */
+enum { crowd_most = 512 };
+
+static int mark_below(const struct sqz_tree* t, int32_t top, uint8_t bit, uint8_t* mark,
+                      uint16_t* crowd, uint32_t* filled) {
+    int16_t stack[2 * sqz_lit_symbols];
+    int sp = 0;
+    if (top >= 2 * t->n - 1) { return 1; }           /* the comparators "always" and "never": no leaves */
+    stack[sp++] = (int16_t)top;
+    while (sp > 0) {
+        const int32_t i = stack[--sp];
+        if (i < t->n) {
+            mark[i] |= bit;
+            if (*filled == crowd_most) { return 0; }
+            crowd[(*filled)++] = (uint16_t)i;
+            continue;
+        }
+        if (t->lo[i] >= 0) { stack[sp++] = t->lo[i]; }
+        if (t->hi[i] >= 0) { stack[sp++] = t->hi[i]; }
+    }
     return 1;
 }
 
-/* count the symbols of the words [0, n) into one part's tallies */
+static int culprit_leaves(const struct sqz_tree* t, const struct culprits* who, uint8_t* below, uint8_t* beside,
+                          uint16_t* crowd, uint32_t* edge) {
+    uint32_t filled = 0;
+    int fits = 1;
+    memset(below, 0, (size_t)t->n);
+    memset(beside, 0, (size_t)t->n);
+    for (int32_t q = 0; q < who->count; q++) {
+        edge[2 * q] = filled;
+        fits &= mark_below(t, who->node[q], (uint8_t)(1u << q), below, crowd, &filled);
+        edge[2 * q + 1] = filled;
+        fits &= mark_below(t, who->over[q], (uint8_t)(1u << q), beside, crowd, &filled);
+    }
+    edge[2 * who->count] = filled;
+    return fits;
+}
+
+/* count the symbols of the words [0, n) into one part's tallies (n <= part_tokens) */
 static __attribute__((noinline))
 void tally_words(uint16_t* lit_count, uint16_t* pos_count, const uint32_t* words, uint32_t n) {
+    /* whether a token is a match cannot be predicted: no branch on it -- every token stores its
+     * distance field, the position only moves on behind a match (bit 8 of the symbol) */
+    uint8_t far[part_tokens + 1];
+    uint32_t matches = 0;
     for (uint32_t k = 0; k < n; k++) {
         const uint32_t w = words[k];
-        /* a literal (bit 8 of the symbol clear; its distance field is 0) counts into one of eight idle
-         * slots instead: one slot would chain every literal's load-add-store to the one before.  No
-         * branch: which of the two a token is cannot be predicted */
-        const uint32_t slot = ((w >> 14) & 31) | ((0u - ((~w >> 8) & 1)) & (sqz_pos_symbols | (k & 7)));
         lit_count[w & 0x1FF]++;
-        pos_count[slot]++;
+        far[matches] = (uint8_t)((w >> 14) & 31);
+        matches += (w >> 8) & 1;
     }
+    for (uint32_t k = 0; k < matches; k++) { pos_count[far[k]]++; }
 }
 
 /* The symbol words [0, n) -- parts [first, first + parts) of the block tallied in y -- on both trees
- * as one span.  1 = done; 0 = nothing changed.  Words that are no symbol words never pass (their
- * symbol is not in the tree, or is the escape) except for flaws the model does not look at -- the
- * emitter reports those.                                                                        */
+ * as one span; words[0] is word `offset` of that block.  Returns n: done.  -1: nothing changed and the span cannot go as one (a symbol without
+ * a leaf, no lazy stretch, too many culprits).  0 <= t < n: nothing changed; the words before t can
+ * go as one span and word t is the first at which a node may outgrow its comparator -- found by
+ * walking the words with the start weights of the culprits and their comparators, counting who is
+ * below which (exact for those pairs; every other pair passed the end-against-start test).  When no
+ * word is one, the span stands although that test failed.  Words that are no symbol words never
+ * pass (their symbol is not in the tree, or is the escape) except for flaws the model does not look
+ * at -- the emitter reports those.                                                              */
 #ifdef SQZ_STATS
-uint64_t st_tries[3], st_fails[3], st_one, st_kinds, st_t[4], st_lv[3][2][2], st_kl[3][2];
+uint64_t st_calls, st_tok, st_ok, st_okscan, st_refused, st_cut, st_cut_at, st_culprits, st_toomany, st_one, st_t[4];
 #include <x86intrin.h>
 #endif
-static int count_span(struct sqz* s, struct tally* y, const uint32_t* words, uint32_t n,
-                      uint32_t first, uint32_t parts, uint64_t* matches_) {
+static int32_t count_span(struct sqz* s, struct tally* y, const uint32_t* words, uint32_t offset, uint32_t n,
+                          uint32_t first, uint32_t parts, uint64_t* matches_) {
 #ifdef SQZ_STATS
-    const int lv = parts > 4 ? 0 : parts > 1 ? 1 : 2; st_tries[lv]++; uint64_t t0 = __rdtsc();
+    st_calls++; st_tok += n; const uint64_t t0_ = __rdtsc();
 #endif
     struct sqz_tree* const lit = &s->lit;
     struct sqz_tree* const pos = &s->pos;
@@ -791,38 +915,119 @@ static int count_span(struct sqz* s, struct tally* y, const uint32_t* words, uin
         lit_kinds += y->lit_count[k] != 0;
     }
     for (uint32_t k = sqz_lit_nyt + 1; k < sqz_lit_symbols; k++) { strays |= y->lit_count[k]; }
-    if (strays != 0) { return 0; }                   /* symbols no tree has */
+    if (strays != 0) { return -1; }                  /* symbols no tree has */
     for (uint32_t pb = 0; pb < sqz_pos_symbols; pb++) {
         y->pos_seen[pos_kinds] = (uint16_t)pb;
         pos_kinds += y->pos_count[pb] != 0;
         matches += y->pos_count[pb];
     }
+    const int lit_how = span_ready(lit, y->lit_seen, lit_kinds, n, sqz_lit_nyt);
+    const int pos_how = lit_how == 0 ? 0 : span_ready(pos, y->pos_seen, pos_kinds, matches, sqz_pos_nyt);
+    if (lit_how == 0 || pos_how == 0) {
+#ifdef SQZ_STATS
+        st_refused++;
+#endif
+        return -1;
+    }
 #ifdef SQZ_SELFCHECK
     settle(lit); settle(pos);           /* so that the replay below starts from the very same weights */
 #endif
 #ifdef SQZ_STATS
-    st_kinds += lit_kinds; uint64_t t1 = __rdtsc(); st_t[0] += t1 - t0;
+    const uint64_t t1_ = __rdtsc(); st_t[0] += t1_ - t0_;
 #endif
-    int ok = tree_count_block(pos, y->pos_seen, pos_kinds, y->pos_count, matches, y->pos_start,
-                              pos_plan, sqz_pos_nyt);
-    if (ok && !tree_count_block(lit, y->lit_seen, lit_kinds, y->lit_count, n, y->lit_start,
-                                lit_plan, sqz_lit_nyt)) {
-        ok = 0;
-        if (matches != 0) { restore_weights(pos, y->pos_start); pos->lazy += (int32_t)matches; }
-    }
-    if (ok) { *matches_ += matches; }
+    const int pos_fine = span_apply(pos, y->pos_seen, pos_kinds, y->pos_count, y->pos_start, y->pos_suspect, pos_plan, pos_how);
+    const int lit_fine = span_apply(lit, y->lit_seen, lit_kinds, y->lit_count, y->lit_start, y->lit_suspect, lit_plan, lit_how);
+    int32_t reach = (int32_t)n;
 #ifdef SQZ_STATS
-    { const uint64_t t2 = __rdtsc(); st_t[1] += t2 - t1; if (!ok) st_fails[lv]++; st_lv[lv][ok][0] += t1 - t0; st_lv[lv][ok][1] += t2 - t1; st_kl[lv][ok] += lit_kinds; }
+    const uint64_t t2_ = __rdtsc(); st_t[1] += t2_ - t1_;
 #endif
+    if (!pos_fine || !lit_fine) {
+        struct culprits lit_who = { 0, { 0 }, { 0 } }, pos_who = { 0, { 0 }, { 0 } };
+        if (!lit_fine) { span_culprits(lit, y->lit_seen, lit_kinds, y->lit_start, y->lit_suspect, lit_how, &lit_who); }
+        if (!pos_fine) { span_culprits(pos, y->pos_seen, pos_kinds, y->pos_start, y->pos_suspect, pos_how, &pos_who); }
+        if (lit_who.count < 0 || pos_who.count < 0) {
+            reach = -1;
+        } else {
+            int64_t lit_lead[culprits_most], pos_lead[culprits_most];   /* comparator's weight - culprit's */
+            for (int32_t q = 0; q < lit_who.count; q++) {
+                lit_lead[q] = (int64_t)y->lit_start[lit_who.over[q]] - (int64_t)y->lit_start[lit_who.node[q]];
+            }
+            for (int32_t q = 0; q < pos_who.count; q++) {
+                pos_lead[q] = (int64_t)y->pos_start[pos_who.over[q]] - (int64_t)y->pos_start[pos_who.node[q]];
+            }
+            uint16_t lit_crowd[crowd_most], pos_crowd[crowd_most];
+            uint32_t lit_edge[2 * culprits_most + 1], pos_edge[2 * culprits_most + 1];
+            const int listed = culprit_leaves(lit, &lit_who, y->lit_below, y->lit_beside, lit_crowd, lit_edge) &
+                               culprit_leaves(pos, &pos_who, y->pos_below, y->pos_beside, pos_crowd, pos_edge);
+            /* Row by row: a row in which a culprit cannot catch up with its comparator even if all its
+             * own symbols came first only moves the leads; the others are walked word by word. */
+            for (uint32_t r = first; r < first + parts && reach == (int32_t)n; r++) {
+                const uint32_t from = r * part_tokens > offset ? r * part_tokens - offset : 0;
+                const uint32_t to = (r + 1) * part_tokens - offset < n ? (r + 1) * part_tokens - offset : n;
+                int walk = !listed;
+                int64_t lit_gain[culprits_most], pos_gain[culprits_most];
+                for (int32_t q = 0; q < lit_who.count && !walk; q++) {
+                    int64_t own = 0, other = 0;
+                    for (uint32_t j = lit_edge[2 * q]; j < lit_edge[2 * q + 1]; j++) { own += y->lit_part[r][lit_crowd[j]]; }
+                    for (uint32_t j = lit_edge[2 * q + 1]; j < lit_edge[2 * q + 2]; j++) { other += y->lit_part[r][lit_crowd[j]]; }
+                    walk = lit_lead[q] - own < 0;
+                    lit_gain[q] = other - own;
+                }
+                for (int32_t q = 0; q < pos_who.count && !walk; q++) {
+                    int64_t own = 0, other = 0;
+                    for (uint32_t j = pos_edge[2 * q]; j < pos_edge[2 * q + 1]; j++) { own += y->pos_part[r][pos_crowd[j]]; }
+                    for (uint32_t j = pos_edge[2 * q + 1]; j < pos_edge[2 * q + 2]; j++) { other += y->pos_part[r][pos_crowd[j]]; }
+                    walk = pos_lead[q] - own < 0;
+                    pos_gain[q] = other - own;
+                }
+                if (!walk) {
+                    for (int32_t q = 0; q < lit_who.count; q++) { lit_lead[q] += lit_gain[q]; }
+                    for (int32_t q = 0; q < pos_who.count; q++) { pos_lead[q] += pos_gain[q]; }
+                    continue;
+                }
+                for (uint32_t k = from; k < to && reach == (int32_t)n; k++) {
+                    const uint32_t w = words[k], sym = w & 0x1FF;
+                    /* a symbol's walk adds 1 to every node above it, then each is compared with its
+                     * comparator; the comparator is never on the same walk */
+                    for (uint32_t x = y->lit_below[sym]; x != 0; x &= x - 1) {
+                        if (--lit_lead[__builtin_ctz(x)] < 0) { reach = (int32_t)k; }
+                    }
+                    for (uint32_t c = y->lit_beside[sym]; c != 0; c &= c - 1) { lit_lead[__builtin_ctz(c)]++; }
+                    if (sym >= len_symbol0 && pos_who.count != 0) {
+                        const uint32_t pb = (w >> 14) & 31;
+                        for (uint32_t x = y->pos_below[pb]; x != 0; x &= x - 1) {
+                            if (--pos_lead[__builtin_ctz(x)] < 0) { reach = (int32_t)k; }
+                        }
+                        for (uint32_t c = y->pos_beside[pb]; c != 0; c &= c - 1) { pos_lead[__builtin_ctz(c)]++; }
+                    }
+                }
+            }
+        }
+#ifdef SQZ_STATS
+        st_t[3] += __rdtsc() - t2_;
+        st_culprits += lit_who.count + pos_who.count; if (reach < 0) st_toomany++; else if (reach == (int32_t)n) st_okscan++; else { st_cut++; st_cut_at += reach; }
+#endif
+        if (reach != (int32_t)n) {
+            restore_weights(lit, y->lit_start);
+            restore_weights(pos, y->pos_start);
+            return reach;
+        }
+    }
+#ifdef SQZ_STATS
+    st_ok++;
+#endif
+    span_done(lit, n, lit_how);
+    span_done(pos, matches, pos_how);
+    *matches_ += matches;
 #ifdef SQZ_SELFCHECK
-    if (ok) {
+    {
         /* the same symbols one by one from the same start: no reordering, the same weights */
         static _Thread_local uint64_t lit_after[2 * sqz_lit_symbols - 1], pos_after[2 * sqz_pos_symbols - 1];
         settle(lit); settle(pos);
         memcpy(lit_after, lit->freq, sizeof(lit_after));
         memcpy(pos_after, pos->freq, sizeof(pos_after));
         restore_weights(lit, y->lit_start);
-        if (matches != 0) { restore_weights(pos, y->pos_start); }
+        restore_weights(pos, y->pos_start);
         lit->lazy = lit->lazy_start = lit->eager = 0;       /* the top is exact, nothing is decided */
         pos->lazy = pos->lazy_start = pos->eager = 0;
         const uint64_t shape = selfcheck_relabels;
@@ -840,10 +1045,8 @@ static int count_span(struct sqz* s, struct tally* y, const uint32_t* words, uin
         }
         selfcheck(lit); selfcheck(pos);
     }
-#else
-    (void)words;
 #endif
-    return ok;
+    return (int32_t)n;
 }
 
 /* ======================================================================== *
@@ -1253,24 +1456,39 @@ static int pass_one_by_one(struct pass* p, uint64_t k, uint64_t until) {
     return model_one_by_one(p, k, until) == until;
 }
 
-/* The tokens [k, k + n) = parts [first, first + parts) of the tallied block: as one span if that
- * passes, else its quarters, else its parts, else one by one.  1 = go on, 0 = stop.             */
-static int pass_span(struct pass* p, uint64_t k, uint32_t n, uint32_t first, uint32_t parts) {
-    if (count_span(p->s, p->y, p->words + k, n, first, parts, &p->matches)) {
-        if (p->ct != NULL) {
-            /* no code changed while the span was counted: its bits are those of the codes as they are */
-            emit_run(&p->s->error, p->s->bs, p->words, k, k + n, p->ct);
-            return p->s->error == 0;
-        }
-        return 1;
+/* The rows of tallies of a block are aligned to the block: row r holds tokens [r * part_tokens,
+ * (r + 1) * part_tokens) of it -- or, at either end of what is left of the block, the part of that
+ * range that is left (pass_block tallies such a row again).                                     */
+static void tally_row(struct pass* p, uint64_t block, uint32_t row, uint32_t lo, uint32_t hi) {
+    struct tally* const y = p->y;
+    const uint32_t from = lo > row * part_tokens ? lo : row * part_tokens;
+    const uint32_t to = hi < (row + 1) * part_tokens ? hi : (row + 1) * part_tokens;
+    memset(y->lit_part[row], 0, sizeof(y->lit_part[row]));
+    memset(y->pos_part[row], 0, sizeof(y->pos_part[row]));
+    if (from < to) { tally_words(y->lit_part[row], y->pos_part[row], p->words + block + from, to - from); }
+}
+
+static int pass_emit(struct pass* p, uint64_t from, uint64_t until) {
+    if (p->ct == NULL) { return 1; }
+    /* no code changed while the span was counted: its bits are those of the codes as they are */
+    emit_run(&p->s->error, p->s->bs, p->words, from, until, p->ct);
+    return p->s->error == 0;
+}
+
+/* The tokens [lo, hi) of the block that starts at word `block`, tallied in rows [row, row + rows):
+ * as one span if that passes, else by groups of four rows, else row by row, else one by one -- the
+ * way for spans that cannot be helped by finding the one word that matters.  1 = go on, 0 = stop. */
+static int pass_rows(struct pass* p, uint64_t block, uint32_t lo, uint32_t hi, uint32_t row, uint32_t rows) {
+    if (count_span(p->s, p->y, p->words + block + lo, lo, hi - lo, row, rows, &p->matches) == (int32_t)(hi - lo)) {
+        return pass_emit(p, block + lo, block + hi);
     }
-    if (parts == 1) { return pass_one_by_one(p, k, k + n); }
-    const uint32_t step = parts > 4 ? 4 : 1;
-    for (uint32_t q = 0; q < parts; q += step) {
-        const uint32_t some = parts - q < step ? parts - q : step;
-        const uint32_t from = q * part_tokens;
-        const uint32_t to = (q + some) * part_tokens < n ? (q + some) * part_tokens : n;
-        if (!pass_span(p, k + from, to - from, first + q, some)) { return 0; }
+    if (rows == 1) { return pass_one_by_one(p, block + lo, block + hi); }
+    const uint32_t step = rows > 4 ? 4 : 1;
+    for (uint32_t q = 0; q < rows; q += step) {
+        const uint32_t some = rows - q < step ? rows - q : step;
+        const uint32_t from = lo > (row + q) * part_tokens ? lo : (row + q) * part_tokens;
+        const uint32_t to = hi < (row + q + some) * part_tokens ? hi : (row + q + some) * part_tokens;
+        if (from < to && !pass_rows(p, block, from, to, row + q, some)) { return 0; }
     }
     return 1;
 }
@@ -1278,27 +1496,71 @@ static int pass_span(struct pass* p, uint64_t k, uint32_t n, uint32_t first, uin
 /* the next block of the chunk, at most up to `until`; returns the tokens dealt with (fewer than it
  * took on when something stopped the pass: p->flaw, p->eyes->error, p->s->error) */
 static uint64_t pass_block(struct pass* p, uint64_t k, uint64_t until) {
-    struct tally* const y = p->y;
     const struct sqz_tree* const lit = &p->s->lit;
-    uint64_t n = until - k < block_most ? until - k : block_most;
-    if ((int64_t)n > lit->lazy) { n = lit->lazy > 0 ? (uint64_t)lit->lazy : 0; }
-    if (n < block_least) {              /* no lazy stretch is on (or it ends): the one-by-one path renews it */
-        n = until - k < block_least ? until - k : block_least;
+    uint64_t most = until - k < block_most ? until - k : block_most;
+    if ((int64_t)most > lit->lazy) { most = lit->lazy > 0 ? (uint64_t)lit->lazy : 0; }
+    if (most < block_least) {           /* no lazy stretch is on (or it ends): the one-by-one path renews it */
+        most = until - k < block_least ? until - k : block_least;
         if (p->ct != NULL) {
-            p->matches += code_one_by_one(p->s, p->words, k, k + n);
-            return n;
+            p->matches += code_one_by_one(p->s, p->words, k, k + most);
+            return most;
         }
-        return model_one_by_one(p, k, k + n) - k;
+        return model_one_by_one(p, k, k + most) - k;
     }
-    const uint32_t parts = (uint32_t)((n + part_tokens - 1) / part_tokens);
-    for (uint32_t q = 0; q < parts; q++) {
-        const uint64_t from = k + (uint64_t)q * part_tokens;
-        const uint64_t to = from + part_tokens < k + n ? from + part_tokens : k + n;
-        tally_words(y->lit_part[q], y->pos_part[q], p->words + from, (uint32_t)(to - from));
+    const uint32_t n = (uint32_t)most;
+    const uint32_t rows = (n + part_tokens - 1) / part_tokens;
+    for (uint32_t r = 0; r < rows; r++) { tally_row(p, k, r, 0, n); }
+    uint32_t lo = 0;
+    int went = 1;
+    while (lo < n && went) {
+        const uint32_t row = lo / part_tokens;
+        const int32_t reach = count_span(p->s, p->y, p->words + k + lo, lo, n - lo, row, rows - row, &p->matches);
+        if (reach == (int32_t)(n - lo)) {
+            went = pass_emit(p, k + lo, k + n);
+            lo = n;
+        } else if (reach < 0) {
+            /* a symbol without a leaf yet, a tree between two lazy stretches, a crowd of culprits: up to
+             * the end of the row one by one (that settles the first two as a rule), then the rest again */
+            const uint32_t to = (row + 1) * part_tokens < n ? (row + 1) * part_tokens : n;
+            went = pass_one_by_one(p, k + lo, k + to);
+            lo = to;
+            if (went) {
+                renew_stretch(&p->s->lit);
+                renew_stretch(&p->s->pos);
+            }
+            if (went && lo < n && p->s->lit.lazy < (int32_t)(n - lo)) {
+                for (uint32_t r = 0; r < rows; r++) { tally_row(p, k, r, 0, 0); }
+                return lo;
+            }
+        } else {
+            /* everything before word `at` as one span (it passes: the words that matter were walked),
+             * that word by itself -- it may reorder the tree --, then what is left of the block */
+            const uint32_t at = lo + (uint32_t)reach;
+            if (at - lo >= block_least) {
+                const uint32_t last = (at - 1) / part_tokens;
+                tally_row(p, k, last, lo, at);
+                went = pass_rows(p, k, lo, at, row, last - row + 1);
+            } else if (at > lo) {
+                went = pass_one_by_one(p, k + lo, k + at);
+            }
+            if (went) { went = pass_one_by_one(p, k + at, k + at + 1); }
+            lo = at + 1;
+            if (went) {                 /* a reordering ends the lazy stretch of its tree */
+                renew_stretch(&p->s->lit);
+                renew_stretch(&p->s->pos);
+            }
+            if (went && lo < n && p->s->lit.lazy < (int32_t)(n - lo)) {
+                /* no stretch long enough for what is left: it is another block's */
+                for (uint32_t r = 0; r < rows; r++) { tally_row(p, k, r, 0, 0); }
+                return lo;
+            }
+            if (lo < n) { tally_row(p, k, lo / part_tokens, lo, n); }
+        }
     }
-    const int went = pass_span(p, k, (uint32_t)n, 0, parts);
-    memset(y->lit_part, 0, sizeof(y->lit_part[0]) * parts);
-    memset(y->pos_part, 0, sizeof(y->pos_part[0]) * parts);
+    for (uint32_t r = 0; r < rows; r++) {
+        memset(p->y->lit_part[r], 0, sizeof(p->y->lit_part[r]));
+        memset(p->y->pos_part[r], 0, sizeof(p->y->pos_part[r]));
+    }
     if (!went && p->flaw) {             /* where the model stopped is what its caller wants to know */
         return p->eyes->k_now - k;
     }
@@ -1878,15 +2140,20 @@ static int host_cores(void) {
 
 /* after coder_begin: start the threads coder_threads asks for (0: by the stream's length and the
  * host's cores); 0 = none were started (not wanted, or not to be had), one thread will do */
-static int team_start(struct sqz* s, struct team* t, uint64_t expected_tokens) {
-    t->two.d = NULL;
-    t->crew = NULL;
+static int team_size(const struct sqz* s, uint64_t expected_tokens) {
     int threads = s->coder_threads;
     if (threads <= 0) {
         const int cores = host_cores();
         threads = expected_tokens < duo_least || cores < 2 ? 1 :
                   expected_tokens < crew_least || cores < 8 ? 2 : 4;
     }
+    return threads;
+}
+
+static int team_start(struct sqz* s, struct team* t, uint64_t expected_tokens) {
+    t->two.d = NULL;
+    t->crew = NULL;
+    int threads = team_size(s, expected_tokens);
     if (threads >= 3) {
         t->crew = crew_start(s, threads - 1);
         if (t->crew != NULL) { return 1; }
@@ -1981,27 +2248,48 @@ void sqz_compress(struct sqz* s, struct sqz_bitstream* bs,
      * while the host entropy-codes chunk k the device already searches chunk k+1. */
     sqz_gpu_stream* st = NULL;
     double t_search = 0, t_code = 0, t0 = now_seconds();
+    /* The stream's own chunking (2, 4, 8, 16, then 32 MiB) suits a coder that is slower than the search:
+     * it starts after milliseconds.  A crew is faster than the search; then what counts is that the
+     * device works on chunks of a size it is efficient at: a quarter of the input each, between 4 and
+     * 32 MiB, the first two shorter (the coder's first tokens are its slowest: every symbol is new). */
+    size_t chunk = 0;
+    if (team_size(s, bytes / 2) >= 3) {
+        const uint64_t quarter = ((bytes / 4) | 0xFFFFF) + 1;
+        chunk = (size_t)(quarter < ((uint64_t)4 << 20) ? (uint64_t)4 << 20 :
+                         quarter > ((uint64_t)32 << 20) ? (uint64_t)32 << 20 : quarter);
+    }
     int r = sqz_gpu_stream_open(&st, s->device, data, (size_t)bytes, window,
-                                sqz_min_len, sqz_max_len, window - 1, 0, SQZ_GPU_STREAM_SYMBOLS);
+                                sqz_min_len, sqz_max_len, window - 1, chunk,
+                                SQZ_GPU_STREAM_SYMBOLS | (chunk != 0 ? SQZ_GPU_STREAM_SHORT_START : 0));
     t_search += now_seconds() - t0;
     if (r != 0) { s->error = r; return; }
     struct team run;
     const int two = team_start(s, &run, bytes / 2);    /* about 0.6 tokens per byte on mixed data */
+    const int trace = getenv("SQZ_TRACE") != NULL;     /* per-chunk times on stderr */
+    const double t_begin = t0;
+    if (trace) { fprintf(stderr, "sqz_compress: open + team %.1f ms\n", 1e3 * (now_seconds() - t_begin)); }
     for (;;) {
         const uint32_t* words = NULL;
         size_t count = 0;
         t0 = now_seconds();
         r = sqz_gpu_stream_next(st, &words, &count);
-        t_search += now_seconds() - t0;
+        const double t1 = now_seconds();
+        t_search += t1 - t0;
         if (r != 0) { s->error = r; break; }
         if (count == 0) { break; }
-        t0 = now_seconds();
         if (two) { team_emit(s, &run, words, count); } else { code_symbols(s, words, count); }
-        t_code += now_seconds() - t0;
+        const double t2 = now_seconds();
+        t_code += t2 - t1;
+        if (trace) {
+            fprintf(stderr, "sqz_compress: at %.1f ms: waited %.1f ms, coded %zu tokens in %.1f ms\n",
+                    1e3 * (t0 - t_begin), 1e3 * (t1 - t0), count, 1e3 * (t2 - t1));
+        }
         if (s->error != 0) { break; }
     }
+    t0 = now_seconds();
     if (two) { team_finish(s, &run); }
     sqz_gpu_stream_close(st);
+    if (trace) { fprintf(stderr, "sqz_compress: close %.1f ms, all %.1f ms\n", 1e3 * (now_seconds() - t0), 1e3 * (now_seconds() - t_begin)); }
     if (s->error == 0) { pad_to_word(bs); s->error = bs->error; }
     s->search_seconds = t_search;
     s->entropy_seconds = t_code;

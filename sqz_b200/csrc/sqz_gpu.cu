@@ -1027,8 +1027,10 @@ tokens_to_host(const uint32_t* __restrict__ d_tokens, const uint64_t* __restrict
 
 struct Slot {
     cudaStream_t stream = nullptr;
+    cudaStream_t ahead_of_all = nullptr;   // highest priority: a consumer's parse and token copy (kModeTokensPinned)
     cudaEvent_t done = nullptr;       // everything of the chunk has been issued and finished
     cudaEvent_t parsed = nullptr;     // the chunk's token count and overshoot are in h_result
+    cudaEvent_t tabled = nullptr;     // the chunk's match table is complete
     uint8_t* d_data = nullptr;        // back halo + chunk + ahead halo
     uint32_t* d_table = nullptr;
     uint32_t* d_tokens = nullptr;
@@ -1066,6 +1068,7 @@ struct sqz_gpu_stream {
     Slot slot[2];
     const uint64_t* prev_result = nullptr;   // device: previous chunk's result (entry hand-off)
     cudaEvent_t prev_parsed = nullptr;
+    cudaEvent_t prev_tabled = nullptr;
 };
 
 // the calling thread's current device is the caller's business: every entry point that has to
@@ -1083,6 +1086,8 @@ static void slot_free(Slot& s) {
     cudaFreeHost(s.h_result); cudaFreeHost(s.h_tokens);
     if (s.done) { cudaEventDestroy(s.done); }
     if (s.parsed) { cudaEventDestroy(s.parsed); }
+    if (s.tabled) { cudaEventDestroy(s.tabled); }
+    if (s.ahead_of_all) { cudaStreamSynchronize(s.ahead_of_all); cudaStreamDestroy(s.ahead_of_all); }
     if (s.stream) { cudaStreamDestroy(s.stream); }
     s = Slot();
 }
@@ -1092,6 +1097,7 @@ static int slot_alloc(Slot& s, int device, size_t chunk, uint32_t max_len, uint3
     CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&s.parsed, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&s.tabled, cudaEventDisableTiming));
     const size_t data_bytes = (size_t)max_dist + chunk + max_len + 64;
     CU(cudaMalloc(&s.d_data, data_bytes));
     CU(cudaMalloc(&s.d_table, chunk * 4));
@@ -1106,6 +1112,9 @@ static int slot_alloc(Slot& s, int device, size_t chunk, uint32_t max_len, uint3
         if (mode == kModeTokensPinned) {
             CU(cudaHostAlloc(&s.h_tokens, chunk * 4 + 16, cudaHostAllocDefault));
             s.pinned_bytes = chunk * 4 + 16;
+            int least = 0, greatest = 0;
+            CU(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+            CU(cudaStreamCreateWithPriority(&s.ahead_of_all, cudaStreamNonBlocking, greatest));
         }
     } else {
         CU(cudaMalloc(&s.d_len, chunk * 2));
@@ -1209,25 +1218,38 @@ static int stream_launch_next(sqz_gpu_stream* st, uint16_t* len_out, uint16_t* d
     CU(cudaMemcpyAsync(s.d_data, st->data + first - back, back + n + ahead,
                        cudaMemcpyHostToDevice, s.stream));
     const uint8_t* d_shard = s.d_data + back;
+    if (st->mode == kModeTokensPinned && st->prev_tabled != nullptr) {
+        // A consumer waits for the chunks in order: two searches sharing the device would both be ready
+        // late.  This chunk's search starts when the one before has its table; only that one's parse and
+        // copy run beside it.
+        CU(cudaStreamWaitEvent(s.stream, st->prev_tabled, 0));
+    }
     if (int r = sqz_gpu_match_table_device_ws(d_shard, back, n, ahead, st->min_len, st->max_len,
                                               st->max_dist, s.d_table, s.d_mwork, s.stream)) { return r; }
+    CU(cudaEventRecord(s.tabled, s.stream));
+    st->prev_tabled = s.tabled;
+    // A consumer's parse and token copy go on a stream of the highest priority: the next chunk's search
+    // is queued behind this one's and fills the device as soon as it may -- at equal priority the few
+    // small kernels that finish this chunk would wait for free CTA slots until that search is over.
+    cudaStream_t late = st->mode == kModeTokensPinned ? s.ahead_of_all : s.stream;
+    if (late != s.stream) { CU(cudaStreamWaitEvent(late, s.tabled, 0)); }
     if (st->mode != kModeTable) {
         const uint32_t* d_entry = nullptr;
         if (st->prev_result != nullptr) {
-            CU(cudaStreamWaitEvent(s.stream, st->prev_parsed, 0));
+            CU(cudaStreamWaitEvent(late, st->prev_parsed, 0));
             d_entry = reinterpret_cast<const uint32_t*>(st->prev_result + 1);  // low half of overshoot
         }
         if (int r = parse_launch(d_shard, s.d_table, n, d_entry, 0, st->min_len, st->max_len,
-                                 s.d_tokens, n, s.d_work, s.d_result, s.stream, st->symbols)) { return r; }
-        CU(cudaMemcpyAsync(s.h_result, s.d_result, 16, cudaMemcpyDeviceToHost, s.stream));
-        CU(cudaEventRecord(s.parsed, s.stream));
+                                 s.d_tokens, n, s.d_work, s.d_result, late, st->symbols)) { return r; }
+        CU(cudaMemcpyAsync(s.h_result, s.d_result, 16, cudaMemcpyDeviceToHost, late));
+        CU(cudaEventRecord(s.parsed, late));
         st->prev_parsed = s.parsed;
         st->prev_result = s.d_result;
         if (st->mode == kModeTokensPinned) {
             // the tokens follow right away, exactly as many as there are: the consumer finds them
             // in pinned memory when it asks
             const unsigned grid = (unsigned)std::min<size_t>((n / 4 + 255) / 256 + 1, (size_t)sm_count() * 4);
-            tokens_to_host<<<grid, 256, 0, s.stream>>>(s.d_tokens, s.d_result, s.h_tokens);
+            tokens_to_host<<<grid, 256, 0, late>>>(s.d_tokens, s.d_result, s.h_tokens);
             LAUNCHED("tokens_to_host");
         }
         // kModeTokensDirect: the caller copies count x 4 bytes to their final place once it knows the count
@@ -1235,6 +1257,10 @@ static int stream_launch_next(sqz_gpu_stream* st, uint16_t* len_out, uint16_t* d
         if (int r = sqz_gpu_unpack_table_device(s.d_table, n, s.d_len, s.d_dist, s.stream)) { return r; }
         CU(cudaMemcpyAsync(len_out + first, s.d_len, n * 2, cudaMemcpyDeviceToHost, s.stream));
         CU(cudaMemcpyAsync(dist_out + first, s.d_dist, n * 2, cudaMemcpyDeviceToHost, s.stream));
+    }
+    if (late != s.stream) {             // the slot is free when both streams are through
+        CU(cudaEventRecord(s.done, late));
+        CU(cudaStreamWaitEvent(s.stream, s.done, 0));
     }
     CU(cudaEventRecord(s.done, s.stream));
     s.busy = true;
@@ -1252,7 +1278,7 @@ static size_t default_chunk(size_t bytes, bool consumer) {
 
 static int stream_open(sqz_gpu_stream** out, int device, const uint8_t* data, size_t bytes,
                        uint32_t window, uint32_t min_len, uint32_t max_len, uint32_t max_dist,
-                       size_t chunk, int mode) {
+                       size_t chunk, int mode, bool short_start = false) {
     *out = nullptr;
     if (int r = check_rules(min_len, max_len, max_dist)) { return r; }
     if (window == 0 || (window & (window - 1)) != 0 || max_dist > window) {
@@ -1270,6 +1296,7 @@ static int stream_open(sqz_gpu_stream** out, int device, const uint8_t* data, si
     st->mode = mode;
     // token streams with the default chunking start with short chunks: 2, 4, 8, 16 MiB, then 32 MiB
     if (mode == kModeTokensPinned && chunk == 0 && st->chunk > ((size_t)2 << 20)) { st->ramp = (size_t)2 << 20; }
+    if (short_start && chunk >= ((size_t)4 << 20)) { st->ramp = chunk / 4; }
     const int slots = bytes > (st->ramp ? st->ramp : st->chunk) ? 2 : 1;
     for (int k = 0; k < slots && bytes > 0; k++) {
         if (int r = slot_take(st->slot[k], device, st->chunk, max_len, max_dist, mode)) {
@@ -1286,13 +1313,15 @@ extern "C" int sqz_gpu_stream_open(sqz_gpu_stream** st, int device, const uint8_
                                    uint32_t max_len, uint32_t max_dist, size_t chunk_bytes,
                                    uint32_t flags) {
     if (st == nullptr) { return fail(EINVAL, "null stream handle"); }
-    if ((flags & ~(uint32_t)SQZ_GPU_STREAM_SYMBOLS) != 0) { return fail(EINVAL, "unknown stream flags"); }
+    if ((flags & ~(uint32_t)(SQZ_GPU_STREAM_SYMBOLS | SQZ_GPU_STREAM_SHORT_START)) != 0) {
+        return fail(EINVAL, "unknown stream flags");
+    }
     if (flags & SQZ_GPU_STREAM_SYMBOLS) {
         if (int r = check_symbol_rules(min_len, max_len, max_dist)) { return r; }
     }
     DeviceScope keep;
     if (int r = stream_open(st, device, data, bytes, window, min_len, max_len, max_dist,
-                            chunk_bytes, kModeTokensPinned)) { return r; }
+                            chunk_bytes, kModeTokensPinned, (flags & SQZ_GPU_STREAM_SHORT_START) != 0)) { return r; }
     (*st)->symbols = (flags & SQZ_GPU_STREAM_SYMBOLS) != 0;
     if (bytes > 0) {
         if (int r = stream_launch_next(*st, nullptr, nullptr)) {
@@ -1312,11 +1341,20 @@ extern "C" int sqz_gpu_stream_next(sqz_gpu_stream* st, const uint32_t** tokens, 
     DeviceScope keep;
     CU(cudaSetDevice(st->device));
     // keep the device busy: the slot the caller has just finished reading is free now
+    static const bool trace = getenv("SQZ_TRACE") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     if (st->launched < st->bytes) {
         if (int r = stream_launch_next(st, nullptr, nullptr)) { return r; }
     }
+    const auto t1 = std::chrono::steady_clock::now();
     Slot& s = st->slot[st->read_slot];
     CU(cudaEventSynchronize(s.done));
+    if (trace) {
+        const auto t2 = std::chrono::steady_clock::now();
+        fprintf(stderr, "sqz_gpu_stream_next: queued the next chunk in %.1f ms, waited %.1f ms for this one\n",
+                std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                std::chrono::duration<double, std::milli>(t2 - t1).count());
+    }
     const uint64_t n_tok = s.h_result[0];
     if (n_tok > s.n) { return fail(EIO, "parse produced more tokens than positions"); }
     s.busy = false;

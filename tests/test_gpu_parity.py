@@ -77,3 +77,23 @@ def test_config_2_far_max_len_repeats(inputs, golden, oracle, reference):
     assert comp == reference.compress(d, 15)
     t = sq.tokens(d, 1 << 15)
     assert (t == reference.tokens(comp)).all()
+
+
+def test_compress_with_every_coder_team(reference):
+    """sqz_compress on 20 MiB of the bench corpus (several chunks of the GPU stream whatever the chunking:
+    the default ramp for one and two coder threads, quarter-of-the-input chunks with a short start for
+    crews): one thread, model + emitter, crews of 2, 3 and 7 emitters and the automatic choice all give
+    the bytes of the unmodified reference's encoder on the same tokens; `into` writes the caller's buffer."""
+    from sqz_b200 import corpus
+    d = corpus.synthetic(20 << 20, 11 << 20)
+    want = reference.encode_tokens(sq.tokens(d), d.size, 15)
+    buf = np.empty(sq.capacity(d.size), np.uint8)
+    for threads in (1, 2, 3, 4, 8, 0):
+        st = {}
+        got = sq.compress(d, 15, threads=threads, stats=st, into=buf)
+        assert got.base is buf or got is buf or np.shares_memory(got, buf)
+        assert got.tobytes() == want, threads
+        assert st["tokens"] > 0 and st["matches"] > 0
+    assert sq.decompress(want) == d.tobytes()
+    with pytest.raises(ValueError):
+        sq.compress(d, 15, into=np.empty(16, np.uint8))

@@ -1,5 +1,5 @@
 """Host entropy stage alone, no GPU: tokens of a corpus prefix from the oracle (cached under .scratch/),
-then sqz_encode_symbols with one and two coder threads and sqz_decompress, best of three.
+then sqz_encode_symbols with one, two and more coder threads and sqz_decompress, best of three.
 
     python tools/bench_coder.py [MiB]
 """
@@ -25,7 +25,7 @@ else:
     np.save(cache, toks)
 words = sq.symbols_of_tokens(toks)
 ref = None
-for threads in (1, 2):
+for threads in (1, 2, 3, 4, 6, 8):
     best = 1e9
     for it in range(int(os.environ.get("REPS", "3"))):
         t0 = time.perf_counter(); comp = sq.encode_symbols(words, n, 15, threads=threads); best = min(best, time.perf_counter() - t0)
