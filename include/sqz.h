@@ -100,9 +100,11 @@ struct sqz {
     uint64_t matches;
     double   search_seconds;            /* GPU search + parse + copies */
     double   entropy_seconds;           /* host adaptive-Huffman stage */
-    int32_t  coder_threads;             /* 0 = automatic (two threads for streams of 64 Ki tokens and more),
-                                           1 = one thread, 2 = two threads: the model on a thread of its own,
-                                           the caller's thread packs the bits (sqz_codec.c); same bytes either way */
+    int32_t  coder_threads;             /* 1 = one thread; 2 = the model of both trees on a thread of its own, the
+                                           caller's thread packs the bits; n >= 3 = model thread + n - 1 emitter
+                                           threads working on segments + the caller's thread appending them in
+                                           order; 0 = automatic (1 below 64 Ki tokens, 2 below 1 Mi tokens or on
+                                           fewer than 8 cores, else 4); same bytes in every case (sqz_codec.c) */
     int32_t  reserved;
     struct sqz_tree lit;
     uint8_t len_index[sqz_max_len + 2]; /* len -> length bucket, squeeze.h:151-161.  Also keeps the two tree

@@ -658,17 +658,24 @@ static void tree_count(struct sqz_tree* t, int32_t s) {
 
 /* ======================================================================== *
  *  counting a block of symbols at once                                      *
- *  A reordering happens about once per 2700 symbols; in between the model   *
- *  only adds 1 along a path per symbol, and additions commute.  So a block  *
- *  of symbols is tallied per leaf and every distinct leaf walks its plan    *
- *  once, adding its count -- provided no walk of the block, taken one by    *
- *  one in any order, could have reordered anything: all weights only grow   *
- *  during the block, so if a node's weight at the END of the block does not *
- *  exceed its comparator's weight at the START of the block, it exceeded it *
- *  at no moment in between.  A block that fails the test is undone from the *
- *  snapshot the start weights are kept in, and its symbols go through the   *
- *  one-by-one path in smaller portions.  Exact, not approximate: the test   *
- *  only ever errs towards the slow path.                                    *
+ *  A reordering happens about once per 3600 symbols on the bench corpus; in *
+ *  between the model only adds 1 along a path per symbol, and additions     *
+ *  commute.  So a block of symbols (4096 tokens) is tallied per leaf and    *
+ *  every distinct leaf walks its plan once, adding its count -- provided no *
+ *  walk of the block, taken one by one, could have reordered anything.      *
+ *  First test, for every node walked: all weights only grow during the      *
+ *  block, so a node whose weight at the END of the block does not exceed    *
+ *  its comparator's weight at the START of the block exceeded it at no      *
+ *  moment in between, whatever the order of the symbols.  The few nodes     *
+ *  that fail it (the culprits; two near-equal siblings as a rule) get the   *
+ *  exact answer: the words are walked in order with just those nodes' and   *
+ *  their comparators' weights, counting who lies below which -- and only    *
+ *  the rows of the block's tallies in which a culprit could catch up at     *
+ *  all.  No word at which one does: the block stands.  Else everything      *
+ *  before that word is one span (it passes by construction), the word goes  *
+ *  through the one-by-one path -- it may reorder the tree --, and the rest  *
+ *  of the block goes on from its tallies.  Exact, not approximate: what is  *
+ *  not proven harmless takes the reference's walk.                          *
  * ======================================================================== */
 
 #ifndef SQZ_PART_TOKENS
@@ -697,11 +704,20 @@ struct tally {
     uint8_t pos_below[sqz_pos_symbols], pos_beside[sqz_pos_symbols];
     uint64_t lit_start[2 * sqz_lit_symbols + 1];   /* weights as they were when the span began, and */
     uint64_t pos_start[2 * sqz_pos_symbols + 1];   /* the comparators "always" (0) and "never" (2^63-1) */
+    /* Where reorderings come every few hundred tokens -- the first 100,000 tokens of any stream, bytes
+     * that are close to uniform throughout -- a block is cut so often that the one-by-one path is the
+     * faster one: after such a block the next `rest` tokens go one by one, twice as many each time it
+     * happens again (up to rest_most), and blocks are tried again after that.                        */
+    uint32_t rest, rest_next;
 };
+
+enum { rest_least = block_most, rest_most = 16 * block_most,
+       cut_every = 512 };               /* tokens per cut below which blocks do not pay */
 
 static void tally_init(struct tally* y) {
     memset(y->lit_part, 0, sizeof(y->lit_part));
     memset(y->pos_part, 0, sizeof(y->pos_part));
+    y->rest = y->rest_next = 0;
     y->lit_start[2 * sqz_lit_symbols - 1] = 0;  y->lit_start[2 * sqz_lit_symbols] = (uint64_t)INT64_MAX;
     y->pos_start[2 * sqz_pos_symbols - 1] = 0;  y->pos_start[2 * sqz_pos_symbols] = (uint64_t)INT64_MAX;
 }
@@ -883,15 +899,8 @@ void tally_words(uint16_t* lit_count, uint16_t* pos_count, const uint32_t* words
  * word is one, the span stands although that test failed.  Words that are no symbol words never
  * pass (their symbol is not in the tree, or is the escape) except for flaws the model does not look
  * at -- the emitter reports those.                                                              */
-#ifdef SQZ_STATS
-uint64_t st_calls, st_tok, st_ok, st_okscan, st_refused, st_cut, st_cut_at, st_culprits, st_toomany, st_one, st_t[4];
-#include <x86intrin.h>
-#endif
 static int32_t count_span(struct sqz* s, struct tally* y, const uint32_t* words, uint32_t offset, uint32_t n,
                           uint32_t first, uint32_t parts, uint64_t* matches_) {
-#ifdef SQZ_STATS
-    st_calls++; st_tok += n; const uint64_t t0_ = __rdtsc();
-#endif
     struct sqz_tree* const lit = &s->lit;
     struct sqz_tree* const pos = &s->pos;
     uint32_t lit_kinds = 0, pos_kinds = 0, matches = 0, strays = 0;
@@ -924,23 +933,14 @@ static int32_t count_span(struct sqz* s, struct tally* y, const uint32_t* words,
     const int lit_how = span_ready(lit, y->lit_seen, lit_kinds, n, sqz_lit_nyt);
     const int pos_how = lit_how == 0 ? 0 : span_ready(pos, y->pos_seen, pos_kinds, matches, sqz_pos_nyt);
     if (lit_how == 0 || pos_how == 0) {
-#ifdef SQZ_STATS
-        st_refused++;
-#endif
         return -1;
     }
 #ifdef SQZ_SELFCHECK
     settle(lit); settle(pos);           /* so that the replay below starts from the very same weights */
 #endif
-#ifdef SQZ_STATS
-    const uint64_t t1_ = __rdtsc(); st_t[0] += t1_ - t0_;
-#endif
     const int pos_fine = span_apply(pos, y->pos_seen, pos_kinds, y->pos_count, y->pos_start, y->pos_suspect, pos_plan, pos_how);
     const int lit_fine = span_apply(lit, y->lit_seen, lit_kinds, y->lit_count, y->lit_start, y->lit_suspect, lit_plan, lit_how);
     int32_t reach = (int32_t)n;
-#ifdef SQZ_STATS
-    const uint64_t t2_ = __rdtsc(); st_t[1] += t2_ - t1_;
-#endif
     if (!pos_fine || !lit_fine) {
         struct culprits lit_who = { 0, { 0 }, { 0 } }, pos_who = { 0, { 0 }, { 0 } };
         if (!lit_fine) { span_culprits(lit, y->lit_seen, lit_kinds, y->lit_start, y->lit_suspect, lit_how, &lit_who); }
@@ -1003,19 +1003,12 @@ static int32_t count_span(struct sqz* s, struct tally* y, const uint32_t* words,
                 }
             }
         }
-#ifdef SQZ_STATS
-        st_t[3] += __rdtsc() - t2_;
-        st_culprits += lit_who.count + pos_who.count; if (reach < 0) st_toomany++; else if (reach == (int32_t)n) st_okscan++; else { st_cut++; st_cut_at += reach; }
-#endif
         if (reach != (int32_t)n) {
             restore_weights(lit, y->lit_start);
             restore_weights(pos, y->pos_start);
             return reach;
         }
     }
-#ifdef SQZ_STATS
-    st_ok++;
-#endif
     span_done(lit, n, lit_how);
     span_done(pos, matches, pos_how);
     *matches_ += matches;
@@ -1444,11 +1437,6 @@ static uint64_t model_one_by_one(struct pass* p, uint64_t k, uint64_t until) {
 
 /* [k, until) one by one; 1 = go on, 0 = stop (an error, a flaw) */
 static int pass_one_by_one(struct pass* p, uint64_t k, uint64_t until) {
-#ifdef SQZ_STATS
-    st_one += until - k; const uint64_t t0_ = __rdtsc();
-    const int r_ = p->ct != NULL ? (p->matches += code_one_by_one(p->s, p->words, k, until), p->s->error == 0) : model_one_by_one(p, k, until) == until;
-    st_t[2] += __rdtsc() - t0_; return r_;
-#endif
     if (p->ct != NULL) {
         p->matches += code_one_by_one(p->s, p->words, k, until);
         return p->s->error == 0;
@@ -1507,10 +1495,19 @@ static uint64_t pass_block(struct pass* p, uint64_t k, uint64_t until) {
         }
         return model_one_by_one(p, k, k + most) - k;
     }
+    if (p->y->rest > 0) {               /* blocks did not pay a moment ago */
+        if (most > p->y->rest) { most = p->y->rest; }
+        p->y->rest -= (uint32_t)most;
+        if (p->ct != NULL) {
+            p->matches += code_one_by_one(p->s, p->words, k, k + most);
+            return most;
+        }
+        return model_one_by_one(p, k, k + most) - k;
+    }
     const uint32_t n = (uint32_t)most;
     const uint32_t rows = (n + part_tokens - 1) / part_tokens;
     for (uint32_t r = 0; r < rows; r++) { tally_row(p, k, r, 0, n); }
-    uint32_t lo = 0;
+    uint32_t lo = 0, cuts = 0;
     int went = 1;
     while (lo < n && went) {
         const uint32_t row = lo / part_tokens;
@@ -1522,6 +1519,7 @@ static uint64_t pass_block(struct pass* p, uint64_t k, uint64_t until) {
             /* a symbol without a leaf yet, a tree between two lazy stretches, a crowd of culprits: up to
              * the end of the row one by one (that settles the first two as a rule), then the rest again */
             const uint32_t to = (row + 1) * part_tokens < n ? (row + 1) * part_tokens : n;
+            cuts++;
             went = pass_one_by_one(p, k + lo, k + to);
             lo = to;
             if (went) {
@@ -1530,12 +1528,14 @@ static uint64_t pass_block(struct pass* p, uint64_t k, uint64_t until) {
             }
             if (went && lo < n && p->s->lit.lazy < (int32_t)(n - lo)) {
                 for (uint32_t r = 0; r < rows; r++) { tally_row(p, k, r, 0, 0); }
+                if (cuts * cut_every > lo) { p->y->rest = p->y->rest_next = rest_least; }
                 return lo;
             }
         } else {
             /* everything before word `at` as one span (it passes: the words that matter were walked),
              * that word by itself -- it may reorder the tree --, then what is left of the block */
             const uint32_t at = lo + (uint32_t)reach;
+            cuts++;
             if (at - lo >= block_least) {
                 const uint32_t last = (at - 1) / part_tokens;
                 tally_row(p, k, last, lo, at);
@@ -1552,7 +1552,13 @@ static uint64_t pass_block(struct pass* p, uint64_t k, uint64_t until) {
             if (went && lo < n && p->s->lit.lazy < (int32_t)(n - lo)) {
                 /* no stretch long enough for what is left: it is another block's */
                 for (uint32_t r = 0; r < rows; r++) { tally_row(p, k, r, 0, 0); }
+                if (cuts * cut_every > lo) { p->y->rest = p->y->rest_next = rest_least; }
                 return lo;
+            }
+            if (went && lo < n && cuts * cut_every > lo + cut_every) {
+                /* cut after cut: what is left of the block one by one, and no blocks for a while */
+                went = pass_one_by_one(p, k + lo, k + n);
+                lo = n;
             }
             if (lo < n) { tally_row(p, k, lo / part_tokens, lo, n); }
         }
@@ -1560,6 +1566,12 @@ static uint64_t pass_block(struct pass* p, uint64_t k, uint64_t until) {
     for (uint32_t r = 0; r < rows; r++) {
         memset(p->y->lit_part[r], 0, sizeof(p->y->lit_part[r]));
         memset(p->y->pos_part[r], 0, sizeof(p->y->pos_part[r]));
+    }
+    if (cuts * cut_every > n) {
+        p->y->rest_next = p->y->rest_next == 0 ? rest_least : (p->y->rest_next < rest_most ? 2 * p->y->rest_next : rest_most);
+        p->y->rest = p->y->rest_next;
+    } else {
+        p->y->rest_next = 0;
     }
     if (!went && p->flaw) {             /* where the model stopped is what its caller wants to know */
         return p->eyes->k_now - k;
