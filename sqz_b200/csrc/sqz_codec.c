@@ -211,6 +211,7 @@ static void tree_init(struct sqz_tree* t) {
  * (huffman.h:41-62).  Iterative: the order of visits does not matter.       */
 #ifdef SQZ_SELFCHECK
 static _Thread_local uint64_t selfcheck_relabels;    /* how often this thread changed a tree's shape */
+uint64_t sqz_selfcheck_spans, sqz_selfcheck_span_tokens;   /* spans replayed one by one, for the tests to see */
 #endif
 
 static void relabel(struct sqz_tree* t, int32_t top) {
@@ -712,7 +713,7 @@ struct tally {
 };
 
 enum { rest_least = block_most, rest_most = 16 * block_most,
-       cut_every = 512 };               /* tokens per cut below which blocks do not pay */
+       cut_every = block_most / 8 };    /* tokens per cut below which blocks do not pay */
 
 static void tally_init(struct tally* y) {
     memset(y->lit_part, 0, sizeof(y->lit_part));
@@ -1024,6 +1025,8 @@ static int32_t count_span(struct sqz* s, struct tally* y, const uint32_t* words,
         lit->lazy = lit->lazy_start = lit->eager = 0;       /* the top is exact, nothing is decided */
         pos->lazy = pos->lazy_start = pos->eager = 0;
         const uint64_t shape = selfcheck_relabels;
+        __atomic_fetch_add(&sqz_selfcheck_spans, 1, __ATOMIC_RELAXED);
+        __atomic_fetch_add(&sqz_selfcheck_span_tokens, n, __ATOMIC_RELAXED);
         for (uint32_t k = 0; k < n; k++) {
             const uint32_t w = words[k], sym = w & 0x1FF;
             tree_count_as(lit, (int32_t)sym, lit_plan);

@@ -118,6 +118,13 @@ def selfcheck_lib(tmp_path_factory):
 
 
 @pytest.fixture(scope="module")
+def selfcheck_small_blocks_lib(tmp_path_factory):
+    """The self-check build with blocks of 16 x 16 tokens: spans, cuts and the one-by-one rests all happen
+    within a few thousand tokens."""
+    return _codec_variant(tmp_path_factory, "sqzchecksmall", "-DSQZ_SELFCHECK", "-DSQZ_PART_TOKENS=16")
+
+
+@pytest.fixture(scope="module")
 def tiny_log_lib(tmp_path_factory):
     """Built with a 64-entry change log: the two-thread coder's hand-off runs full all the time."""
     return _codec_variant(tmp_path_factory, "sqztinylog", "-DSQZ_LOG_SIZE=64")
@@ -235,6 +242,42 @@ def test_random_streams_keep_the_self_check_quiet(seed, selfcheck_lib, reference
     assert selfcheck_lib.sqz_decompress_buffer(c.ctypes.data_as(_lib.u8p), c.size, out.ctypes.data_as(_lib.u8p),
                                                out.size, C.byref(got)) == 0
     assert out[:nbytes].tobytes() == reference.decompress(ours)
+
+
+@pytest.mark.parametrize("threads", [2, 4])
+def test_model_thread_under_the_self_check(threads, selfcheck_lib, oracle, reference, inputs):
+    """The model thread of the two-thread coder and of a crew in the self-check build: every span it
+    accepts is replayed one by one from the same start (same weights, no reordering), every plan and
+    weight is checked after every one-by-one symbol; bytes against the unmodified reference's encoder."""
+    d = np.concatenate([inputs["confucius.txt"], inputs["x64.elf"][:150000], inputs["mandrill.bmp"][:60000]])
+    t = oracle_tokens(oracle, d, 15)
+    words = sq.symbols_of_tokens(t)
+    assert sq.encode_symbols(words, d.size, 15, threads=threads, lib=selfcheck_lib) == reference.encode_tokens(t, d.size, 15)
+
+
+@pytest.mark.parametrize("threads", [1, 2, 3])
+@pytest.mark.parametrize("case", ["confucius.txt", "x64.elf", "mandrill.bmp", "skewed", "random"])
+def test_spans_replayed_one_by_one(case, threads, selfcheck_small_blocks_lib, oracle, reference, inputs):
+    """Blocks of 256 tokens in the self-check build: thousands of spans are accepted -- by the
+    end-against-start test or by the walk over the culprits' rows --, each is replayed one by one from the
+    same start and has to leave the same weights without a reordering; cuts, full-walk spans and the
+    one-by-one rests in between; the bytes are the reference's."""
+    import ctypes as C
+    L = selfcheck_small_blocks_lib
+    if case == "skewed":
+        t = _skewed(60000, 9)
+        nbytes = int(np.where(t >> 16 != 0, t >> 16, 1).sum())
+    elif case == "random":
+        t, nbytes = _random_stream(np.random.default_rng(77))
+    else:
+        d = inputs[case][:100000]
+        t, nbytes = oracle_tokens(oracle, d, 15), d.size
+    spans = C.c_uint64.in_dll(L, "sqz_selfcheck_spans")
+    before = spans.value
+    got = sq.encode_symbols(sq.symbols_of_tokens(t), nbytes, 15, threads=threads, lib=L)
+    assert got == reference.encode_tokens(t, nbytes, 15)
+    if t.size > 20000:
+        assert spans.value - before > t.size // 2000, (spans.value - before, t.size)
 
 
 @pytest.mark.parametrize("seed", range(30))

@@ -173,6 +173,34 @@ def test_streaming_pipeline_chunk_sizes(chunk, flags, inputs, oracle):
     assert got.size == want.size and (got == want).all()
 
 
+def test_streaming_pipeline_short_start_and_flags(oracle):
+    """SQZ_GPU_STREAM_SHORT_START: explicit chunks of 4 MiB, the first two 1 and 2 MiB (what sqz_compress
+    asks for when it codes with a crew) -- the same symbol words, chunk sizes as described; a flag nobody
+    defined is refused."""
+    import ctypes as C
+    from sqz_b200 import _lib, corpus
+    L = _lib.load()
+    d = corpus.synthetic(11 << 20, 7 << 20)
+    want = sq.symbols_of_tokens(sq.tokens(d))
+    st = C.c_void_p()
+    assert L.sqz_gpu_stream_open(C.byref(st), 0, d.ctypes.data_as(_lib.u8p), d.size, 1 << 15, 3, 257, 32767, 4 << 20, 4) == errno.EINVAL
+    rc = L.sqz_gpu_stream_open(C.byref(st), 0, d.ctypes.data_as(_lib.u8p), d.size, 1 << 15, 3, 257, 32767, 4 << 20, 1 | 2)
+    assert rc == 0, L.sqz_gpu_last_error()
+    got = []
+    while True:
+        p, n = _lib.u32p(), C.c_size_t()
+        rc = L.sqz_gpu_stream_next(st, C.byref(p), C.byref(n))
+        assert rc == 0, L.sqz_gpu_last_error()
+        if n.value == 0:
+            break
+        got.append(np.ctypeslib.as_array(p, shape=(n.value,)).copy())
+    L.sqz_gpu_stream_close(st)
+    assert len(got) == 4                                   # 1 + 2 + 4 + 4 MiB
+    assert got[0].size < got[1].size < got[2].size
+    got = np.concatenate(got)
+    assert got.size == want.size and (got == want).all()
+
+
 def lz77_decode(tokens, n):
     """Independent check of a token stream: plain LZ77 expansion."""
     out = np.zeros(n, np.uint8)
