@@ -2391,6 +2391,13 @@ static inline int32_t window_symbol(struct window* w, struct sqz_tree* t,
     return i;
 }
 
+/* the 57 bits (at least) that follow bit `bit` of a memory source, at the top of the result */
+static inline uint64_t peek_bits(const uint8_t* src, uint64_t bit) {
+    uint64_t be;
+    memcpy(&be, src + (bit >> 3), 8);
+    return __builtin_bswap64(be) << (bit & 7);
+}
+
 /* data != NULL: execute the tokens (squeeze.h:502-551); tokens != NULL: hand them out */
 static void decode_stream(struct sqz* s, struct sqz_bitstream* bs, uint8_t* data, uint64_t bytes,
                           uint32_t* tokens, uint64_t cap, uint64_t* count) {
@@ -2407,6 +2414,92 @@ static void decode_stream(struct sqz* s, struct sqz_bitstream* bs, uint8_t* data
     uint64_t i = 0;
     int err = s->error;
     while (i < bytes && err == 0) {
+        /* Memory sources, away from the end of the stream: tokens of symbols seen before are read
+         * straight from the bytes -- the stream is big-endian words of first-bit-highest bits, so
+         * the next 57 bits are one unaligned load and one shift, and where a token ends is a bit
+         * count, no reader state.  Anything else (an escape, a code that leads nowhere, a token that
+         * does not fit, the last bytes of the stream) is left to the window reader below, token by
+         * token, which reports it the reference's way; nothing of such a token is counted here.   */
+        if (bs->data != NULL && w.dry == 0 && bs->bytes >= 64) {
+            const uint8_t* const src = bs->data;
+            const uint64_t last_start = 8 * (bs->bytes - 24);          /* two 8-byte loads per token at most */
+            uint64_t at = 8 * bs->read - (uint64_t)(w.have + w.pend_bits);
+            const uint64_t at_first = at;
+#define SQZ_PEEK(bit_) peek_bits(src, (bit_))
+            while (i < bytes && at <= last_start) {
+                uint64_t peek = SQZ_PEEK(at);
+                const uint32_t entry = lit->lut[peek >> (64 - lit_lut_bits)];
+                if (entry == no_node) { break; }
+                int32_t node = (int32_t)(entry & ((1u << lut_node_bits) - 1));
+                uint32_t nb = entry >> lut_node_bits;
+                while (node >= lit->n && nb < 48) {                     /* a longer code */
+                    node = (peek << nb) >> 63 ? lit->hi[node] : lit->lo[node];
+                    nb++;
+                    if (node < 0) { break; }
+                }
+                if (node < 0 || node >= lit->n) { break; }
+                if (node <= 0xFF) {                                     /* a literal seen before: the common case */
+                    at += nb;
+                    tree_count_as(lit, node, lit_plan);
+                    SQZ_CHECK(lit);
+                    if (data != NULL) { data[i] = (uint8_t)node; }
+                    if (n_tokens < cap) { tokens[n_tokens] = (uint32_t)node; }
+                    n_tokens++;
+                    i++;
+                    continue;
+                }
+                const int32_t b = node - len_symbol0;
+                if (b < 0 || b >= 28) { break; }                        /* 256, the escape */
+                const uint64_t rest = at + nb;
+                peek = SQZ_PEEK(rest);
+                uint32_t used = len_extra[b];
+                const uint32_t len = len_base[b] + (used > 0 ? reverse_field((uint32_t)(peek >> (64 - used)), used) : 0);
+                if (len > sqz_max_len) { break; }
+                const uint32_t far_entry = pos->lut[(peek << used) >> (64 - pos_lut_bits)];
+                if (far_entry == no_node) { break; }
+                int32_t far = (int32_t)(far_entry & ((1u << lut_node_bits) - 1));
+                used += far_entry >> lut_node_bits;
+                while (far >= pos->n && used < 44) {
+                    far = (peek << used) >> 63 ? pos->hi[far] : pos->lo[far];
+                    used++;
+                    if (far < 0) { break; }
+                }
+                if (far < 0 || far >= 30) { break; }                    /* the escape, no symbol */
+                const uint32_t more = pos_extra[far];
+                const uint32_t dist = pos_base[far] +
+                                      (more > 0 ? reverse_field((uint32_t)((peek << used) >> (64 - more)), more) : 0);
+                used += more;
+                if (dist > 0x7FFF || dist > i || len > bytes - i) { break; }
+                at = rest + used;
+                tree_count_as(lit, node, lit_plan);
+                SQZ_CHECK(lit);
+                tree_count_as(pos, far, pos_plan);
+                SQZ_CHECK(pos);
+                if (data != NULL) {
+                    uint8_t* to = data + i;
+                    const uint8_t* from = to - dist;
+                    if (dist >= len)    { memcpy(to, from, len); }
+                    else if (dist == 1) { memset(to, from[0], len); }
+                    else                { for (uint32_t k = 0; k < len; k++) { to[k] = from[k]; } }
+                }
+                if (n_tokens < cap) { tokens[n_tokens] = len << 16 | dist; }
+                n_tokens++;
+                i += len;
+            }
+#undef SQZ_PEEK
+            if (at != at_first) {                                       /* the window reader goes on from bit `at` */
+                bs->read = 8 * (at / 64);
+                w.acc = w.pend = 0;
+                w.have = w.pend_bits = 0;
+                for (uint32_t skip = (uint32_t)(at % 64); skip > 0; ) {
+                    window_fill(&w);
+                    const int32_t take = skip < 16 ? (int32_t)skip : 16;   /* like every field: window_fill relies on it */
+                    if (!window_skip(&w, take)) { break; }
+                    skip -= (uint32_t)take;
+                }
+            }
+            if (i >= bytes) { break; }
+        }
         int32_t sym = window_symbol(&w, lit, lit_lut_bits, lit_plan);
         if (sym <= 0xFF && sym >= 0) {                              /* a literal seen before: the common case */
             if (data != NULL) { data[i] = (uint8_t)sym; }
