@@ -1,5 +1,6 @@
 """GPU parity beyond whole files: rule sets, shards with halos through the device ABI, the
 chunked streaming pipeline, seam hand-off, and size-independent properties at larger sizes."""
+import errno
 import numpy as np
 import pytest
 
