@@ -909,13 +909,15 @@ static int32_t count_span(struct sqz* s, struct tally* y, const uint32_t* words,
      * ever holds strays (symbols no tree has) */
     enum { lit_quads = sqz_lit_symbols / 4, pos_quads = sqz_pos_symbols / 4 };
     {
-        uint64_t* const ls = (uint64_t*)(void*)y->lit_count;
-        uint64_t* const ps = (uint64_t*)(void*)y->pos_count;
+        /* four counters at a time: a type that may alias the 16-bit ones it is laid over */
+        typedef uint64_t __attribute__((may_alias)) four_counts;
+        four_counts* const ls = (four_counts*)(void*)y->lit_count;
+        four_counts* const ps = (four_counts*)(void*)y->pos_count;
         memcpy(ls, y->lit_part[first], sizeof(y->lit_count));
         memcpy(ps, y->pos_part[first], sizeof(uint16_t) * sqz_pos_symbols);
         for (uint32_t q = first + 1; q < first + parts; q++) {
-            const uint64_t* const lp = (const uint64_t*)(const void*)y->lit_part[q];
-            const uint64_t* const pp = (const uint64_t*)(const void*)y->pos_part[q];
+            const four_counts* const lp = (const four_counts*)(const void*)y->lit_part[q];
+            const four_counts* const pp = (const four_counts*)(const void*)y->pos_part[q];
             for (uint32_t k = 0; k < lit_quads; k++) { ls[k] += lp[k]; }
             for (uint32_t k = 0; k < pos_quads; k++) { ps[k] += pp[k]; }
         }
