@@ -1,6 +1,6 @@
 """A/B of host coder builds on the same tokens, no GPU: every C file given (a copy of sqz_codec.c, with
 optional -D flags after a colon) is built with the GPU entry points stubbed and timed with 1, 2 and 4
-coder threads, best of REPS.
+coder threads and as a decoder, best of REPS.
 
     python tools/bench_coder_variants.py MiB file.c[:-DFLAG...] ...
 """
@@ -33,7 +33,7 @@ for spec in sys.argv[2:]:
     subprocess.check_call(["gcc", "-std=gnu11", "-O2", "-fPIC", "-shared", "-pthread", "-w", *flags.split(), "-I" + os.path.join(ROOT, "include"),
                            src, os.path.join(tmp, "stub.c"), "-o", so])
     L = C.CDLL(so)
-    for fn_name in ("sqz_write_header", "sqz_init", "sqz_encode_tokens", "sqz_encode_symbols"):
+    for fn_name in ("sqz_write_header", "sqz_init", "sqz_encode_tokens", "sqz_encode_symbols", "sqz_decompress_buffer"):
         fn = getattr(L, fn_name)
         fn.restype, fn.argtypes = _lib.SYMBOLS[fn_name]
     libs.append((spec, L))
@@ -49,3 +49,15 @@ for it in range(reps):
             best[(spec, threads)] = min(best.get((spec, threads), 1e9), t)
 for (spec, threads), t in best.items():
     print("%-60s %d thread(s): %.2f ns/token = %.0f MB/s of input" % (spec, threads, t * 1e9 / toks.size, n / 1e6 / t))
+c = np.frombuffer(ref, np.uint8)
+out = np.empty(n, np.uint8)
+for spec, L in libs:
+    t_best = 1e9
+    for it in range(reps):
+        got = C.c_uint64()
+        t0 = time.perf_counter()
+        rc = L.sqz_decompress_buffer(c.ctypes.data_as(_lib.u8p), c.size, out.ctypes.data_as(_lib.u8p), out.size, C.byref(got))
+        t_best = min(t_best, time.perf_counter() - t0)
+        assert rc == 0 and got.value == n
+    assert out.tobytes() == d.tobytes()
+    print("%-60s sqz_decompress: %.2f ns/token = %.0f MB/s of output" % (spec, t_best * 1e9 / toks.size, n / 1e6 / t_best))
