@@ -280,13 +280,21 @@ def decompress_gpu(comp, stats: dict | None = None) -> bytes:
     return out[: n.value].tobytes()
 
 
-def decompress(comp) -> bytes:
-    """squeeze.read_header + squeeze.decompress (host only, never touches the GPU)."""
+def decompress(comp, into=None):
+    """squeeze.read_header + squeeze.decompress (host only, never touches the GPU).  Returns bytes -- or,
+    with `into` (a C-contiguous writable uint8 array of at least the stream's size, the caller's buffer as
+    in the C API), a view of the part of it that was written, without a copy."""
     L = _lib.load()
     c = _u8(comp)
     n, _ = read_header(c)
-    out = np.empty(max(n, 1), dtype=np.uint8)
+    if into is not None:
+        if not (isinstance(into, np.ndarray) and into.dtype == np.uint8 and into.flags.c_contiguous and
+                into.flags.writeable and into.size >= max(n, 1)):
+            raise ValueError("into: a writable C-contiguous uint8 array of at least read_header(comp)[0] bytes")
+        out = into
+    else:
+        out = np.empty(max(n, 1), dtype=np.uint8)
     got = C.c_uint64()
     rc = L.sqz_decompress_buffer(c.ctypes.data_as(u8p), c.size, out.ctypes.data_as(u8p), out.size, C.byref(got))
     _check(rc, "sqz_decompress")
-    return out[: got.value].tobytes()
+    return out[: got.value].tobytes() if into is None else out[: got.value]

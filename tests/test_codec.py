@@ -363,6 +363,16 @@ def test_coders_agree_on_a_long_stream(oracle, reference):
         assert sq.encode_symbols(words, d.size, 15, threads=threads) == want, threads
 
 
+def test_decompress_into_the_callers_buffer(oracle, inputs):
+    d = inputs["confucius.txt"]
+    comp = sq.encode_tokens(oracle_tokens(oracle, d, 15), d.size, 15)
+    buf = np.zeros(d.size + 100, np.uint8)
+    out = sq.decompress(comp, into=buf)
+    assert np.shares_memory(out, buf) and out.size == d.size and (out == d).all()
+    with pytest.raises(ValueError):
+        sq.decompress(comp, into=np.zeros(d.size - 1, np.uint8))
+
+
 def test_header_bytes():
     """LSB-first fields in an MSB-first register, big-endian words."""
     c = sq.encode_tokens(np.zeros(0, np.uint32), 4096, 15)
